@@ -1,0 +1,45 @@
+"""pytest configuration: the `gpu` marker and shared fixtures (golden vectors, oracle import)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with `-m gpu` under gpurun)")
+
+
+def _seeded(seed, shape, scale=1.0):
+    return np.random.default_rng(seed).standard_normal(shape, dtype=np.float32) * np.float32(scale)
+
+
+# name -> how to rebuild inputs that were too large to commit (oracle/make_golden.py case (v))
+REGENERATED = {
+    "randn_k8192_d256": lambda: (_seeded(7, (2, 256, 320)), _seeded(8, (8192, 256))),
+}
+GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz")) if os.path.isdir(GOLDEN_DIR) else []
+
+
+def load_golden(name):
+    import hashlib
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    if "z" not in g:
+        z, cb = REGENERATED[name]()
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        assert sha(z) == str(g["z_sha"]) and sha(cb) == str(g["codebook_sha"]), \
+            "numpy generator drift: regenerated inputs do not match the fixture's sha256"
+        g["z"], g["codebook"] = z, cb
+    return g
+
+
+@pytest.fixture(params=GOLDEN_CASES)
+def golden(request):
+    g = load_golden(request.param)
+    g["name"] = request.param
+    return g

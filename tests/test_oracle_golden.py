@@ -1,0 +1,86 @@
+"""Pin the numpy oracle (oracle/vq_oracle.py) against outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by oracle/make_golden.py from
+/root/reference/src/model/components/vector_quantizer.py).  CPU only."""
+import numpy as np
+
+from oracle import vq_oracle as O
+
+LOSS_RTOL = 1e-5
+DX_RTOL, DE_RTOL = 1e-5, 1e-4
+
+
+def check_indices(got, g, fwd):
+    """The index parity rule: equal wherever the reference's own fp32 top-2 margin
+    exceeds eps_n; on near-ties the chosen code must be within eps_n of the minimum distance."""
+    ref = g["indices"].astype(np.int64)
+    clear = g["margin"] > fwd.eps
+    assert np.array_equal(got[clear], ref[clear]), f"{(got[clear] != ref[clear]).sum()} mismatches on clear-margin frames"
+    bad = np.nonzero(got != ref)[0]
+    if bad.size:
+        rows = O.bcw_to_rows(g["z"])[bad]
+        d = O.distances(rows, g["codebook"])
+        chosen = d[np.arange(bad.size), got[bad]]
+        assert np.all(chosen - d.min(axis=1) <= fwd.eps[bad])
+    return int(bad.size)
+
+
+def test_forward_matches_reference(golden):
+    g = golden
+    fwd = O.vq_forward(g["z"], g["codebook"], float(g["beta"]))
+    n_bad = check_indices(fwd.indices, g, fwd)
+    np.testing.assert_allclose(fwd.embedding_loss, g["embedding_loss"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(fwd.commitment_loss, g["commitment_loss"], rtol=LOSS_RTOL)
+    if n_bad == 0:
+        np.testing.assert_allclose(fwd.perplexity, g["perplexity"], rtol=LOSS_RTOL)
+        if "quantized" in g:
+            assert np.array_equal(fwd.quantized, g["quantized"]), "straight-through value must be bit-equal"
+    assert list(g["requires_grad"]) == [True, True, True, False, False, False]
+
+
+def test_backward_and_adam_match_reference(golden):
+    g = golden
+    idx = g["indices"].astype(np.int64)
+    dX, dE = O.vq_backward(g["z"], g["codebook"], idx, float(g["beta"]), 1.0, 1.0, g["Gq"])
+    np.testing.assert_allclose(dX, g["dX"], rtol=DX_RTOL, atol=1e-7 * np.abs(g["dX"]).max())
+    if "dE" in g:
+        np.testing.assert_allclose(dE, g["dE"], rtol=DE_RTOL, atol=1e-6 * np.abs(g["dE"]).max())
+        after = O.adam_step(g["codebook"], g["dE"])
+        np.testing.assert_allclose(after, g["codebook_after_adam"], rtol=1e-5, atol=2e-7)
+        untouched = np.bincount(idx, minlength=int(g["K"])) == 0
+        assert np.array_equal(g["codebook_after_adam"][untouched], g["codebook"][untouched])
+        assert np.all(dE[untouched] == 0)
+    else:
+        sel = g["sel_codes"]
+        np.testing.assert_allclose(dE[sel], g["dE_sel"], rtol=DE_RTOL, atol=1e-6 * np.abs(g["dE_sel"]).max())
+        rest = np.ones(int(g["K"]), bool); rest[sel] = False
+        assert np.all(dE[rest] == 0)
+
+
+def test_stats_roundtrip(golden):
+    """[counts | residual sums | SSE | N] is sufficient for losses, perplexity and dE."""
+    g = golden
+    idx = g["indices"].astype(np.int64)
+    K, D = int(g["K"]), int(g["D"])
+    stats = O.shard_stats(g["z"], g["codebook"], idx)
+    mse, com, ppl, dE = O.finalize_from_stats(stats, K, D, float(g["beta"]))
+    np.testing.assert_allclose(mse, g["embedding_loss"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(com, g["commitment_loss"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(ppl, g["perplexity"], rtol=LOSS_RTOL)
+    _, dE_ref = O.vq_backward(g["z"], g["codebook"], idx, float(g["beta"]), 1.0, 0.0, None)
+    np.testing.assert_allclose(dE, dE_ref, rtol=1e-6, atol=1e-12)
+
+
+def test_argmin_semantics():
+    """torch.argmin semantics the reference inherits."""
+    d = np.array([[3, np.nan, 1, 1], [2, 2, 5, 2], [np.inf] * 4, [np.nan, 0, np.nan, 0]], dtype=np.float32)
+    assert O.argmin_first(d).tolist() == [1, 0, 0, 0]
+
+
+def test_window_export_matches_bert_windowing():
+    """bert.py:50-69: 11000 tokens -> 22 windows of 512, last one holds 248 tokens + zero padding, mask 0 there."""
+    idx = np.arange(2 * 11000) % 512
+    tok, mask = O.window_indices(idx, batch=2)
+    assert tok.shape == (2, 22, 512) and mask.shape == (2, 22, 512)
+    assert mask[:, :21].all() and mask[:, 21, :248].all() and not mask[:, 21, 248:].any()
+    assert np.array_equal(tok.reshape(2, -1)[:, :11000], idx.reshape(2, 11000))
+    assert (tok[:, 21, 248:] == 0).all()
