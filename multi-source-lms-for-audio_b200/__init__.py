@@ -1,0 +1,10 @@
+"""vq-b200: the VQ-VAE vector-quantiser bottleneck of deborahdore/multi-source-lms-for-audio, rebuilt for B200.
+
+Only the hot path lives here: `csrc/` (CUDA kernels + C ABI -> libvqb_b200.so), the ctypes binding, the
+`VectorQuantizer` drop-in and the small host-side helpers either side of it.
+"""
+from ._lib import LIB_PATH, VqbError
+from .quantizer import VectorQuantizer
+from . import functional, distributed
+
+__all__ = ["VectorQuantizer", "functional", "distributed", "LIB_PATH", "VqbError"]

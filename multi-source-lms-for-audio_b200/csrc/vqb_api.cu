@@ -1,0 +1,260 @@
+// C ABI of libvqb_b200.so (see include/vqb.h).  Argument checking, workspace carving and the launch sequence of
+// the forward / backward of the VQ bottleneck.  No host synchronisation, no hidden streams, no CPU fallback.
+#include "vqb_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace vqb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+WsLayout ws_layout(int64_t N, int K, int D, int flags) {
+    WsLayout L{};
+    const int prec = flags & VQB_PREC_MASK;
+    L.k_pad = (K + kTileCodes - 1) / kTileCodes * kTileCodes;
+    L.n_pad = (N + kTileRows - 1) / kTileRows * kTileRows;
+    L.n_partials = kTailGridMax;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    L.meta = take(sizeof(WsMeta));
+    L.e2 = take((size_t)L.k_pad * 4);
+    L.counts = take((size_t)K * 4);
+    L.sse_partials = take((size_t)L.n_partials * 8);
+    if (prec == VQB_PREC_FP32) {
+        L.idx32 = take((size_t)N * 4);
+        L.cand_cnt = L.cand_idx = L.fallback_rows = L.x2 = L.eb = L.xb = 0;
+    } else {
+        L.idx32 = 0;
+        L.cand_cnt = take((size_t)L.n_pad);
+        L.cand_idx = take((size_t)L.n_pad * kCandMax * 2);
+        L.fallback_rows = take((size_t)L.n_pad * 4);
+        L.x2 = take((size_t)L.n_pad * 4);
+        L.eb = take((size_t)L.k_pad * D * 2);
+        L.xb = take((size_t)L.n_pad * D * 2);
+    }
+    L.total = off;
+    return L;
+}
+
+static int check_device() {
+    static thread_local int ok_device = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev == ok_device) return 0;
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    if (major != 10) {
+        set_error("device %d has compute capability %d.x; libvqb_b200 only runs on sm_100 (B200) and has no fallback", dev, major);
+        return VQB_E_DEVICE;
+    }
+    ok_device = dev;
+    return 0;
+}
+
+static int check_shape(int B, int D, int64_t W, int K) {
+    if (B < 1 || W < 1 || K < 1 || K > 65536 || D < 16 || D > 512 || (D % 16) != 0) {
+        set_error("unsupported shape B=%d D=%d W=%lld K=%d (need 1<=K<=65536, 16<=D<=512, D%%16==0)", B, D, (long long)W, K);
+        return VQB_E_SHAPE;
+    }
+    if ((int64_t)B * W >= (1LL << 31) - kTileRows) {
+        set_error("N = B*W = %lld does not fit the 31-bit frame index; split the batch", (long long)((int64_t)B * W));
+        return VQB_E_SHAPE;
+    }
+    return 0;
+}
+
+#define VQB_CUDA(call, what)                                   \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what);   \
+    } while (0)
+
+// accumulate: keep counts / resid / SSE / N from earlier chunks (used by the host-buffer path)
+int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W, int K, int flags, int64_t* idx_out,
+                 float* q_out, float* stats_out, void* workspace, size_t ws_bytes, cudaStream_t s, bool accumulate,
+                 float* scores_dbg) {
+    int rc;
+    if ((rc = check_device()) != 0) return rc;
+    if (!z || !codebook || !workspace || (!scores_dbg && (!idx_out || !stats_out))) {
+        set_error("vqb_forward: NULL pointer argument");
+        return VQB_E_NULL;
+    }
+    if ((rc = check_shape(B, D, W, K)) != 0) return rc;
+    const int prec = flags & VQB_PREC_MASK;
+    if (prec != VQB_PREC_FP32 && prec != VQB_PREC_BF16) {
+        set_error("vqb_forward: precision %d is not built in this version (use VQB_PREC_FP32 or VQB_PREC_BF16)", prec);
+        return VQB_E_FLAGS;
+    }
+    if ((flags & VQB_WANT_Q) && !q_out) {
+        set_error("vqb_forward: VQB_WANT_Q set but q_bcw_out is NULL");
+        return VQB_E_NULL;
+    }
+    if (((uintptr_t)z | (uintptr_t)codebook | (uintptr_t)workspace) & 15) {
+        set_error("vqb_forward: z, codebook and workspace must be 16-byte aligned");
+        return VQB_E_ALIGN;
+    }
+    const int64_t N = (int64_t)B * W;
+    const WsLayout L = ws_layout(N, K, D, flags);
+    if (ws_bytes < L.total) {
+        set_error("vqb_forward: workspace has %zu bytes, %zu needed", ws_bytes, L.total);
+        return VQB_E_WORKSPACE;
+    }
+    char* ws = static_cast<char*>(workspace);
+    WsMeta* meta = reinterpret_cast<WsMeta*>(ws + L.meta);
+    float* e2 = reinterpret_cast<float*>(ws + L.e2);
+    int* counts = reinterpret_cast<int*>(ws + L.counts);
+    float* part = reinterpret_cast<float*>(ws + L.sse_partials);
+    float* resid = (flags & VQB_WANT_RESID) ? stats_out + K : nullptr;
+
+    if (!accumulate) {
+        VQB_CUDA(cudaMemsetAsync(meta, 0, sizeof(WsMeta), s), "memset meta");
+        VQB_CUDA(cudaMemsetAsync(counts, 0, (size_t)K * 4, s), "memset counts");
+        if (resid) VQB_CUDA(cudaMemsetAsync(resid, 0, (size_t)K * D * 4, s), "memset resid");
+    } else {
+        VQB_CUDA(cudaMemsetAsync(&meta->fallback_count, 0, sizeof(int), s), "memset fallback_count");
+    }
+
+    if (prec == VQB_PREC_FP32) {
+        int* idx32 = reinterpret_cast<int*>(ws + L.idx32);
+        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, nullptr, meta, s), "codebook_prep");
+        VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, nullptr, nullptr, idx32, nullptr, nullptr, s), "exact_search");
+        VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, idx32, nullptr, nullptr, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
+                             counts, resid, part, L.n_partials, meta, s), "tail");
+    } else {
+        uint8_t* cand_cnt = reinterpret_cast<uint8_t*>(ws + L.cand_cnt);
+        uint16_t* cand_idx = reinterpret_cast<uint16_t*>(ws + L.cand_idx);
+        int* fb_rows = reinterpret_cast<int*>(ws + L.fallback_rows);
+        float* x2 = reinterpret_cast<float*>(ws + L.x2);
+        __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(ws + L.eb);
+        __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + L.xb);
+        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, eb, meta, s), "codebook_prep");
+        VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");
+        rc = launch_tc_search(xb, eb, e2, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, scores_dbg, s);
+        if (rc != 0) return rc;
+        if (scores_dbg) return 0;
+        VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, fb_rows, &meta->fallback_count, nullptr, cand_cnt, cand_idx, s),
+                 "exact_search(fallback)");
+        VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, nullptr, cand_cnt, cand_idx, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
+                             counts, resid, part, L.n_partials, meta, s), "tail");
+    }
+    VQB_CUDA(launch_pack_stats(counts, part, L.n_partials, N, K, D, stats_out, accumulate, s), "pack_stats");
+    return 0;
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" {
+
+int vqb_version(void) { return VQB_VERSION; }
+const char* vqb_last_error(void) { return g_err; }
+
+int vqb_workspace_bytes(int64_t N, int K, int D, int flags, size_t* bytes_out) {
+    if (!bytes_out) { set_error("vqb_workspace_bytes: NULL output"); return VQB_E_NULL; }
+    if (N < 1 || K < 1 || K > 65536 || D < 16 || D > 512 || D % 16) {
+        set_error("vqb_workspace_bytes: unsupported N=%lld K=%d D=%d", (long long)N, K, D);
+        return VQB_E_SHAPE;
+    }
+    const int prec = flags & VQB_PREC_MASK;
+    if (prec != VQB_PREC_FP32 && prec != VQB_PREC_BF16) { set_error("vqb_workspace_bytes: unknown precision %d", prec); return VQB_E_FLAGS; }
+    *bytes_out = ws_layout(N, K, D, flags).total;
+    return 0;
+}
+
+int vqb_forward(const float* z_bcw, const float* codebook, int B, int D, int64_t W, int K, int flags, int64_t* idx_out,
+                float* q_bcw_out, float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return forward_impl(z_bcw, codebook, B, D, W, K, flags, idx_out, q_bcw_out, stats_out, workspace, workspace_bytes,
+                        static_cast<cudaStream_t>(stream), false, nullptr);
+}
+
+int vqb_finalize(const float* stats, int K, int D, float beta, float* losses_out, void* stream) {
+    int rc;
+    if ((rc = check_device()) != 0) return rc;
+    if (!stats || !losses_out) { set_error("vqb_finalize: NULL pointer argument"); return VQB_E_NULL; }
+    if (K < 1 || D < 1) { set_error("vqb_finalize: bad K/D"); return VQB_E_SHAPE; }
+    VQB_CUDA(launch_finalize(stats, K, D, beta, losses_out, static_cast<cudaStream_t>(stream)), "finalize");
+    return 0;
+}
+
+int vqb_backward(const float* z_bcw, const float* codebook, const int64_t* idx, const float* stats, const float* Gq_bcw,
+                 const float* g_e_dev, const float* g_c_dev, float beta, int B, int D, int64_t W, int K, float* dX_bcw,
+                 float* dE, void* stream) {
+    int rc;
+    if ((rc = check_device()) != 0) return rc;
+    if ((rc = check_shape(B, D, W, K)) != 0) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dX_bcw) {
+        if (!z_bcw || !codebook || !idx) { set_error("vqb_backward: dX needs z, codebook and idx"); return VQB_E_NULL; }
+        VQB_CUDA(launch_backward_dx(z_bcw, codebook, idx, Gq_bcw, g_c_dev, beta, B, D, W, K, dX_bcw, s), "backward_dx");
+    }
+    if (dE) {
+        if (!stats) { set_error("vqb_backward: dE needs stats"); return VQB_E_NULL; }
+        VQB_CUDA(launch_backward_de(stats, g_e_dev, K, D, dE, s), "backward_de");
+    }
+    return 0;
+}
+
+int vqb_onehot(const int64_t* idx, int64_t N, int K, float* encodings_out, void* stream) {
+    int rc;
+    if ((rc = check_device()) != 0) return rc;
+    if (!idx || !encodings_out) { set_error("vqb_onehot: NULL pointer argument"); return VQB_E_NULL; }
+    if (N < 1 || K < 1) { set_error("vqb_onehot: bad N/K"); return VQB_E_SHAPE; }
+    VQB_CUDA(launch_onehot(idx, N, K, encodings_out, static_cast<cudaStream_t>(stream)), "onehot");
+    return 0;
+}
+
+int vqb_gather(const float* codebook, const int64_t* idx, int B, int D, int64_t W, int K, float* out_bcw, void* stream) {
+    int rc;
+    if ((rc = check_device()) != 0) return rc;
+    if (!codebook || !idx || !out_bcw) { set_error("vqb_gather: NULL pointer argument"); return VQB_E_NULL; }
+    if ((rc = check_shape(B, D, W, K)) != 0) return rc;
+    VQB_CUDA(launch_gather(codebook, idx, B, D, W, K, out_bcw, static_cast<cudaStream_t>(stream)), "gather");
+    return 0;
+}
+
+int vqb_window_indices(const int64_t* idx, int B, int64_t L, int window, int64_t pad_id, int64_t* tokens_out, float* mask_out,
+                       void* stream) {
+    int rc;
+    if ((rc = check_device()) != 0) return rc;
+    if (!idx || !tokens_out || !mask_out) { set_error("vqb_window_indices: NULL pointer argument"); return VQB_E_NULL; }
+    if (B < 1 || L < 1 || window < 1) { set_error("vqb_window_indices: bad B/L/window"); return VQB_E_SHAPE; }
+    VQB_CUDA(launch_window(idx, B, L, window, pad_id, tokens_out, mask_out, static_cast<cudaStream_t>(stream)), "window");
+    return 0;
+}
+
+int vqb_debug_counters(const void* workspace, int64_t* counters_out_host) {
+    if (!workspace || !counters_out_host) { set_error("vqb_debug_counters: NULL pointer argument"); return VQB_E_NULL; }
+    WsMeta m;
+    VQB_CUDA(cudaMemcpy(&m, workspace, sizeof(WsMeta), cudaMemcpyDeviceToHost), "memcpy meta");
+    counters_out_host[0] = (int64_t)m.rescored;
+    counters_out_host[1] = (int64_t)m.fallback_total;
+    counters_out_host[2] = (int64_t)m.shortlisted;
+    return 0;
+}
+
+int vqb_debug_tc_scores(const float* z_bcw, const float* codebook, int B, int D, int64_t W, int K, int flags, float* scores_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!scores_out) { set_error("vqb_debug_tc_scores: NULL output"); return VQB_E_NULL; }
+    return forward_impl(z_bcw, codebook, B, D, W, K, (flags & ~VQB_PREC_MASK) | VQB_PREC_BF16, nullptr, nullptr, nullptr, workspace,
+                        workspace_bytes, static_cast<cudaStream_t>(stream), false, scores_out);
+}
+
+}  // extern "C"

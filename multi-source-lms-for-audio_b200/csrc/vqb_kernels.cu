@@ -1,0 +1,635 @@
+// CUDA-core kernels of the VQ bottleneck for sm_100a: codebook / latent preparation, the exact fp32 search
+// (parity anchor + fallback of the tensor-core shortlist), the fused tail (fp32 rescoring in the reference's op
+// order, codeword gather, SSE, straight-through value, per-code statistics) and the backward kernels.
+//
+// Reference semantics restated here (never copied): src/model/components/vector_quantizer.py:25-52.
+// All of these are HBM-bound: they read latents straight from the reference's [B, D, W] layout with frame-contiguous
+// (coalesced) accesses, transpose through padded shared memory, and touch every latent byte once per kernel.
+#include "vqb_internal.h"
+
+#include <math.h>
+
+namespace vqb {
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ float ld_stream(const float* p) {   // read-once data: keep it out of L1
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// torch.argmin ordering (vector_quantizer.py:37): NaN beats everything, otherwise smaller distance, ties -> lower index.
+__device__ __forceinline__ bool better(float d, int i, float bd, int bi) {
+    if (bi < 0) return true;
+    const bool dn = isnan(d), bn = isnan(bd);
+    if (dn) return !bn || i < bi;
+    if (bn) return false;
+    return d < bd || (d == bd && i < bi);
+}
+// The reference's distance in its association order (vector_quantizer.py:32-33):
+//   fl(|x|^2 + fl(|e|^2 - fl(2 * dot)));  2*dot is exact, so fma(-2, dot, e2) is the same single rounding.
+__device__ __forceinline__ float ref_distance(float x2, float e2, float dot) {
+    return __fadd_rn(x2, __fmaf_rn(-2.0f, dot, e2));
+}
+
+// ------------------------------------------------------------------------------------------------ codebook prep
+// One warp per code: |e_k|^2 in fp32 (vector_quantizer.py:33), bf16 copy for the tensor-core tiles, max |e|^2 for the
+// guard band, non-finite flag.  Rows K..K_pad-1 get e2 = +inf (never shortlisted) and zero operands.
+__global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restrict__ E, int K, int K_pad, int D,
+                                                            float* __restrict__ e2, __nv_bfloat16* __restrict__ eb,
+                                                            WsMeta* meta) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= K_pad) return;
+    float s = 0.f, st = 0.f, sd = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float v = (k < K) ? E[(size_t)k * D + d] : 0.f;
+        s = __fadd_rn(s, __fmul_rn(v, v));
+        if (eb) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const float vt = __bfloat162float(h), dv = v - vt;
+            st = fmaf(vt, vt, st);
+            sd = fmaf(dv, dv, sd);
+            eb[(size_t)k * D + d] = h;
+        }
+    }
+    s = warp_sum(s);
+    st = warp_sum(st);
+    sd = warp_sum(sd);
+    if (lane == 0) {
+        if (k < K) {
+            e2[k] = s;
+            if (!isfinite(s)) atomicExch(&meta->cb_nonfinite, 1);
+            else {
+                atomicMax(&meta->emax2_bits, __float_as_uint(s));
+                if (eb) {
+                    atomicMax(&meta->etmax2_bits, __float_as_uint(st));
+                    atomicMax(&meta->demax2_bits, __float_as_uint(sd));
+                }
+            }
+        } else {
+            e2[k] = INFINITY;
+        }
+    }
+}
+
+cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb, WsMeta* meta,
+                                 cudaStream_t s) {
+    codebook_prep_kernel<<<(K_pad + 7) / 8, 256, 0, s>>>(codebook, K, K_pad, D, e2, eb, meta);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ latent prep (bf16)
+// z [B, D, W] fp32 -> xb [N_pad, D] bf16 (frame-major = K-major A operand for tcgen05) and the per-frame guard band.
+// One block = 32 frames x all D, transposed through shared memory so both the read and the write are coalesced.
+//
+// Guard band (DESIGN.md "shortlist exactness"): with xt = bf16(x) = x + dx and et = bf16(e) = e + de,
+//   xt.et - x.e = dx.et + x.de,  so  |score_bf16(k) - score(k)| <= 2 (|dx| |et_k| + |x| |de_k|) + accumulation error.
+// Two codes are compared, hence the factor 4; the last term bounds fp32 accumulation in the tensor core and in the
+// reference's own sgemm.  |dx|, |x| are measured per frame here; max|et|, max|de|, max|e| come from codebook_prep.
+__global__ void __launch_bounds__(256) latent_prep_bf16_kernel(const float* __restrict__ z, int D, int64_t W, int64_t N,
+                                                               int64_t N_pad, __nv_bfloat16* __restrict__ xb,
+                                                               float* __restrict__ band, const WsMeta* __restrict__ meta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int stride = D + 2;                                         // bf16 elements; (D+2)/2 words is odd -> no conflicts
+    __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [32][D+2]
+    float* part = reinterpret_cast<float*>(Xs + 32 * stride);         // [2][8][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * 32 + lane;
+    const bool valid = n < N;
+    int64_t b = 0, w = 0;
+    if (valid) { b = n / W; w = n - b * W; }
+    const float* zp = z + (size_t)b * D * W + w;
+    float s = 0.f, sd = 0.f;
+    for (int d = warp; d < D; d += 8) {
+        const float v = valid ? ld_stream(zp + (size_t)d * W) : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const float dv = v - __bfloat162float(h);
+        s = fmaf(v, v, s);
+        sd = fmaf(dv, dv, sd);
+        Xs[lane * stride + d] = h;
+    }
+    part[warp * 32 + lane] = s;
+    part[256 + warp * 32 + lane] = sd;
+    __syncthreads();
+    if (warp == 0 && valid) {
+        float t = 0.f, td = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { t += part[i * 32 + lane]; td += part[256 + i * 32 + lane]; }
+        const float xn = sqrtf(t) * 1.0001f, dxn = sqrtf(td) * 1.0001f;
+        const float etmax = sqrtf(__uint_as_float(meta->etmax2_bits)) * 1.0001f;
+        const float demax = sqrtf(__uint_as_float(meta->demax2_bits)) * 1.0001f;
+        const float emax = sqrtf(__uint_as_float(meta->emax2_bits)) * 1.0001f;
+        band[n] = 4.0f * (dxn * etmax + xn * demax) * 1.001f + 8.0f * (float)D * 2.3841858e-07f * xn * emax + 1e-30f;
+    }
+    const uint32_t* Xw = reinterpret_cast<const uint32_t*>(Xs);
+    const int wstride = stride / 2;
+    for (int f = warp; f < 32; f += 8) {
+        const int64_t nf = (int64_t)blockIdx.x * 32 + f;
+        if (nf >= N_pad) break;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(xb + (size_t)nf * D);
+        for (int c = lane; c < D / 2; c += 32) dst[c] = Xw[f * wstride + c];
+    }
+}
+
+cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int64_t N_pad, __nv_bfloat16* xb, float* band,
+                                    const WsMeta* meta, cudaStream_t s) {
+    const int64_t N = (int64_t)B * W;
+    const size_t smem = (size_t)32 * (D + 2) * 2 + 2 * 8 * 32 * 4;
+    latent_prep_bf16_kernel<<<(unsigned)((N_pad + 31) / 32), 256, smem, s>>>(z, D, W, N, N_pad, xb, band, meta);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ exact fp32 search
+// Nearest code per frame with every distance evaluated in fp32 in the reference's association order.
+// Block = 64 frames (resident in shared memory) x all K codes in tiles of 64, 4x4 register micro-tiles.
+constexpr int XT_M = 64, XT_N = 64, XT_K = 16, XT_LD = XT_N + 4;
+
+__global__ void __launch_bounds__(256) exact_search_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                           const float* __restrict__ e2, int D, int64_t W, int64_t N, int K,
+                                                           const int* __restrict__ rows, const int* __restrict__ row_count,
+                                                           int* __restrict__ idx32, uint8_t* __restrict__ cand_cnt,
+                                                           uint16_t* __restrict__ cand_idx) {
+    extern __shared__ __align__(16) float smem_f[];
+    float* Xs = smem_f;                                   // [D][64]   x tile, d-major
+    float* Es = Xs + (size_t)D * XT_M;                    // [16][68]  codebook chunk, d-major
+    float* x2s = Es + XT_K * XT_LD;                       // [64]
+    int* rown = reinterpret_cast<int*>(x2s + XT_M);       // [64] frame id or -1
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t total = rows ? (int64_t)*row_count : N;
+
+    for (int64_t tile = blockIdx.x; tile * XT_M < total; tile += gridDim.x) {
+        __syncthreads();
+        if (tid < XT_M) {
+            const int64_t r = tile * XT_M + tid;
+            rown[tid] = (r < total) ? (rows ? rows[r] : (int)r) : -1;
+        }
+        __syncthreads();
+        {
+            const int r = tid & 63;
+            const int n = rown[r];
+            int64_t b = 0, w = 0;
+            if (n >= 0) { b = n / W; w = n - b * W; }
+            const float* zp = z + (size_t)b * D * W + w;
+            for (int d = tid >> 6; d < D; d += 4) Xs[d * XT_M + r] = (n >= 0) ? zp[(size_t)d * W] : 0.f;
+        }
+        __syncthreads();
+        if (tid < XT_M) {   // |x|^2 = sum of rounded squares (vector_quantizer.py:32)
+            float s = 0.f;
+            for (int d = 0; d < D; ++d) { const float v = Xs[d * XT_M + tid]; s = __fadd_rn(s, __fmul_rn(v, v)); }
+            x2s[tid] = s;
+        }
+        float bd[4];
+        int bi[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { bd[i] = 0.f; bi[i] = -1; }
+
+        for (int k0 = 0; k0 < K; k0 += XT_N) {
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int d0 = 0; d0 < D; d0 += XT_K) {
+                __syncthreads();
+                {
+                    const int dd = tid & 15;
+                    for (int kk = tid >> 4; kk < XT_N; kk += 16) {
+                        const int k = k0 + kk;
+                        Es[dd * XT_LD + kk] = (k < K) ? E[(size_t)k * D + d0 + dd] : 0.f;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int dd = 0; dd < XT_K; ++dd) {
+                    const float4 a = *reinterpret_cast<const float4*>(&Xs[(d0 + dd) * XT_M + ty * 4]);
+                    const float4 c = *reinterpret_cast<const float4*>(&Es[dd * XT_LD + tx * 4]);
+                    const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], cv[j], acc[i][j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + tx * 4 + j;
+                if (k < K) {
+                    const float ek = e2[k];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float dist = ref_distance(x2s[ty * 4 + i], ek, acc[i][j]);
+                        if (better(dist, k, bd[i], bi[i])) { bd[i] = dist; bi[i] = k; }
+                    }
+                }
+            }
+        }
+        // combine the 16 threads (tx) that share a frame: lanes differ in their low 4 bits
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd[i], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi[i], o);
+                if (oi >= 0 && better(od, oi, bd[i], bi[i])) { bd[i] = od; bi[i] = oi; }
+            }
+            if (tx == 0) {
+                const int n = rown[ty * 4 + i];
+                if (n >= 0) {
+                    if (rows) { cand_cnt[n] = 1; cand_idx[(size_t)n * kCandMax] = (uint16_t)bi[i]; }
+                    else idx32[n] = bi[i];
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_exact_search(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
+                                const int* rows, const int* row_count, int* idx32, uint8_t* cand_cnt, uint16_t* cand_idx,
+                                cudaStream_t s) {
+    const int64_t N = (int64_t)B * W;
+    const size_t smem = ((size_t)D * XT_M + XT_K * XT_LD + XT_M) * 4 + XT_M * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(exact_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int64_t tiles = (N + XT_M - 1) / XT_M;
+    const int per_sm = (int)(220 * 1024 / (smem + 1024)) > 0 ? (int)(220 * 1024 / (smem + 1024)) : 1;
+    int64_t grid = 148LL * (per_sm > 4 ? 4 : per_sm);
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    exact_search_kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, rows, row_count, idx32, cand_cnt,
+                                                          cand_idx);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ fused tail
+// Per frame: (a) settle the index - either given (exact search) or by rescoring the shortlist in fp32 in the reference's
+// op order, ties -> lowest index; (b) gather the codeword (vector_quantizer.py:42 as a gather), (c) SSE for both MSE
+// losses (:45-46), (d) straight-through value fl(x + fl(q - x)) written back in BCW (:48,:52), (e) code histogram (:49)
+// and, for training, the per-code residual sums that give the codebook gradient.  Latents are read exactly once.
+constexpr int TL_F = 32;              // frames per tile
+constexpr int TL_LD = TL_F + 1;       // padded: column (fixed d) and row (fixed frame) accesses are both conflict-free
+constexpr int TL_J = 16;              // D <= 512 -> at most 16 elements per lane
+
+template <bool kResid>
+__global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                   const float* __restrict__ e2, int D, int64_t W, int64_t N,
+                                                   const int* __restrict__ idx32, const uint8_t* __restrict__ cand_cnt,
+                                                   const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
+                                                   float* __restrict__ q_out, int* __restrict__ counts,
+                                                   float* __restrict__ resid, double* __restrict__ sse_partials,
+                                                   WsMeta* meta) {
+    extern __shared__ __align__(16) float Xs[];   // [D][33]
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float sse = 0.f, sse_c = 0.f;                 // Kahan-compensated per-thread SSE
+    unsigned int n_resc = 0, n_short = 0;
+
+    for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x) {
+        const int64_t nl = tile * TL_F + lane;
+        const bool valid = nl < N;
+        int64_t b = 0, w = 0;
+        if (valid) { b = nl / W; w = nl - b * W; }
+        const size_t col = (size_t)b * D * W + w;
+        __syncthreads();
+        for (int d = warp; d < D; d += 8) Xs[d * TL_LD + lane] = valid ? ld_stream(z + col + (size_t)d * W) : 0.f;
+        __syncthreads();
+#pragma unroll 1
+        for (int fi = 0; fi < TL_F / 8; ++fi) {
+            const int f = warp * (TL_F / 8) + fi;
+            const int64_t n = tile * TL_F + f;
+            if (n >= N) break;
+            float xv[TL_J];
+#pragma unroll
+            for (int j = 0; j < TL_J; ++j) {
+                const int d = lane + 32 * j;
+                xv[j] = (d < D) ? Xs[d * TL_LD + f] : 0.f;
+            }
+            int k;
+            if (idx32) {
+                k = idx32[n];
+            } else {
+                const int cnt = cand_cnt[n];
+                const uint16_t* c = cand_idx + (size_t)n * kCandMax;
+                k = c[0];
+                if (cnt > 1) {
+                    float x2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < TL_J; ++j) x2 = __fadd_rn(x2, __fmul_rn(xv[j], xv[j]));
+                    x2 = warp_sum(x2);
+                    float bd = 0.f;
+                    int bk = -1;
+                    for (int ci = 0; ci < cnt; ++ci) {
+                        const int kc = c[ci];
+                        const float* er = E + (size_t)kc * D;
+                        float dot = 0.f;
+#pragma unroll
+                        for (int j = 0; j < TL_J; ++j) {
+                            const int d = lane + 32 * j;
+                            if (d < D) dot = fmaf(xv[j], er[d], dot);
+                        }
+                        dot = warp_sum(dot);
+                        const float dist = ref_distance(x2, e2[kc], dot);
+                        if (better(dist, kc, bd, bk)) { bd = dist; bk = kc; }
+                    }
+                    k = bk;
+                    n_resc += 1;
+                    n_short += cnt;
+                } else {
+                    n_short += 1;
+                }
+            }
+            const float* er = E + (size_t)k * D;
+            float fs = 0.f;
+#pragma unroll
+            for (int j = 0; j < TL_J; ++j) {
+                const int d = lane + 32 * j;
+                if (d < D) {
+                    const float q = er[d];
+                    const float diff = __fsub_rn(q, xv[j]);
+                    fs = fmaf(diff, diff, fs);
+                    Xs[d * TL_LD + f] = __fadd_rn(xv[j], diff);      // straight-through VALUE (vector_quantizer.py:48)
+                    if (kResid) atomicAdd(resid + (size_t)k * D + d, -diff);
+                }
+            }
+            {   // Kahan: sse += fs
+                const float y = fs - sse_c, t = sse + y;
+                sse_c = (t - sse) - y;
+                sse = t;
+            }
+            if (lane == 0) {
+                atomicAdd(counts + k, 1);
+                idx_out[n] = (int64_t)k;
+            }
+        }
+        if (q_out) {
+            __syncthreads();
+            if (valid)
+                for (int d = warp; d < D; d += 8) st_stream(q_out + col + (size_t)d * W, Xs[d * TL_LD + lane]);
+        }
+    }
+    double t = (double)sse - (double)sse_c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) red[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        sse_partials[blockIdx.x] = s;
+    }
+    if (lane == 0 && (n_resc | n_short)) {
+        atomicAdd(&meta->rescored, (unsigned long long)n_resc);
+        atomicAdd(&meta->shortlisted, (unsigned long long)n_short);
+    }
+}
+
+cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
+                        const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
+                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, cudaStream_t s) {
+    (void)K;
+    const int64_t N = (int64_t)B * W;
+    const size_t smem = (size_t)D * TL_LD * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int64_t tiles = (N + TL_F - 1) / TL_F;
+    int64_t grid = n_partials < tiles ? n_partials : tiles;
+    if (grid < 1) grid = 1;
+    cudaError_t e = cudaMemsetAsync(sse_partials, 0, (size_t)n_partials * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    double* part = reinterpret_cast<double*>(sse_partials);
+    if (resid)
+        tail_kernel<true><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, idx32, cand_cnt, cand_idx, idx_out, q_out,
+                                                            counts, resid, part, meta);
+    else
+        tail_kernel<false><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, idx32, cand_cnt, cand_idx, idx_out, q_out,
+                                                             counts, nullptr, part, meta);
+    return cudaGetLastError();
+}
+
+// counts (int) and SSE partials (double) -> the fp32 statistics buffer [counts | resid | SSE | N]
+__global__ void __launch_bounds__(256) pack_stats_kernel(const int* __restrict__ counts, const double* __restrict__ part,
+                                                         int n_partials, int64_t N, int K, int D, float* __restrict__ stats,
+                                                         bool accumulate) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < K) stats[i] = (float)counts[i];
+    if (blockIdx.x == 0) {
+        __shared__ double red[256];
+        double s = 0.0;
+        for (int j = threadIdx.x; j < n_partials; j += 256) s += part[j];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const size_t base = (size_t)K * ((size_t)D + 1);
+            stats[base] = (float)(red[0] + (accumulate ? (double)stats[base] : 0.0));
+            stats[base + 1] = (float)((double)N + (accumulate ? (double)stats[base + 1] : 0.0));
+        }
+    }
+}
+
+cudaError_t launch_pack_stats(const int* counts, const float* sse_partials, int n_partials, int64_t N, int K, int D,
+                              float* stats, bool accumulate, cudaStream_t s) {
+    pack_stats_kernel<<<(K + 255) / 256, 256, 0, s>>>(counts, reinterpret_cast<const double*>(sse_partials), n_partials, N, K, D,
+                                                      stats, accumulate);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+__global__ void __launch_bounds__(1024) finalize_kernel(const float* __restrict__ stats, int K, int D, float beta,
+                                                        float* __restrict__ losses) {
+    __shared__ double red[32];
+    const size_t base = (size_t)K * ((size_t)D + 1);
+    const float n = stats[base + 1];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < K; k += 1024) {
+        const float p = stats[k] / n;                         // avg_probs (vector_quantizer.py:49)
+        s += (double)(p * logf(p + 1e-10f));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += red[i];
+        const float mse = (float)((double)stats[base] / ((double)n * (double)D));
+        losses[0] = mse;                                     // embedding_loss (:46)
+        losses[1] = beta * mse;                              // commitment_loss (:45)
+        losses[2] = expf((float)(-t));                       // perplexity (:50)
+    }
+}
+
+cudaError_t launch_finalize(const float* stats, int K, int D, float beta, float* losses, cudaStream_t s) {
+    finalize_kernel<<<1, 1024, 0, s>>>(stats, K, D, beta, losses);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// dX[b,:,w] = Gq[b,:,w] + g_c * beta * 2 (x - q) / (N D); same transposing tile as the tail kernel.
+__global__ void __launch_bounds__(256) backward_dx_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                          const int64_t* __restrict__ idx, const float* __restrict__ Gq,
+                                                          const float* __restrict__ g_c, float beta, int D, int64_t W,
+                                                          int64_t N, float* __restrict__ dX) {
+    extern __shared__ __align__(16) float Xs[];   // [D][33]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float gc = g_c ? *g_c : 0.f;
+    const float coef = gc * beta * (2.0f / ((float)N * (float)D));
+    for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x) {
+        const int64_t nl = tile * TL_F + lane;
+        const bool valid = nl < N;
+        int64_t b = 0, w = 0;
+        if (valid) { b = nl / W; w = nl - b * W; }
+        const size_t col = (size_t)b * D * W + w;
+        __syncthreads();
+        for (int d = warp; d < D; d += 8) Xs[d * TL_LD + lane] = valid ? ld_stream(z + col + (size_t)d * W) : 0.f;
+        __syncthreads();
+        for (int fi = 0; fi < TL_F / 8; ++fi) {
+            const int f = warp * (TL_F / 8) + fi;
+            const int64_t n = tile * TL_F + f;
+            if (n >= N) break;
+            const float* er = E + (size_t)idx[n] * D;
+            for (int d = lane; d < D; d += 32) Xs[d * TL_LD + f] = coef * __fsub_rn(Xs[d * TL_LD + f], er[d]);
+        }
+        __syncthreads();
+        if (valid)
+            for (int d = warp; d < D; d += 8) {
+                const size_t a = col + (size_t)d * W;
+                st_stream(dX + a, (Gq ? ld_stream(Gq + a) : 0.f) + Xs[d * TL_LD + lane]);
+            }
+    }
+}
+
+cudaError_t launch_backward_dx(const float* z, const float* codebook, const int64_t* idx, const float* Gq, const float* g_c,
+                               float beta, int B, int D, int64_t W, int K, float* dX, cudaStream_t s) {
+    (void)K;
+    const int64_t N = (int64_t)B * W;
+    const size_t smem = (size_t)D * TL_LD * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(backward_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int64_t tiles = (N + TL_F - 1) / TL_F;
+    int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
+    if (grid < 1) grid = 1;
+    backward_dx_kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, dX);
+    return cudaGetLastError();
+}
+
+// dE[k,:] = -g_e * (2 / (N D)) * resid[k,:]; rows never selected have resid == 0 exactly -> dE == 0 exactly.
+__global__ void __launch_bounds__(256) backward_de_kernel(const float* __restrict__ stats, const float* __restrict__ g_e,
+                                                          int K, int D, float* __restrict__ dE) {
+    const size_t total = (size_t)K * D;
+    const float n = stats[total + K + 1];
+    const float coef = -(g_e ? *g_e : 0.f) * (2.0f / (n * (float)D));
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256)
+        dE[i] = coef * stats[K + i];
+}
+
+cudaError_t launch_backward_de(const float* stats, const float* g_e, int K, int D, float* dE, cudaStream_t s) {
+    const size_t total = (size_t)K * D;
+    size_t grid = (total + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    backward_de_kernel<<<(unsigned)grid, 256, 0, s>>>(stats, g_e, K, D, dE);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ one-hot / gather / windows
+__global__ void __launch_bounds__(256) onehot_kernel(const int64_t* __restrict__ idx, int64_t N, int K, float* __restrict__ out) {
+    const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (n < N) out[(size_t)n * K + idx[n]] = 1.0f;
+}
+
+cudaError_t launch_onehot(const int64_t* idx, int64_t N, int K, float* out, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * K * sizeof(float), s);
+    if (e != cudaSuccess) return e;
+    onehot_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(idx, N, K, out);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ E, const int64_t* __restrict__ idx, int D,
+                                                     int64_t W, int64_t N, float* __restrict__ out) {
+    extern __shared__ __align__(16) float Xs[];   // [D][33]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x) {
+        const int64_t nl = tile * TL_F + lane;
+        const bool valid = nl < N;
+        int64_t b = 0, w = 0;
+        if (valid) { b = nl / W; w = nl - b * W; }
+        const size_t col = (size_t)b * D * W + w;
+        __syncthreads();
+        for (int fi = 0; fi < TL_F / 8; ++fi) {
+            const int f = warp * (TL_F / 8) + fi;
+            const int64_t n = tile * TL_F + f;
+            if (n >= N) break;
+            const float* er = E + (size_t)idx[n] * D;
+            for (int d = lane; d < D; d += 32) Xs[d * TL_LD + f] = er[d];
+        }
+        __syncthreads();
+        if (valid)
+            for (int d = warp; d < D; d += 8) st_stream(out + col + (size_t)d * W, Xs[d * TL_LD + lane]);
+    }
+}
+
+cudaError_t launch_gather(const float* codebook, const int64_t* idx, int B, int D, int64_t W, int K, float* out, cudaStream_t s) {
+    (void)K;
+    const int64_t N = (int64_t)B * W;
+    const size_t smem = (size_t)D * TL_LD * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int64_t tiles = (N + TL_F - 1) / TL_F;
+    int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
+    if (grid < 1) grid = 1;
+    gather_kernel<<<(unsigned)grid, 256, smem, s>>>(codebook, idx, D, W, N, out);
+    return cudaGetLastError();
+}
+
+// idx [B, L] -> tokens [B, n_win, window] (pad_id past L) + mask (bert.py:50-69)
+__global__ void __launch_bounds__(256) window_kernel(const int64_t* __restrict__ idx, int64_t L, int window, int64_t n_win,
+                                                     int64_t total, int64_t pad_id, int64_t* __restrict__ tokens,
+                                                     float* __restrict__ mask) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t per_b = n_win * window;
+        const int64_t b = i / per_b, pos = i - b * per_b;
+        const bool real = pos < L;
+        tokens[i] = real ? idx[b * L + pos] : pad_id;
+        mask[i] = real ? 1.0f : 0.0f;
+    }
+}
+
+cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int64_t pad_id, int64_t* tokens, float* mask,
+                          cudaStream_t s) {
+    const int64_t n_win = (L + window - 1) / window;
+    const int64_t total = (int64_t)B * n_win * window;
+    int64_t grid = (total + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    window_kernel<<<(unsigned)grid, 256, 0, s>>>(idx, L, window, n_win, total, pad_id, tokens, mask);
+    return cudaGetLastError();
+}
+
+}  // namespace vqb

@@ -1,0 +1,491 @@
+// Tensor-core nearest-code shortlist for sm_100a: the fused distance + running-argmin kernel.
+//
+//   score[n, k] = |e_k|^2 - 2 * bf16(x_n) . bf16(e_k)        (the |x_n|^2 term is constant per frame)
+//
+// replaces `distances` + `argmin` of src/model/components/vector_quantizer.py:32-37.  The N x K score matrix never
+// leaves the SM: tcgen05.mma accumulates a 128-frame x 256-code tile in TMEM, epilogue warps pull it back with
+// tcgen05.ld, add |e_k|^2 and keep, per frame, the codes whose score is within a rigorous guard band of the running
+// minimum (at most 4 per column half).  The fused tail kernel then rescoring those few codes in fp32 in the reference's
+// operation order decides the index; frames whose shortlist overflowed go to the exact fp32 search.
+//
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0      TMA producer: latent tile A (128 frames x D, resident per M tile) and codebook tiles B
+//               (256 codes x 64 dims per stage) as 128B-swizzled K-major boxes, |e|^2 slices by bulk copy
+//   warp 1      MMA issuer: one lane issues tcgen05.mma cta_group::1 kind::f16 M128 N256 K16, fp32 accumulate,
+//               two TMEM accumulator stages (2 x 256 columns) so the epilogue of tile j overlaps the MMAs of tile j+1
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).., column half (w-4)/4
+#include "vqb_internal.h"
+
+#include <cuda.h>
+
+namespace vqb {
+
+namespace tc {
+
+constexpr int BM = kTileRows;      // 128 frames per tile (= TMEM lanes)
+constexpr int BN = kTileCodes;     // 256 codes per tile (= TMEM columns of one accumulator stage)
+constexpr int BK = 64;             // bf16 elements per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_CHUNK_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
+constexpr int E2_SLICE_BYTES = BN * 4;       // 1 KiB
+constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 4;
+constexpr int E2_SLOTS = 4;                  // |e|^2 slices ride their own ring so the producer never waits on the epilogue
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4, EPI_THREADS = 256;
+constexpr int MERGE_WORDS = 10;              // per frame and half: 4 scores, 4 codes, dropped-min, pad
+
+struct Barriers {
+    unsigned long long b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
+    unsigned long long a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
+    unsigned long long e2_full[E2_SLOTS], e2_empty[E2_SLOTS], tmem_full[2], tmem_empty[2];
+    unsigned int tmem_base;
+    unsigned int pad;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a pipeline bug must become a trapped launch, never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((it & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();   // ~2 s
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+#define VQB_R32(r) \
+    "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), \
+    "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),   \
+    "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),  \
+    "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+#define VQB_RW32(r) \
+    "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), \
+    "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),   \
+    "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),  \
+    "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+
+// 32 lanes x 32 consecutive columns: thread i of the warp receives columns [col, col+32) of TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : VQB_R32(r)
+        : "r"(taddr)
+        : "memory");
+}
+// The wait names the destination registers as read-write operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : VQB_RW32(r)::"memory");
+}
+
+// ---------------------------------------------------------------------------------------------- shortlist
+struct Shortlist {
+    float v[4];     // ascending scores
+    int   i[4];     // codes (-1 = empty)
+    float dropped;  // smallest score ever pushed out of / refused by the list
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = INFINITY; i[j] = -1; }
+        dropped = INFINITY;
+    }
+    __device__ __forceinline__ void insert(float s, int code) {
+        if (s < v[3]) {
+            dropped = fminf(dropped, v[3]);
+            if (s < v[2]) {
+                v[3] = v[2]; i[3] = i[2];
+                if (s < v[1]) {
+                    v[2] = v[1]; i[2] = i[1];
+                    if (s < v[0]) { v[1] = v[0]; i[1] = i[0]; v[0] = s; i[0] = code; }
+                    else { v[1] = s; i[1] = code; }
+                } else { v[2] = s; i[2] = code; }
+            } else { v[3] = s; i[3] = code; }
+        } else {
+            dropped = fminf(dropped, s);
+        }
+    }
+};
+
+// One 32-column slab of scores for this thread's frame.  Fast path: 8 FFMA + 4 FMNMX3 + 1 compare per 8 codes.
+__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int code0, float band,
+                                          float& thr, Shortlist& sl) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float4 ea = *reinterpret_cast<const float4*>(e2s + g * 8);
+        const float4 eb = *reinterpret_cast<const float4*>(e2s + g * 8 + 4);
+        float s[8];
+        s[0] = fmaf(-2.f, __uint_as_float(r[g * 8 + 0]), ea.x);
+        s[1] = fmaf(-2.f, __uint_as_float(r[g * 8 + 1]), ea.y);
+        s[2] = fmaf(-2.f, __uint_as_float(r[g * 8 + 2]), ea.z);
+        s[3] = fmaf(-2.f, __uint_as_float(r[g * 8 + 3]), ea.w);
+        s[4] = fmaf(-2.f, __uint_as_float(r[g * 8 + 4]), eb.x);
+        s[5] = fmaf(-2.f, __uint_as_float(r[g * 8 + 5]), eb.y);
+        s[6] = fmaf(-2.f, __uint_as_float(r[g * 8 + 6]), eb.z);
+        s[7] = fmaf(-2.f, __uint_as_float(r[g * 8 + 7]), eb.w);
+        float t = fminf(fminf(s[0], s[1]), s[2]);
+        t = fminf(fminf(t, s[3]), s[4]);
+        t = fminf(fminf(t, s[5]), s[6]);
+        t = fminf(t, s[7]);
+        if (t < thr) {   // rare after the first few tiles: some code here is within the band of the running minimum
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (s[j] < thr) {
+                    sl.insert(s[j], code0 + g * 8 + j);
+                    thr = sl.v[0] + band;
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int code0, int K, float* row_out) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+        if (code0 + j < K) row_out[code0 + j] = fmaf(-2.f, __uint_as_float(r[j]), e2s[j]);
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
+                 const float* __restrict__ e2, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
+                 int num_kb, int a_slots, int b_stages, int K, uint8_t* __restrict__ cand_cnt, uint16_t* __restrict__ cand_idx,
+                 int* __restrict__ fallback_rows, WsMeta* meta, float* __restrict__ scores_dbg) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sA = smem;                                            // a_slots x 16 KiB
+    unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB
+    float* sE2 = reinterpret_cast<float*>(sB + (size_t)b_stages * B_STAGE_BYTES);   // E2_SLOTS x 256 floats
+    float* sMerge = sE2 + E2_SLOTS * BN;                                 // 2 x 128 x MERGE_WORDS
+    Barriers* bars = reinterpret_cast<Barriers*>(sMerge + 2 * BM * MERGE_WORDS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_e);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
+        for (int i = 0; i < a_slots; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+        for (int i = 0; i < E2_SLOTS; ++i) {
+            mbar_init(smem_u32(&bars->e2_full[i]), 1);
+            mbar_init(smem_u32(&bars->e2_empty[i]), EPI_THREADS / 32);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bars->tmem_full[i]), 1);
+            mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_THREADS / 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        uint32_t a_it = 0, b_it = 0, n_it = 0;
+        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
+                const uint32_t es = n_it % E2_SLOTS;
+                mbar_wait(smem_u32(&bars->e2_empty[es]), ((n_it / E2_SLOTS) & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(smem_u32(&bars->e2_full[es]), E2_SLICE_BYTES);
+                    bulk_load_1d(smem_u32(sE2 + es * BN), e2 + (size_t)nt * BN, E2_SLICE_BYTES, smem_u32(&bars->e2_full[es]));
+                }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (nt == 0) {
+                        const uint32_t slot = a_it % a_slots, ph = (a_it / a_slots) & 1;
+                        mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
+                        if (lane == 0) {
+                            mbar_expect_tx(smem_u32(&bars->a_full[slot]), A_CHUNK_BYTES);
+                            tma_load_2d(smem_u32(sA + (size_t)slot * A_CHUNK_BYTES), &tmap_x, smem_u32(&bars->a_full[slot]), kb * BK,
+                                        mt * BM);
+                        }
+                        ++a_it;
+                    }
+                    const uint32_t st = b_it % b_stages, ph = (b_it / b_stages) & 1;
+                    mbar_wait(smem_u32(&bars->b_empty[st]), ph ^ 1);
+                    if (lane == 0) {
+                        mbar_expect_tx(smem_u32(&bars->b_full[st]), B_STAGE_BYTES);
+                        tma_load_2d(smem_u32(sB + (size_t)st * B_STAGE_BYTES), &tmap_e, smem_u32(&bars->b_full[st]), kb * BK, nt * BN);
+                    }
+                    ++b_it;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        uint32_t a_base = 0, b_it = 0, n_it = 0;   // a_base: A chunk counter at the start of the current M tile
+        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
+                const uint32_t as = n_it & 1;
+                mbar_wait(smem_u32(&bars->tmem_empty[as]), ((n_it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const uint32_t a_idx = a_base + kb, slot = a_idx % a_slots;
+                    if (nt == 0) mbar_wait(smem_u32(&bars->a_full[slot]), (a_idx / a_slots) & 1);
+                    const uint32_t st = b_it % b_stages;
+                    mbar_wait(smem_u32(&bars->b_full[st]), (b_it / b_stages) & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t da = make_desc_sw128(smem_u32(sA + (size_t)slot * A_CHUNK_BYTES));
+                        const uint64_t db = make_desc_sw128(smem_u32(sB + (size_t)st * B_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes per K step inside the swizzle row: +2 in 16-byte units
+                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+                        umma_commit(smem_u32(&bars->b_empty[st]));
+                        if (nt == num_n_tiles - 1) umma_commit(smem_u32(&bars->a_empty[slot]));
+                        if (kb == num_kb - 1) umma_commit(smem_u32(&bars->tmem_full[as]));
+                    }
+                    __syncwarp();
+                    ++b_it;
+                }
+            }
+            a_base += num_kb;
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ================================================================ epilogue
+        const int ew = warp - EPI_WARP0;
+        const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32*quarter .. +31
+        const int half = ew >> 2;                // column half of every tile
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
+        const bool force_fallback = meta->cb_nonfinite != 0;
+        uint32_t n_it = 0;
+        Shortlist sl;
+        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+            const int64_t row = (int64_t)mt * BM + row_in_tile;
+            const float band = (row < N) ? band_g[row] : 0.f;
+            float thr = INFINITY;
+            sl.reset();
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
+                const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1, es = n_it % E2_SLOTS;
+                mbar_wait(smem_u32(&bars->e2_full[es]), (n_it / E2_SLOTS) & 1);
+                mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + t_lane + as * BN + half * (BN / 2);
+                const float* e2s = sE2 + es * BN + half * (BN / 2);
+                const int code0 = nt * BN + half * (BN / 2);
+                uint32_t ra[32], rb[32];
+                tmem_ld32(taddr, ra);
+                tmem_ld_wait(ra);
+                if (scores_dbg) {
+                    float* row_out = scores_dbg + (size_t)row * K;
+                    tmem_ld32(taddr + 32, rb);
+                    if (row < N) dump_slab(ra, e2s, code0, K, row_out);
+                    tmem_ld_wait(rb);
+                    tmem_ld32(taddr + 64, ra);
+                    if (row < N) dump_slab(rb, e2s + 32, code0 + 32, K, row_out);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 96, rb);
+                    if (row < N) dump_slab(ra, e2s + 64, code0 + 64, K, row_out);
+                    tmem_ld_wait(rb);
+                    if (row < N) dump_slab(rb, e2s + 96, code0 + 96, K, row_out);
+                } else {
+                    tmem_ld32(taddr + 32, rb);
+                    scan_slab(ra, e2s, code0, band, thr, sl);
+                    tmem_ld_wait(rb);
+                    tmem_ld32(taddr + 64, ra);
+                    scan_slab(rb, e2s + 32, code0 + 32, band, thr, sl);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 96, rb);
+                    scan_slab(ra, e2s + 64, code0 + 64, band, thr, sl);
+                    tmem_ld_wait(rb);
+                    scan_slab(rb, e2s + 96, code0 + 96, band, thr, sl);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(smem_u32(&bars->tmem_empty[as]));
+                    mbar_arrive(smem_u32(&bars->e2_empty[es]));
+                }
+            }
+            // ---- merge the two column halves of this frame and publish the shortlist
+            float* mine = sMerge + ((size_t)half * BM + row_in_tile) * MERGE_WORDS;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mine[j] = sl.v[j]; mine[4 + j] = __int_as_float(sl.i[j]); }
+            mine[8] = sl.dropped;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0 && row < N && !scores_dbg) {
+                const float* other = sMerge + ((size_t)BM + row_in_tile) * MERGE_WORDS;
+                const float gmin = fminf(sl.v[0], other[0]);
+                const float cutoff = gmin + band;
+                int cnt = 0;
+                unsigned long long lo = 0ull, hi = 0ull;   // up to 8 codes of 16 bits, own half first
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (sl.i[j] >= 0 && sl.v[j] <= cutoff) { lo |= (unsigned long long)sl.i[j] << (16 * cnt); ++cnt; }
+                }
+                const int cnt0 = cnt;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int oi = __float_as_int(other[4 + j]);
+                    if (oi >= 0 && other[j] <= cutoff) { hi |= (unsigned long long)oi << (16 * (cnt - cnt0)); ++cnt; }
+                }
+                // close the gap between the two halves: 64-bit funnel of hi into the free slots of lo
+                const unsigned long long hi_lo = cnt0 == 4 ? 0ull : hi << (16 * cnt0);
+                const unsigned long long hi_hi = cnt0 == 0 ? 0ull : (cnt0 == 4 ? hi : hi >> (16 * (4 - cnt0)));
+                lo |= hi_lo;
+                hi = hi_hi;
+                const bool overflow = force_fallback || cnt == 0 || !(band < INFINITY) || fminf(sl.dropped, other[8]) <= cutoff;
+                if (overflow) {
+                    cand_cnt[row] = 0;
+                    fallback_rows[atomicAdd(&meta->fallback_count, 1)] = (int)row;
+                    atomicAdd(&meta->fallback_total, 1ull);
+                } else {
+                    cand_cnt[row] = (uint8_t)cnt;
+                    *reinterpret_cast<uint4*>(cand_idx + (size_t)row * kCandMax) =
+                        make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+                }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// rows x D bf16, row-major; box = 64 columns (128 B) x box_rows, 128B swizzle, out-of-bounds reads return zeros
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t D, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VQB_E_DEVICE; }
+    const cuuint64_t dims[2] = {D, rows};
+    const cuuint64_t strides[1] = {D * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return 1000 + (int)r; }
+    return 0;
+}
+
+}  // namespace tc
+
+int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const float* e2, const float* band, int64_t N, int64_t N_pad,
+                     int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
+                     float* scores_dbg, cudaStream_t s) {
+    using namespace tc;
+    CUtensorMap mx, me;
+    int rc;
+    if ((rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM)) != 0) return rc;
+    if ((rc = make_map(&me, eb, (uint64_t)K_pad, (uint64_t)D, BN)) != 0) return rc;
+    const int num_kb = (D + BK - 1) / BK;
+    const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + 2 * BM * MERGE_WORDS * 4 + sizeof(Barriers) + 1024;
+    int b_stages = (int)((227 * 1024 - fixed) / B_STAGE_BYTES);
+    if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
+    if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
+    const size_t smem = fixed + (size_t)b_stages * B_STAGE_BYTES;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_search_kernel)");
+        attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int num_m_tiles = (int)(N_pad / BM);
+    const int num_n_tiles = K_pad / BN;
+    const int grid = num_m_tiles < sms ? num_m_tiles : sms;
+    tc_search_kernel<<<grid, NUM_THREADS, smem, s>>>(mx, me, e2, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, K,
+                                                     cand_cnt, cand_idx, fallback_rows, meta, scores_dbg);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "tc_search_kernel launch");
+    return 0;
+}
+
+}  // namespace vqb

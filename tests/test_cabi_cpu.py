@@ -1,0 +1,77 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol include/vqb.h declares, validates its
+arguments before touching a device, and fails loudly (no fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import vq_b200
+from vq_b200 import _lib, functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "vqb.h")).read()
+    return sorted(set(re.findall(r"VQB_API\s+(?:const\s+char\*|int)\s+(vqb_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 17
+    assert sorted(_lib.EXPORTS) == names, "ctypes table and include/vqb.h disagree"
+    handle = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in vqb.h but not exported by libvqb_b200.so"
+
+
+def test_version_and_workspace_sizing():
+    lib = _lib.lib()
+    assert lib.vqb_version() == 100
+    small = F.workspace_bytes(1000, 512, 64, _lib.PREC_FP32)
+    big = F.workspace_bytes(1 << 20, 1024, 64, _lib.PREC_BF16)
+    assert 0 < small < big
+    # bf16 path: bf16 latent copy (2 B/elem) dominates; never anything like N*K
+    assert big < (1 << 20) * (64 * 2 + 64) + (32 << 20)
+
+
+@pytest.mark.parametrize("N,K,D", [(100, 0, 64), (100, 70000, 64), (100, 512, 24), (100, 512, 1024), (0, 512, 64)])
+def test_argument_errors_are_reported_not_swallowed(N, K, D):
+    with pytest.raises(_lib.VqbError) as ei:
+        F.workspace_bytes(N, K, D, _lib.PREC_BF16)
+    assert ei.value.code == -2 and "unsupported" in str(ei.value)
+
+
+def test_unknown_precision_flag():
+    with pytest.raises(_lib.VqbError) as ei:
+        F.workspace_bytes(100, 512, 64, 0x07)
+    assert ei.value.code == -6
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    vq = vq_b200.VectorQuantizer(16, 16, 0.25)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vq(torch.zeros(1, 16, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F.vq_forward(torch.zeros(1, 16, 8), torch.zeros(16, 16))
+    # calling the C ABI directly without a device is an error code, never a silent CPU result
+    z = torch.zeros(1, 16, 8)
+    cb = torch.zeros(16, 16)
+    idx = torch.zeros(8, dtype=torch.int64)
+    stats = torch.zeros(_lib.stats_len(16, 16))
+    ws = torch.zeros(1 << 16, dtype=torch.uint8)
+    rc = _lib.lib().vqb_forward(z.data_ptr(), cb.data_ptr(), 1, 16, 8, 16, 0, idx.data_ptr(), None, stats.data_ptr(), ws.data_ptr(),
+                                ws.numel(), None)
+    assert rc != 0 and _lib.lib().vqb_last_error()
+
+
+def test_module_interface_matches_reference():
+    """ctor / attributes / state_dict key of vector_quantizer.py:11-21 and the init range U(-1/K, 1/K)."""
+    vq = vq_b200.VectorQuantizer(num_embedding=128, embedding_dim=32, commitment_cost=0.25)
+    assert (vq.num_embedding, vq.embedding_dim, vq.commitment_cost) == (128, 32, 0.25)
+    assert isinstance(vq.codebook, torch.nn.Embedding) and list(vq.state_dict()) == ["codebook.weight"]
+    w = vq.codebook.weight
+    assert w.shape == (128, 32) and w.requires_grad and float(w.abs().max()) <= 1 / 128

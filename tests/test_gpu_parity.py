@@ -1,0 +1,277 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes) and through the drop-in module, against the
+CPU oracle and the reference-generated golden fixtures.  Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+import torch
+
+import vq_b200
+from oracle import vq_oracle as O
+from vq_b200 import _lib, functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+LOSS_RTOL = 1e-5
+PRECISIONS = ["fp32", "bf16"]
+
+
+def seeded(seed, shape, scale=1.0):
+    return np.random.default_rng(seed).standard_normal(shape, dtype=np.float32) * np.float32(scale)
+
+
+def assert_index_parity(got, z, cb, ref_idx, margin, eps):
+    """Equal on every frame whose oracle fp32 top-2 margin exceeds eps_n; on near-ties the chosen code must lie within
+    eps_n of the minimum oracle distance (the stated near-tie tolerance)."""
+    got = np.asarray(got).reshape(-1)
+    clear = margin > eps
+    n_clear_bad = int((got[clear] != ref_idx[clear]).sum())
+    assert n_clear_bad == 0, f"{n_clear_bad} index mismatches on clear-margin frames"
+    bad = np.nonzero(got != ref_idx)[0]
+    if bad.size:
+        d = O.distances(O.bcw_to_rows(z)[bad], cb)
+        chosen = d[np.arange(bad.size), got[bad]]
+        assert np.all(chosen - d.min(axis=1) <= eps[bad]), "near-tie frame resolved to a code outside the tolerance"
+    return int(bad.size)
+
+
+def run_module(z, cb, beta, precision, Gq=None, **kw):
+    K, D = cb.shape
+    vq = vq_b200.VectorQuantizer(K, D, beta, precision=precision, **kw).to(DEV)
+    with torch.no_grad():
+        vq.codebook.weight.copy_(torch.from_numpy(cb))
+    zt = torch.from_numpy(z).to(DEV).requires_grad_(True)
+    out = vq(zt)
+    if Gq is not None:
+        emb, com, q = out[0], out[1], out[2]
+        (emb + com + (q * torch.from_numpy(Gq).to(DEV)).sum()).backward()
+    return vq, zt, out
+
+
+# ----------------------------------------------------------------------------------------------- tensor-core tile
+@pytest.mark.parametrize("B,D,W,K", [(1, 64, 128, 256), (2, 64, 333, 512), (1, 256, 640, 8192), (3, 128, 100, 300),
+                                     (1, 80, 257, 1000), (1, 512, 130, 512), (1, 16, 200, 64)])
+def test_tcgen05_scores_match_bf16_matmul(B, D, W, K):
+    """Validates TMA boxes, UMMA descriptors, TMEM addressing and the |e|^2 add: raw scores of the tcgen05 tile equal
+    |e|^2 - 2 bf16(x).bf16(e) evaluated in float64 from the same bf16-rounded operands."""
+    z = torch.from_numpy(seeded(11, (B, D, W))).to(DEV)
+    cb = torch.from_numpy(seeded(12, (K, D))).to(DEV)
+    got = F.debug_tc_scores(z, cb)
+    rows = z.permute(0, 2, 1).reshape(-1, D)
+    xb = rows.to(torch.bfloat16).to(torch.float64)
+    eb = cb.to(torch.bfloat16).to(torch.float64)
+    want = (cb.double() ** 2).sum(1)[None, :] - 2.0 * xb @ eb.T
+    assert not torch.isnan(got).any(), "tile left scores unwritten"
+    err = (got.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= 2e-5 * scale + 1e-4, f"max |score error| {err} (scale {scale})"
+
+
+# ----------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_golden_forward_backward(golden, precision):
+    g = golden
+    z, cb, beta = g["z"], g["codebook"], float(g["beta"])
+    K, D = cb.shape
+    vq, zt, (emb, com, q, ppl, enc, idx) = run_module(z, cb, beta, precision, Gq=g["Gq"])
+    assert [t.requires_grad for t in (emb, com, q, ppl, enc, idx)] == [True, True, True, False, False, False]
+    assert idx.shape == (z.shape[0] * z.shape[2], 1) and idx.dtype == torch.int64 and enc.shape == (idx.shape[0], K)
+    got = idx.reshape(-1).cpu().numpy()
+    x2 = (O.bcw_to_rows(z) ** 2).sum(1)
+    eps = O.near_tie_eps(x2, float((cb ** 2).sum(1).max()))
+    n_bad = assert_index_parity(got, z, cb, g["indices"].astype(np.int64), g["margin"], eps)
+    np.testing.assert_allclose(emb.item(), g["embedding_loss"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(com.item(), g["commitment_loss"], rtol=LOSS_RTOL)
+    assert torch.equal(enc.argmax(1), idx.reshape(-1)) and float(enc.sum()) == idx.shape[0]
+    if n_bad == 0:
+        np.testing.assert_allclose(ppl.item(), g["perplexity"], rtol=LOSS_RTOL)
+        if "quantized" in g:
+            assert np.array_equal(q.detach().cpu().numpy(), g["quantized"]), "straight-through value must be bit-equal"
+        np.testing.assert_allclose(zt.grad.cpu().numpy(), g["dX"], rtol=1e-5, atol=1e-7 * np.abs(g["dX"]).max())
+        dE = vq.codebook.weight.grad.cpu().numpy()
+        if "dE" in g:
+            np.testing.assert_allclose(dE, g["dE"], rtol=1e-4, atol=1e-6 * np.abs(g["dE"]).max())
+            untouched = np.bincount(got, minlength=K) == 0
+            assert np.all(dE[untouched] == 0), "never-selected codes must get an exactly zero gradient"
+            opt = torch.optim.Adam(vq.parameters(), lr=1e-4, amsgrad=False)     # vqvae.py:168-171
+            opt.step()
+            after = vq.codebook.weight.detach().cpu().numpy()
+            np.testing.assert_allclose(after, g["codebook_after_adam"], rtol=1e-5, atol=2e-7)
+            assert np.array_equal(after[untouched], cb[untouched]), "never-selected rows must stay bit-identical"
+        else:
+            sel = g["sel_codes"]
+            np.testing.assert_allclose(dE[sel], g["dE_sel"], rtol=1e-4, atol=1e-6 * np.abs(g["dE_sel"]).max())
+            rest = np.ones(K, bool); rest[sel] = False
+            assert np.all(dE[rest] == 0)
+
+
+# ----------------------------------------------------------------------------------------------- oracle on seeded inputs
+CASES = [
+    # B, D, W, K, codebook scale (None = reference default init U(-1/K, 1/K)), latent scale
+    (2, 64, 11000, 512, None, 1.0),     # cfg-1 shape, tie-heavy default init
+    (8, 64, 4099, 1024, 1.0, 1.0),      # W not a multiple of anything
+    (1, 256, 3000, 8192, 1.0, 1.0),     # headline shape class
+    (5, 128, 777, 384, 0.3, 2.0),       # K not a multiple of 256
+    (1, 16, 50, 7, 1.0, 1.0),           # tiny everything
+    (3, 512, 200, 1000, 1.0, 0.5),      # largest D
+    (1, 64, 1, 512, 1.0, 1.0),          # a single frame
+    (2, 48, 500, 1, 1.0, 1.0),          # a single code
+]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("B,D,W,K,cb_scale,z_scale", CASES)
+def test_oracle_parity(B, D, W, K, cb_scale, z_scale, precision):
+    z = seeded(100 + D + K, (B, D, W), z_scale)
+    if cb_scale is None:
+        cb = np.random.default_rng(5).uniform(-1 / K, 1 / K, (K, D)).astype(np.float32)
+    else:
+        cb = seeded(200 + D + K, (K, D), cb_scale)
+    beta = 0.25
+    ref = O.vq_forward(z, cb, beta)
+    Gq = seeded(7, z.shape, 1e-3)
+    vq, zt, (emb, com, q, ppl, enc, idx) = run_module(z, cb, beta, precision, Gq=Gq)
+    got = idx.reshape(-1).cpu().numpy()
+    n_bad = assert_index_parity(got, z, cb, ref.indices, ref.margin, ref.eps)
+    np.testing.assert_allclose(emb.item(), ref.embedding_loss, rtol=LOSS_RTOL)
+    np.testing.assert_allclose(com.item(), ref.commitment_loss, rtol=LOSS_RTOL)
+    if n_bad == 0:
+        np.testing.assert_allclose(ppl.item(), ref.perplexity, rtol=LOSS_RTOL)
+        assert np.array_equal(q.detach().cpu().numpy(), ref.quantized)
+    dX, dE = O.vq_backward(z, cb, got, beta, 1.0, 1.0, Gq)
+    np.testing.assert_allclose(zt.grad.cpu().numpy(), dX, rtol=1e-5, atol=1e-7 * np.abs(dX).max())
+    np.testing.assert_allclose(vq.codebook.weight.grad.cpu().numpy(), dE, rtol=1e-4, atol=1e-6 * np.abs(dE).max())
+
+
+def test_trained_like_latents_use_single_candidate_shortlists():
+    """Clustered latents (codeword + noise): the shortlist is a single code for almost every frame and nothing falls back."""
+    K, D = 2048, 128
+    cb = seeded(1, (K, D))
+    pick = np.random.default_rng(2).integers(0, K, 4 * 2048)
+    rows = cb[pick] + seeded(3, (pick.size, D), 0.1)
+    z = np.ascontiguousarray(rows.reshape(4, 2048, D).transpose(0, 2, 1))
+    idx, _, _ = F.vq_forward(torch.from_numpy(z).to(DEV), torch.from_numpy(cb).to(DEV), precision="bf16", want_q=False)
+    c = F.debug_counters()
+    assert np.array_equal(idx.cpu().numpy(), pick)
+    assert c["fallback"] == 0 and c["rescored"] < 0.01 * pick.size
+
+
+# ----------------------------------------------------------------------------------------------- edge semantics
+def test_nan_and_inf_rows_follow_torch_argmin_semantics():
+    """vector_quantizer.py:37 inherits torch.argmin: a NaN distance wins; +inf rows give index 0."""
+    B, D, W, K = 1, 32, 64, 300
+    z = seeded(1, (B, D, W))
+    cb = seeded(2, (K, D))
+    z[0, 3, 5] = np.nan
+    z[0, 0, 9] = np.inf
+    d = O.distances(O.bcw_to_rows(z), cb)
+    want = O.argmin_first(d)
+    for precision in PRECISIONS:
+        idx, _, _ = F.vq_forward(torch.from_numpy(z).to(DEV), torch.from_numpy(cb).to(DEV), precision=precision, want_q=False)
+        got = idx.cpu().numpy()
+        assert got[5] == want[5] == 0 and got[9] == want[9]
+        clean = np.ones(W, bool); clean[[5, 9]] = False
+        assert np.array_equal(got[clean], want[clean])
+    cbn = cb.copy(); cbn[17, 4] = np.nan     # NaN codeword: every distance row has a NaN at 17 -> index 17 everywhere
+    zc = seeded(3, (B, D, W))
+    for precision in PRECISIONS:
+        idx, _, _ = F.vq_forward(torch.from_numpy(zc).to(DEV), torch.from_numpy(cbn).to(DEV), precision=precision, want_q=False)
+        assert (idx == 17).all()
+
+
+def test_duplicate_codes_pick_lowest_index():
+    K, D = 512, 64
+    cb = seeded(4, (K, D)); cb[256:] = cb[:256]
+    z = seeded(5, (2, D, 700))
+    for precision in PRECISIONS:
+        idx, _, _ = F.vq_forward(torch.from_numpy(z).to(DEV), torch.from_numpy(cb).to(DEV), precision=precision, want_q=False)
+        assert int(idx.max()) < 256
+
+
+def test_non_contiguous_input_no_grad_and_eval():
+    vq = vq_b200.VectorQuantizer(256, 64, 0.25).to(DEV).eval()
+    base = torch.randn(2, 500, 64, device=DEV)
+    x = base.permute(0, 2, 1)                 # BCW view of BWC storage
+    assert not x.is_contiguous()
+    with torch.no_grad():
+        a = vq(x)
+        b = vq(x.contiguous())
+    assert torch.equal(a[5], b[5]) and torch.equal(a[2], b[2]) and a[2].is_contiguous()
+    assert not a[0].requires_grad and not a[2].requires_grad
+
+
+def test_detect_anomaly_and_sparse_encodings():
+    vq = vq_b200.VectorQuantizer(128, 32, 0.5, dense_encodings=False).to(DEV)
+    x = torch.randn(2, 32, 300, device=DEV, requires_grad=True)
+    with torch.autograd.detect_anomaly():          # configs/debug/default.yaml:26
+        emb, com, q, ppl, enc, idx = vq(x)
+        (emb + com + q.square().mean()).backward()
+    assert enc.is_sparse and enc.shape == (600, 128)
+    assert torch.equal(enc.to_dense().argmax(1), idx.reshape(-1))
+    assert torch.isfinite(x.grad).all() and torch.isfinite(vq.codebook.weight.grad).all()
+
+
+def test_cabi_argument_errors_on_device():
+    z = torch.zeros(1, 24, 8, device=DEV)          # D % 16 != 0
+    with pytest.raises(_lib.VqbError) as ei:
+        F.vq_forward(z, torch.zeros(16, 24, device=DEV))
+    assert ei.value.code == -2
+    z = torch.zeros(1, 32, 8, device=DEV)
+    ws = torch.empty(64, dtype=torch.uint8, device=DEV)
+    with pytest.raises(_lib.VqbError) as ei:
+        F.vq_forward(z, torch.zeros(16, 32, device=DEV), workspace=ws)
+    assert ei.value.code == -4
+
+
+# ----------------------------------------------------------------------------------------------- helpers around the path
+def test_onehot_gather_window_match_oracle():
+    K, D, B, Lq = 300, 48, 3, 1100
+    cb = seeded(6, (K, D))
+    idx = np.random.default_rng(7).integers(0, K, B * Lq)
+    it = torch.from_numpy(idx).to(DEV)
+    enc = F.onehot(it, K).cpu().numpy()
+    want = np.zeros((B * Lq, K), np.float32); want[np.arange(B * Lq), idx] = 1
+    assert np.array_equal(enc, want)
+    deq = F.gather(torch.from_numpy(cb).to(DEV), it, B, Lq).cpu().numpy()
+    assert np.array_equal(deq, O.rows_to_bcw(cb[idx], B, Lq))
+    tok, mask = F.window_indices(it, B, window=512)
+    wt, wm = O.window_indices(idx, B, 512)
+    assert np.array_equal(tok.cpu().numpy(), wt) and np.array_equal(mask.cpu().numpy(), wm)
+
+
+def test_host_buffer_path_matches_device_path():
+    B, D, W, K = 6, 64, 1500, 512
+    z = torch.from_numpy(seeded(8, (B, D, W))).pin_memory()
+    cb = torch.from_numpy(seeded(9, (K, D))).pin_memory()
+    idx_d, _, stats_d = F.vq_forward(z.to(DEV), cb.to(DEV), precision="bf16", want_q=False, want_resid=True)
+    idx_h, stats_h = F.vq_forward_host(z, cb, precision="bf16", want_resid=True, chunk_batches=4)   # 2 chunks: 4 + 2
+    assert torch.equal(idx_h, idx_d.cpu())
+    sd, sh = stats_d.cpu().numpy(), stats_h.numpy()
+    assert np.array_equal(sd[:K], sh[:K])
+    np.testing.assert_allclose(sh[K:], sd[K:], rtol=1e-4, atol=1e-3)
+    _lib.check("vqb_host_release", _lib.lib().vqb_host_release())
+
+
+# ----------------------------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("B,D,W,K", [(64, 64, 16384, 1024), (16, 256, 16384, 8192)])
+def test_full_size_properties(B, D, W, K):
+    """BASELINE.json config 2 (N = 2^20) and a 2^18-frame slice of config 3: size-independent properties.
+    (a) bf16 shortlist path and exact fp32 path give identical indices; (b) histogram sums to N;
+    (c) idempotence: quantising the gathered codewords returns the same indices with zero loss;
+    (d) a random sample of frames agrees with the oracle."""
+    g = torch.Generator(device=DEV).manual_seed(42)
+    z = torch.randn(B, D, W, device=DEV, generator=g)
+    cb = torch.randn(K, D, device=DEV, generator=g)
+    N = B * W
+    idx_b, _, st_b = F.vq_forward(z, cb, precision="bf16", want_q=False)
+    counters = F.debug_counters()
+    idx_f, _, st_f = F.vq_forward(z, cb, precision="fp32", want_q=False)
+    assert torch.equal(idx_b, idx_f), f"{int((idx_b != idx_f).sum())} frames differ between bf16-shortlist and fp32 paths"
+    assert float(st_b[:K].sum()) == N and torch.equal(st_b[:K], st_f[:K])
+    assert counters["fallback"] < 0.01 * N, counters
+    codes = F.gather(cb, idx_b, B, W)
+    idx_2, q2, st_2 = F.vq_forward(codes, cb, precision="bf16", want_q=True)
+    assert torch.equal(idx_2, idx_b) and float(st_2[K + K * D]) == 0.0 and torch.equal(q2, codes)
+    pick = np.random.default_rng(0).choice(N, 2048, replace=False)
+    rows = z.permute(0, 2, 1).reshape(N, D)[torch.from_numpy(pick).to(DEV)].cpu().numpy()
+    sub = np.ascontiguousarray(rows.T[None])           # [1, D, 2048]
+    ref = O.vq_forward(sub, cb.cpu().numpy(), 0.25)
+    assert_index_parity(idx_b.cpu().numpy()[pick], sub, cb.cpu().numpy(), ref.indices, ref.margin, ref.eps)
