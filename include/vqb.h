@@ -122,6 +122,13 @@ VQB_API int vqb_debug_counters(const void* workspace, int64_t* counters_out_host
 VQB_API int vqb_debug_tc_scores(const float* z_bcw, const float* codebook, int B, int D, int64_t W, int K, int flags,
                         float* scores_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Number of this library's kernel launches since the last reset (bench.py's `gpu_launches`). */
+VQB_API long long vqb_debug_launch_count(int reset);
+/* CUDA-event timing of the dominant kernel (tc_search_kernel) on its launching stream: enable, run, then read the summed
+ * duration and launch count (bench.py's roofline leg).  At most 512 launches are recorded per enable. */
+VQB_API int vqb_debug_kernel_timing(int enable);
+VQB_API int vqb_debug_kernel_time_ms(double* total_ms, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

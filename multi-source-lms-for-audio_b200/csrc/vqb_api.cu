@@ -21,6 +21,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     return (int)e;
 }
 
+static long long g_launches = 0;
+void note_launch(int n) { g_launches += n; }
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 WsLayout ws_layout(int64_t N, int K, int D, int flags) {
@@ -238,6 +241,12 @@ int vqb_window_indices(const int64_t* idx, int B, int64_t L, int window, int64_t
     if (B < 1 || L < 1 || window < 1) { set_error("vqb_window_indices: bad B/L/window"); return VQB_E_SHAPE; }
     VQB_CUDA(launch_window(idx, B, L, window, pad_id, tokens_out, mask_out, static_cast<cudaStream_t>(stream)), "window");
     return 0;
+}
+
+long long vqb_debug_launch_count(int reset) {
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
 }
 
 int vqb_debug_counters(const void* workspace, int64_t* counters_out_host) {

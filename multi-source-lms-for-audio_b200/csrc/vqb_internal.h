@@ -37,6 +37,7 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags);
 constexpr int kTailGridMax = 148 * 8;   // persistent grid of the fused tail kernel (sse partial slots)
 
 void set_error(const char* fmt, ...);
+void note_launch(int n = 1);                       // counts this library's kernel launches (vqb_debug_launch_count)
 int  cuda_fail(cudaError_t e, const char* what);   // records message, returns (int)e
 
 // ---- launchers (vqb_kernels.cu) -------------------------------------------------------------------------------

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restr
 cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb, WsMeta* meta,
                                  cudaStream_t s) {
     codebook_prep_kernel<<<(K_pad + 7) / 8, 256, 0, s>>>(codebook, K, K_pad, D, e2, eb, meta);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -144,6 +145,7 @@ cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int
     const int64_t N = (int64_t)B * W;
     const size_t smem = (size_t)32 * (D + 2) * 2 + 2 * 8 * 32 * 4;
     latent_prep_bf16_kernel<<<(unsigned)((N_pad + 31) / 32), 256, smem, s>>>(z, D, W, N, N_pad, xb, band, meta);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -269,6 +271,7 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
     if (grid < 1) grid = 1;
     exact_search_kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, rows, row_count, idx32, cand_cnt,
                                                           cand_idx);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -419,6 +422,7 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
     else
         tail_kernel<false><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, idx32, cand_cnt, cand_idx, idx_out, q_out,
                                                              counts, nullptr, part, meta);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -450,6 +454,7 @@ cudaError_t launch_pack_stats(const int* counts, const float* sse_partials, int 
                               float* stats, bool accumulate, cudaStream_t s) {
     pack_stats_kernel<<<(K + 255) / 256, 256, 0, s>>>(counts, reinterpret_cast<const double*>(sse_partials), n_partials, N, K, D,
                                                       stats, accumulate);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -480,6 +485,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const float* __restrict_
 
 cudaError_t launch_finalize(const float* stats, int K, int D, float beta, float* losses, cudaStream_t s) {
     finalize_kernel<<<1, 1024, 0, s>>>(stats, K, D, beta, losses);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -533,6 +539,7 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
     int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
     if (grid < 1) grid = 1;
     backward_dx_kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, dX);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -551,6 +558,7 @@ cudaError_t launch_backward_de(const float* stats, const float* g_e, int K, int 
     size_t grid = (total + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
     backward_de_kernel<<<(unsigned)grid, 256, 0, s>>>(stats, g_e, K, D, dE);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -564,6 +572,7 @@ cudaError_t launch_onehot(const int64_t* idx, int64_t N, int K, float* out, cuda
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * K * sizeof(float), s);
     if (e != cudaSuccess) return e;
     onehot_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(idx, N, K, out);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -605,6 +614,7 @@ cudaError_t launch_gather(const float* codebook, const int64_t* idx, int B, int 
     int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
     if (grid < 1) grid = 1;
     gather_kernel<<<(unsigned)grid, 256, smem, s>>>(codebook, idx, D, W, N, out);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -629,6 +639,7 @@ cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int6
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
     window_kernel<<<(unsigned)grid, 256, 0, s>>>(idx, L, window, n_win, total, pad_id, tokens, mask);
+    note_launch();
     return cudaGetLastError();
 }
 

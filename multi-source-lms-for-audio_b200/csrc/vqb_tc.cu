@@ -454,6 +454,27 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 
 }  // namespace tc
 
+// ---- optional CUDA-event timing of the dominant kernel, on the launching stream (bench.py's roofline leg) -------
+struct TimingSlot { cudaEvent_t start, stop; };
+static bool g_timing = false;
+static TimingSlot g_slots[512];
+static int g_slots_used = 0, g_slots_made = 0;
+
+static TimingSlot* timing_begin(cudaStream_t s) {
+    if (!g_timing || g_slots_used >= 512) return nullptr;
+    if (g_slots_used >= g_slots_made) {
+        if (cudaEventCreate(&g_slots[g_slots_made].start) != cudaSuccess || cudaEventCreate(&g_slots[g_slots_made].stop) != cudaSuccess)
+            return nullptr;
+        ++g_slots_made;
+    }
+    TimingSlot* t = &g_slots[g_slots_used++];
+    cudaEventRecord(t->start, s);
+    return t;
+}
+static void timing_end(TimingSlot* t, cudaStream_t s) {
+    if (t) cudaEventRecord(t->stop, s);
+}
+
 int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const float* e2, const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
                      float* scores_dbg, cudaStream_t s) {
@@ -481,11 +502,39 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     const int num_m_tiles = (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
     const int grid = num_m_tiles < sms ? num_m_tiles : sms;
+    TimingSlot* slot = timing_begin(s);
     tc_search_kernel<<<grid, NUM_THREADS, smem, s>>>(mx, me, e2, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, K,
                                                      cand_cnt, cand_idx, fallback_rows, meta, scores_dbg);
     cudaError_t e = cudaGetLastError();
+    timing_end(slot, s);
+    note_launch();
     if (e != cudaSuccess) return cuda_fail(e, "tc_search_kernel launch");
     return 0;
 }
 
 }  // namespace vqb
+
+extern "C" {
+// enable != 0: record a CUDA-event pair around every tc_search_kernel launch from now on (and forget earlier ones)
+int vqb_debug_kernel_timing(int enable) {
+    vqb::g_timing = enable != 0;
+    vqb::g_slots_used = 0;
+    return 0;
+}
+// total milliseconds and number of timed tc_search_kernel launches since timing was enabled (synchronises the events)
+int vqb_debug_kernel_time_ms(double* total_ms, int* launches) {
+    if (!total_ms || !launches) { vqb::set_error("vqb_debug_kernel_time_ms: NULL output"); return VQB_E_NULL; }
+    double t = 0.0;
+    for (int i = 0; i < vqb::g_slots_used; ++i) {
+        cudaError_t e = cudaEventSynchronize(vqb::g_slots[i].stop);
+        if (e != cudaSuccess) return vqb::cuda_fail(e, "cudaEventSynchronize");
+        float ms = 0.f;
+        e = cudaEventElapsedTime(&ms, vqb::g_slots[i].start, vqb::g_slots[i].stop);
+        if (e != cudaSuccess) return vqb::cuda_fail(e, "cudaEventElapsedTime");
+        t += ms;
+    }
+    *total_ms = t;
+    *launches = vqb::g_slots_used;
+    return 0;
+}
+}

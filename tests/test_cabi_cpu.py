@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "vqb.h")).read()
-    return sorted(set(re.findall(r"VQB_API\s+(?:const\s+char\*|int)\s+(vqb_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"VQB_API\s+(?:const\s+char\*|int|long long)\s+(vqb_\w+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -84,3 +84,19 @@ def test_window_export_matches_bert_windowing():
     assert mask[:, :21].all() and mask[:, 21, :248].all() and not mask[:, 21, 248:].any()
     assert np.array_equal(tok.reshape(2, -1)[:, :11000], idx.reshape(2, 11000))
     assert (tok[:, 21, 248:] == 0).all()
+
+
+def test_torch_cpu_port_matches_reference(golden):
+    """oracle/ref_port_torch.py (the timed CPU baseline) reproduces the reference outputs."""
+    import torch
+    from oracle.ref_port_torch import vq_forward_chunked
+    g = golden
+    mse, com, q, ppl, idx = vq_forward_chunked(torch.from_numpy(g["z"]), torch.from_numpy(g["codebook"]), float(g["beta"]), chunk=200)
+    fwd = O.vq_forward(g["z"], g["codebook"], float(g["beta"]))
+    n_bad = check_indices(idx.numpy(), g, fwd)
+    np.testing.assert_allclose(mse, g["embedding_loss"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(com, g["commitment_loss"], rtol=LOSS_RTOL)
+    if n_bad == 0:
+        np.testing.assert_allclose(ppl, g["perplexity"], rtol=LOSS_RTOL)
+        if "quantized" in g:
+            assert np.array_equal(q.numpy(), g["quantized"])
