@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) exact_search_kernel(const float* __restri
             if (tx == 0) {
                 const int n = rown[ty * 4 + i];
                 if (n >= 0) {
-                    if (rows) { cand_cnt[n] = 1; cand_idx[(size_t)n * kCandMax] = (uint16_t)bi[i]; }
+                    if (rows) { cand_cnt[n] = kCandFinal; cand_idx[(size_t)n * kCandMax] = (uint16_t)bi[i]; }
                     else idx32[n] = bi[i];
                 }
             }
@@ -286,7 +286,7 @@ constexpr int TL_J = 16;              // D <= 512 -> at most 16 elements per lan
 
 template <bool kResid>
 __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
-                                                   const float* __restrict__ e2, int D, int64_t W, int64_t N,
+                                                   const float* __restrict__ e2, int D, int64_t W, int64_t N, int K,
                                                    const int* __restrict__ idx32, const uint8_t* __restrict__ cand_cnt,
                                                    const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
                                                    float* __restrict__ q_out, int* __restrict__ counts,
@@ -324,32 +324,63 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ z, 
             } else {
                 const int cnt = cand_cnt[n];
                 const uint16_t* c = cand_idx + (size_t)n * kCandMax;
-                k = c[0];
-                if (cnt > 1) {
+                if (cnt == kCandFinal) {
+                    k = c[0];                                  // settled by the exact fallback search
+                } else {
+                    // fp32 rescoring of the shortlisted chunks (8 consecutive codes each) in the reference's op order
                     float x2 = 0.f;
 #pragma unroll
                     for (int j = 0; j < TL_J; ++j) x2 = __fadd_rn(x2, __fmul_rn(xv[j], xv[j]));
                     x2 = warp_sum(x2);
+                    const int sub = (lane >> 2) & 7;           // which code of the chunk this lane ends up owning
                     float bd = 0.f;
                     int bk = -1;
                     for (int ci = 0; ci < cnt; ++ci) {
-                        const int kc = c[ci];
-                        const float* er = E + (size_t)kc * D;
-                        float dot = 0.f;
+                        const int k0 = (int)c[ci] * kCandChunk;
+                        const float* er0 = E + (size_t)k0 * D;
+                        float p[kCandChunk];
 #pragma unroll
-                        for (int j = 0; j < TL_J; ++j) {
-                            const int d = lane + 32 * j;
-                            if (d < D) dot = fmaf(xv[j], er[d], dot);
+                        for (int cc = 0; cc < kCandChunk; ++cc) {
+                            p[cc] = 0.f;
+                            if (k0 + cc < K) {
+#pragma unroll
+                                for (int j = 0; j < TL_J; ++j) {
+                                    const int d = lane + 32 * j;
+                                    if (d < D) p[cc] = fmaf(xv[j], er0[(size_t)cc * D + d], p[cc]);
+                                }
+                            }
                         }
-                        dot = warp_sum(dot);
-                        const float dist = ref_distance(x2, e2[kc], dot);
-                        if (better(dist, kc, bd, bk)) { bd = dist; bk = kc; }
+                        // 8 dot products reduced over the warp with 9 shuffles: halve the set each step
+                        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                        float q4[4], q2[2];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float send = b4 ? p[i] : p[i + 4], keep = b4 ? p[i + 4] : p[i];
+                            q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float send = b3 ? q4[i] : q4[i + 2], keep = b3 ? q4[i + 2] : q4[i];
+                            q2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+                        float dot = (b2 ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? q2[0] : q2[1], 4);
+                        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                        const int kc = k0 + sub;
+                        if (kc < K) {
+                            const float dist = ref_distance(x2, e2[kc], dot);
+                            if (better(dist, kc, bd, bk)) { bd = dist; bk = kc; }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {         // argmin over the 8 lane groups
+                        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                        if (ok >= 0 && better(od, ok, bd, bk)) { bd = od; bk = ok; }
                     }
                     k = bk;
-                    n_resc += 1;
+                    n_resc += (cnt > 1);
                     n_short += cnt;
-                } else {
-                    n_short += 1;
                 }
             }
             const float* er = E + (size_t)k * D;
@@ -400,7 +431,6 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ z, 
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                         int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, cudaStream_t s) {
-    (void)K;
     const int64_t N = (int64_t)B * W;
     const size_t smem = (size_t)D * TL_LD * 4;
     static bool attr_done = false;
@@ -417,10 +447,10 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
     if (e != cudaSuccess) return e;
     double* part = reinterpret_cast<double*>(sse_partials);
     if (resid)
-        tail_kernel<true><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, idx32, cand_cnt, cand_idx, idx_out, q_out,
+        tail_kernel<true><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out,
                                                             counts, resid, part, meta);
     else
-        tail_kernel<false><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, idx32, cand_cnt, cand_idx, idx_out, q_out,
+        tail_kernel<false><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out,
                                                              counts, nullptr, part, meta);
     note_launch();
     return cudaGetLastError();

@@ -5,8 +5,9 @@
 // replaces `distances` + `argmin` of src/model/components/vector_quantizer.py:32-37.  The N x K score matrix never
 // leaves the SM: tcgen05.mma accumulates a 128-frame x 256-code tile in TMEM, epilogue warps pull it back with
 // tcgen05.ld, add |e_k|^2 and keep, per frame, the codes whose score is within a rigorous guard band of the running
-// minimum (at most 4 per column half).  The fused tail kernel then rescoring those few codes in fp32 in the reference's
-// operation order decides the index; frames whose shortlist overflowed go to the exact fp32 search.
+// minimum.  A shortlist entry is a chunk of 8 consecutive codes (at most 4 chunks per column half); the fused tail kernel
+// then rescores the few shortlisted chunks in fp32 in the reference's operation order, which decides the index.  Frames
+// whose shortlist overflowed go to the exact fp32 search.
 //
 // Structure (one persistent CTA per SM, 384 threads, warp-specialised):
 //   warp 0      TMA producer: latent tile A (128 frames x D, resident per M tile) and codebook tiles B
@@ -151,7 +152,7 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 // ---------------------------------------------------------------------------------------------- shortlist
 struct Shortlist {
     float v[4];     // ascending scores
-    int   i[4];     // codes (-1 = empty)
+    int   i[4];     // chunk ids = code / 8 (-1 = empty)
     float dropped;  // smallest score ever pushed out of / refused by the list
     __device__ __forceinline__ void reset() {
 #pragma unroll
@@ -175,33 +176,36 @@ struct Shortlist {
     }
 };
 
-// One 32-column slab of scores for this thread's frame.  Fast path: 8 FFMA + 4 FMNMX3 + 1 compare per 8 codes.
-__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int code0, float band,
+// One 32-column slab of scores for this thread's frame.  Shortlist entries are CHUNKS of 8 consecutive codes, keyed by
+// the chunk's minimum score.  Fast path per slab: 32 FFMA + 18 FMNMX3 + one compare; only when the slab minimum is
+// within the band of the running minimum (rare after the first tiles) are the four chunk minima looked at one by one.
+__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int chunk0, float band,
                                           float& thr, Shortlist& sl) {
+    float t[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const float4 ea = *reinterpret_cast<const float4*>(e2s + g * 8);
         const float4 eb = *reinterpret_cast<const float4*>(e2s + g * 8 + 4);
-        float s[8];
-        s[0] = fmaf(-2.f, __uint_as_float(r[g * 8 + 0]), ea.x);
-        s[1] = fmaf(-2.f, __uint_as_float(r[g * 8 + 1]), ea.y);
-        s[2] = fmaf(-2.f, __uint_as_float(r[g * 8 + 2]), ea.z);
-        s[3] = fmaf(-2.f, __uint_as_float(r[g * 8 + 3]), ea.w);
-        s[4] = fmaf(-2.f, __uint_as_float(r[g * 8 + 4]), eb.x);
-        s[5] = fmaf(-2.f, __uint_as_float(r[g * 8 + 5]), eb.y);
-        s[6] = fmaf(-2.f, __uint_as_float(r[g * 8 + 6]), eb.z);
-        s[7] = fmaf(-2.f, __uint_as_float(r[g * 8 + 7]), eb.w);
-        float t = fminf(fminf(s[0], s[1]), s[2]);
-        t = fminf(fminf(t, s[3]), s[4]);
-        t = fminf(fminf(t, s[5]), s[6]);
-        t = fminf(t, s[7]);
-        if (t < thr) {   // rare after the first few tiles: some code here is within the band of the running minimum
+        const float s0 = fmaf(-2.f, __uint_as_float(r[g * 8 + 0]), ea.x);
+        const float s1 = fmaf(-2.f, __uint_as_float(r[g * 8 + 1]), ea.y);
+        const float s2 = fmaf(-2.f, __uint_as_float(r[g * 8 + 2]), ea.z);
+        const float s3 = fmaf(-2.f, __uint_as_float(r[g * 8 + 3]), ea.w);
+        const float s4 = fmaf(-2.f, __uint_as_float(r[g * 8 + 4]), eb.x);
+        const float s5 = fmaf(-2.f, __uint_as_float(r[g * 8 + 5]), eb.y);
+        const float s6 = fmaf(-2.f, __uint_as_float(r[g * 8 + 6]), eb.z);
+        const float s7 = fmaf(-2.f, __uint_as_float(r[g * 8 + 7]), eb.w);
+        float m = fminf(fminf(s0, s1), s2);
+        m = fminf(fminf(m, s3), s4);
+        m = fminf(fminf(m, s5), s6);
+        t[g] = fminf(m, s7);
+    }
+    const float slab_min = fminf(fminf(fminf(t[0], t[1]), t[2]), t[3]);
+    if (slab_min < thr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (s[j] < thr) {
-                    sl.insert(s[j], code0 + g * 8 + j);
-                    thr = sl.v[0] + band;
-                }
+        for (int g = 0; g < 4; ++g) {
+            if (t[g] < thr) {
+                sl.insert(t[g], chunk0 + g);
+                thr = sl.v[0] + band;
             }
         }
     }
@@ -354,15 +358,15 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (row < N) dump_slab(rb, e2s + 96, code0 + 96, K, row_out);
                 } else {
                     tmem_ld32(taddr + 32, rb);
-                    scan_slab(ra, e2s, code0, band, thr, sl);
+                    scan_slab(ra, e2s, code0 >> 3, band, thr, sl);
                     tmem_ld_wait(rb);
                     tmem_ld32(taddr + 64, ra);
-                    scan_slab(rb, e2s + 32, code0 + 32, band, thr, sl);
+                    scan_slab(rb, e2s + 32, (code0 + 32) >> 3, band, thr, sl);
                     tmem_ld_wait(ra);
                     tmem_ld32(taddr + 96, rb);
-                    scan_slab(ra, e2s + 64, code0 + 64, band, thr, sl);
+                    scan_slab(ra, e2s + 64, (code0 + 64) >> 3, band, thr, sl);
                     tmem_ld_wait(rb);
-                    scan_slab(rb, e2s + 96, code0 + 96, band, thr, sl);
+                    scan_slab(rb, e2s + 96, (code0 + 96) >> 3, band, thr, sl);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -382,7 +386,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const float gmin = fminf(sl.v[0], other[0]);
                 const float cutoff = gmin + band;
                 int cnt = 0;
-                unsigned long long lo = 0ull, hi = 0ull;   // up to 8 codes of 16 bits, own half first
+                unsigned long long lo = 0ull, hi = 0ull;   // up to 8 chunk ids of 16 bits, own half first
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (sl.i[j] >= 0 && sl.v[j] <= cutoff) { lo |= (unsigned long long)sl.i[j] << (16 * cnt); ++cnt; }
@@ -400,7 +404,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 hi = hi_hi;
                 const bool overflow = force_fallback || cnt == 0 || !(band < INFINITY) || fminf(sl.dropped, other[8]) <= cutoff;
                 if (overflow) {
-                    cand_cnt[row] = 0;
+                    cand_cnt[row] = kCandFinal;   // the exact search fills in the final code
                     fallback_rows[atomicAdd(&meta->fallback_count, 1)] = (int)row;
                     atomicAdd(&meta->fallback_total, 1ull);
                 } else {

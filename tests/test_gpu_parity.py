@@ -264,8 +264,18 @@ def test_full_size_properties(B, D, W, K):
     idx_b, _, st_b = F.vq_forward(z, cb, precision="bf16", want_q=False)
     counters = F.debug_counters()
     idx_f, _, st_f = F.vq_forward(z, cb, precision="fp32", want_q=False)
-    assert torch.equal(idx_b, idx_f), f"{int((idx_b != idx_f).sum())} frames differ between bf16-shortlist and fp32 paths"
-    assert float(st_b[:K].sum()) == N and torch.equal(st_b[:K], st_f[:K])
+    # Both paths score in fp32 in the reference's op order but sum the dot product in different orders, so they may
+    # resolve a near-tie differently: any differing frame must be a near-tie under the stated epsilon.
+    diff = torch.nonzero(idx_b != idx_f).reshape(-1)
+    assert diff.numel() <= max(2, N // 100000), f"{diff.numel()} frames differ between bf16-shortlist and fp32 paths"
+    if diff.numel():
+        rows_d = z.permute(0, 2, 1).reshape(N, D)[diff].cpu().numpy()
+        cbn = cb.cpu().numpy()
+        dd = O.distances(rows_d, cbn)
+        eps_d = O.near_tie_eps((rows_d ** 2).sum(1), float((cbn ** 2).sum(1).max()))
+        ar = np.arange(diff.numel())
+        assert np.all(np.abs(dd[ar, idx_b[diff].cpu().numpy()] - dd[ar, idx_f[diff].cpu().numpy()]) <= eps_d)
+    assert float(st_b[:K].sum()) == N and float(st_f[:K].sum()) == N
     assert counters["fallback"] < 0.01 * N, counters
     codes = F.gather(cb, idx_b, B, W)
     idx_2, q2, st_2 = F.vq_forward(codes, cb, precision="bf16", want_q=True)
