@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-resid", action="store_true", help="diagnostic: skip the per-code residual statistics")
+    ap.add_argument("--no-q", action="store_true", help="diagnostic: index export only (no quantized output)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -177,7 +179,7 @@ def main():
     lib = _lib.lib()
 
     def step():
-        idx, q, st = F.vq_forward(z, codebook, precision=args.precision, want_q=True, want_resid=True, stats=stats)
+        idx, q, st = F.vq_forward(z, codebook, precision=args.precision, want_q=not args.no_q, want_resid=not args.no_resid, stats=stats)
         if comm is not None:
             comm.allreduce(st)
         losses = F.vq_finalize(st, K, D, BETA)

@@ -8,9 +8,8 @@
 
 namespace vqb {
 
-constexpr int kCandMax   = 8;     // shortlist slots per frame written by the tensor-core search (chunk ids)
-constexpr int kCandChunk = 8;     // codes per shortlisted chunk: chunk c covers codes [8c, 8c+8)
-constexpr int kCandFinal = 255;   // cand_cnt marker: slot 0 holds the final CODE (written by the exact fallback search)
+constexpr int kCandMax   = 16;    // uint16 slots per frame in cand_idx (32 B rows); the tensor-core search fills <= 12
+constexpr int kCandFinal = 255;   // cand_cnt marker: slot 0 holds the final code (written by the exact fallback search)
 constexpr int kTileCodes = 256;   // codes per tcgen05 N tile; |e|^2 and the bf16 codebook copy are padded to this
 constexpr int kTileRows  = 128;   // frames per tcgen05 M tile; the bf16 latent copy is padded to this
 

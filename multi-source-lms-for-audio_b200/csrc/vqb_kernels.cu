@@ -276,25 +276,72 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ fused tail
-// Per frame: (a) settle the index - either given (exact search) or by rescoring the shortlist in fp32 in the reference's
-// op order, ties -> lowest index; (b) gather the codeword (vector_quantizer.py:42 as a gather), (c) SSE for both MSE
-// losses (:45-46), (d) straight-through value fl(x + fl(q - x)) written back in BCW (:48,:52), (e) code histogram (:49)
-// and, for training, the per-code residual sums that give the codebook gradient.  Latents are read exactly once.
+// Per frame: (a) settle the index - given (exact search), unique shortlist entry, or by rescoring the shortlisted codes
+// in fp32 in the reference's op order, ties -> lowest index; (b) gather the codeword (vector_quantizer.py:42 as a
+// gather), (c) SSE for both MSE losses (:45-46), (d) straight-through value fl(x + fl(q - x)) written back in BCW
+// (:48,:52), (e) code histogram (:49) and, for training, the per-code residual sums that give the codebook gradient.
+// Latents are read exactly once.
+//
+// Tile = 32 frames x D in shared memory, frame-major with rows of D+4 floats: the transposing global<->shared phases
+// move one float4 (4 consecutive dims of one frame) per thread, the per-frame phase reads float4 rows - both are
+// bank-conflict free - and the codebook rows, residual atomics (red.v4) and shared accesses are all 16 bytes wide.
+// LPF lanes cooperate on one frame (32 / LPF frames per warp at a time), each lane owning 4*J dims.
 constexpr int TL_F = 32;              // frames per tile
-constexpr int TL_LD = TL_F + 1;       // padded: column (fixed d) and row (fixed frame) accesses are both conflict-free
-constexpr int TL_J = 16;              // D <= 512 -> at most 16 elements per lane
 
-template <bool kResid>
-__global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <int LPF>
+__device__ __forceinline__ float group_sum(float v) {   // sum over the LPF lanes that share a frame
+#pragma unroll
+    for (int o = LPF / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// coalesced BCW -> frame-major shared tile: thread = (frame = tid & 31, dim group = tid >> 5), 4 dims per access
+__device__ __forceinline__ void tile_load(float* Xs, int ld, const float* __restrict__ z, size_t col, int64_t W, int D, bool valid) {
+    const int f = threadIdx.x & 31;
+    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            const float* p = z + col + (size_t)d0 * W;
+            v.x = ld_stream(p);
+            v.y = ld_stream(p + W);
+            v.z = ld_stream(p + 2 * W);
+            v.w = ld_stream(p + 3 * W);
+        }
+        *reinterpret_cast<float4*>(Xs + f * ld + d0) = v;
+    }
+}
+__device__ __forceinline__ void tile_store(const float* Xs, int ld, float* __restrict__ out, size_t col, int64_t W, int D, bool valid) {
+    const int f = threadIdx.x & 31;
+    if (!valid) return;
+    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(Xs + f * ld + d0);
+        float* p = out + col + (size_t)d0 * W;
+        st_stream(p, v.x);
+        st_stream(p + W, v.y);
+        st_stream(p + 2 * W, v.z);
+        st_stream(p + 3 * W, v.w);
+    }
+}
+
+template <int LPF, int J, bool kResid>
+__global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                    const float* __restrict__ e2, int D, int64_t W, int64_t N, int K,
                                                    const int* __restrict__ idx32, const uint8_t* __restrict__ cand_cnt,
                                                    const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
                                                    float* __restrict__ q_out, int* __restrict__ counts,
                                                    float* __restrict__ resid, double* __restrict__ sse_partials,
                                                    WsMeta* meta) {
-    extern __shared__ __align__(16) float Xs[];   // [D][33]
+    extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
     __shared__ double red[8];
+    constexpr int FPW = 32 / LPF;                 // frames a warp works on at once
+    constexpr int ITER = (TL_F / 8) / FPW;        // rounds per warp and tile
+    static_assert(ITER >= 1, "a warp must own at least FPW frames of the tile");
+    const int ld = D + 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPF, sl = lane % LPF;
     float sse = 0.f, sse_c = 0.f;                 // Kahan-compensated per-thread SSE
     unsigned int n_resc = 0, n_short = 0;
 
@@ -304,112 +351,116 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ z, 
         int64_t b = 0, w = 0;
         if (valid) { b = nl / W; w = nl - b * W; }
         const size_t col = (size_t)b * D * W + w;
+        // shortlist headers of this warp's frames, requested before the tile load so their latency hides behind it
+        int cnt_r[ITER], k0_r[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int64_t n = tile * TL_F + warp * (TL_F / 8) + it * FPW + sub;
+            cnt_r[it] = 0;
+            k0_r[it] = 0;
+            if (n < N) {
+                if (idx32) { cnt_r[it] = kCandFinal; k0_r[it] = idx32[n]; }
+                else { cnt_r[it] = cand_cnt[n]; k0_r[it] = cand_idx[(size_t)n * kCandMax]; }
+            }
+        }
         __syncthreads();
-        for (int d = warp; d < D; d += 8) Xs[d * TL_LD + lane] = valid ? ld_stream(z + col + (size_t)d * W) : 0.f;
+        tile_load(Xs, ld, z, col, W, D, valid);
         __syncthreads();
 #pragma unroll 1
-        for (int fi = 0; fi < TL_F / 8; ++fi) {
-            const int f = warp * (TL_F / 8) + fi;
+        for (int it = 0; it < ITER; ++it) {
+            const int f = warp * (TL_F / 8) + it * FPW + sub;
             const int64_t n = tile * TL_F + f;
-            if (n >= N) break;
-            float xv[TL_J];
+            const bool live = n < N;
+            float4 xv[J];
 #pragma unroll
-            for (int j = 0; j < TL_J; ++j) {
-                const int d = lane + 32 * j;
-                xv[j] = (d < D) ? Xs[d * TL_LD + f] : 0.f;
+            for (int j = 0; j < J; ++j) {
+                const int d = 4 * sl + 4 * LPF * j;
+                xv[j] = (d < D) ? *reinterpret_cast<const float4*>(Xs + f * ld + d) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            int k;
-            if (idx32) {
-                k = idx32[n];
-            } else {
-                const int cnt = cand_cnt[n];
-                const uint16_t* c = cand_idx + (size_t)n * kCandMax;
-                if (cnt == kCandFinal) {
-                    k = c[0];                                  // settled by the exact fallback search
-                } else {
-                    // fp32 rescoring of the shortlisted chunks (8 consecutive codes each) in the reference's op order
-                    float x2 = 0.f;
+            int cnt = cnt_r[0], k = k0_r[0];          // register-resident select instead of dynamic indexing
 #pragma unroll
-                    for (int j = 0; j < TL_J; ++j) x2 = __fadd_rn(x2, __fmul_rn(xv[j], xv[j]));
-                    x2 = warp_sum(x2);
-                    const int sub = (lane >> 2) & 7;           // which code of the chunk this lane ends up owning
-                    float bd = 0.f;
-                    int bk = -1;
-                    for (int ci = 0; ci < cnt; ++ci) {
-                        const int k0 = (int)c[ci] * kCandChunk;
-                        const float* er0 = E + (size_t)k0 * D;
-                        float p[kCandChunk];
+            for (int u = 1; u < ITER; ++u) {
+                cnt = (it == u) ? cnt_r[u] : cnt;
+                k = (it == u) ? k0_r[u] : k;
+            }
+            const bool need = live && cnt != kCandFinal && cnt > 1;
+            if (__any_sync(0xffffffffu, need)) {
+                // fp32 rescoring of the shortlisted codes in the reference's op order (whole warp takes part in shuffles)
+                float x2 = 0.f;
 #pragma unroll
-                        for (int cc = 0; cc < kCandChunk; ++cc) {
-                            p[cc] = 0.f;
-                            if (k0 + cc < K) {
+                for (int j = 0; j < J; ++j) {
+                    x2 = __fadd_rn(x2, __fmul_rn(xv[j].x, xv[j].x));
+                    x2 = __fadd_rn(x2, __fmul_rn(xv[j].y, xv[j].y));
+                    x2 = __fadd_rn(x2, __fmul_rn(xv[j].z, xv[j].z));
+                    x2 = __fadd_rn(x2, __fmul_rn(xv[j].w, xv[j].w));
+                }
+                x2 = group_sum<LPF>(x2);
+                int cmax = need ? cnt : 0;
 #pragma unroll
-                                for (int j = 0; j < TL_J; ++j) {
-                                    const int d = lane + 32 * j;
-                                    if (d < D) p[cc] = fmaf(xv[j], er0[(size_t)cc * D + d], p[cc]);
-                                }
-                            }
-                        }
-                        // 8 dot products reduced over the warp with 9 shuffles: halve the set each step
-                        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-                        float q4[4], q2[2];
+                for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+                const uint16_t* cl = cand_idx + (size_t)(live ? n : 0) * kCandMax;
+                float bd = 0.f;
+                int bk = -1;
+                for (int ci = 0; ci < cmax; ++ci) {
+                    const bool act = need && ci < cnt;
+                    const int kc = act ? (int)cl[ci] : 0;
+                    const float* er = E + (size_t)kc * D;
+                    float dot = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float send = b4 ? p[i] : p[i + 4], keep = b4 ? p[i + 4] : p[i];
-                            q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const float send = b3 ? q4[i] : q4[i + 2], keep = b3 ? q4[i + 2] : q4[i];
-                            q2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                        }
-                        float dot = (b2 ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? q2[0] : q2[1], 4);
-                        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-                        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-                        const int kc = k0 + sub;
-                        if (kc < K) {
-                            const float dist = ref_distance(x2, e2[kc], dot);
-                            if (better(dist, kc, bd, bk)) { bd = dist; bk = kc; }
+                    for (int j = 0; j < J; ++j) {
+                        const int d = 4 * sl + 4 * LPF * j;
+                        if (d < D) {
+                            const float4 ev = *reinterpret_cast<const float4*>(er + d);
+                            dot = fmaf(xv[j].x, ev.x, dot);
+                            dot = fmaf(xv[j].y, ev.y, dot);
+                            dot = fmaf(xv[j].z, ev.z, dot);
+                            dot = fmaf(xv[j].w, ev.w, dot);
                         }
                     }
-#pragma unroll
-                    for (int o = 4; o < 32; o <<= 1) {         // argmin over the 8 lane groups
-                        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-                        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                        if (ok >= 0 && better(od, ok, bd, bk)) { bd = od; bk = ok; }
+                    dot = group_sum<LPF>(dot);
+                    if (act) {
+                        const float dist = ref_distance(x2, e2[kc], dot);
+                        if (better(dist, kc, bd, bk)) { bd = dist; bk = kc; }
                     }
+                }
+                if (need) {
                     k = bk;
-                    n_resc += (cnt > 1);
-                    n_short += cnt;
+                    if (sl == 0) { n_resc += 1; n_short += cnt; }
                 }
             }
-            const float* er = E + (size_t)k * D;
-            float fs = 0.f;
+            if (live && !need && sl == 0) n_short += 1;
+            if (live) {
+                const float* er = E + (size_t)k * D;
+                float fs = 0.f;
 #pragma unroll
-            for (int j = 0; j < TL_J; ++j) {
-                const int d = lane + 32 * j;
-                if (d < D) {
-                    const float q = er[d];
-                    const float diff = __fsub_rn(q, xv[j]);
-                    fs = fmaf(diff, diff, fs);
-                    Xs[d * TL_LD + f] = __fadd_rn(xv[j], diff);      // straight-through VALUE (vector_quantizer.py:48)
-                    if (kResid) atomicAdd(resid + (size_t)k * D + d, -diff);
+                for (int j = 0; j < J; ++j) {
+                    const int d = 4 * sl + 4 * LPF * j;
+                    if (d < D) {
+                        const float4 q = *reinterpret_cast<const float4*>(er + d);
+                        float4 df, st;
+                        df.x = __fsub_rn(q.x, xv[j].x); df.y = __fsub_rn(q.y, xv[j].y);
+                        df.z = __fsub_rn(q.z, xv[j].z); df.w = __fsub_rn(q.w, xv[j].w);
+                        fs = fmaf(df.x, df.x, fs); fs = fmaf(df.y, df.y, fs); fs = fmaf(df.z, df.z, fs); fs = fmaf(df.w, df.w, fs);
+                        st.x = __fadd_rn(xv[j].x, df.x); st.y = __fadd_rn(xv[j].y, df.y);      // straight-through VALUE (:48)
+                        st.z = __fadd_rn(xv[j].z, df.z); st.w = __fadd_rn(xv[j].w, df.w);
+                        *reinterpret_cast<float4*>(Xs + f * ld + d) = st;
+                        if (kResid) red_add_v4(resid + (size_t)k * D + d, -df.x, -df.y, -df.z, -df.w);
+                    }
                 }
-            }
-            {   // Kahan: sse += fs
-                const float y = fs - sse_c, t = sse + y;
-                sse_c = (t - sse) - y;
-                sse = t;
-            }
-            if (lane == 0) {
-                atomicAdd(counts + k, 1);
-                idx_out[n] = (int64_t)k;
+                {   // Kahan: sse += fs
+                    const float y = fs - sse_c, t = sse + y;
+                    sse_c = (t - sse) - y;
+                    sse = t;
+                }
+                if (sl == 0) {
+                    atomicAdd(counts + k, 1);
+                    idx_out[n] = (int64_t)k;
+                }
             }
         }
         if (q_out) {
             __syncthreads();
-            if (valid)
-                for (int d = warp; d < D; d += 8) st_stream(q_out + col + (size_t)d * W, Xs[d * TL_LD + lane]);
+            tile_store(Xs, ld, q_out, col, W, D, valid);
         }
     }
     double t = (double)sse - (double)sse_c;
@@ -422,38 +473,51 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ z, 
         for (int i = 0; i < 8; ++i) s += red[i];
         sse_partials[blockIdx.x] = s;
     }
-    if (lane == 0 && (n_resc | n_short)) {
+    if (n_resc | n_short) {
         atomicAdd(&meta->rescored, (unsigned long long)n_resc);
         atomicAdd(&meta->shortlisted, (unsigned long long)n_short);
     }
+}
+
+template <int LPF, int J>
+static cudaError_t launch_tail_t(const float* z, const float* codebook, const float* e2, int D, int64_t W, int64_t N, int K,
+                                 const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
+                                 int* counts, float* resid, double* part, int grid, WsMeta* meta, cudaStream_t s) {
+    const size_t smem = (size_t)TL_F * (D + 4) * 4;
+    cudaError_t e;
+    if (resid) {
+        if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+        tail_kernel<LPF, J, true><<<grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
+                                                          resid, part, meta);
+    } else {
+        if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+        tail_kernel<LPF, J, false><<<grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
+                                                           nullptr, part, meta);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                         int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, cudaStream_t s) {
     const int64_t N = (int64_t)B * W;
-    const size_t smem = (size_t)D * TL_LD * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e;
-        if ((e = cudaFuncSetAttribute(tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
-        attr_done = true;
-    }
     const int64_t tiles = (N + TL_F - 1) / TL_F;
     int64_t grid = n_partials < tiles ? n_partials : tiles;
     if (grid < 1) grid = 1;
     cudaError_t e = cudaMemsetAsync(sse_partials, 0, (size_t)n_partials * sizeof(double), s);
     if (e != cudaSuccess) return e;
     double* part = reinterpret_cast<double*>(sse_partials);
-    if (resid)
-        tail_kernel<true><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out,
-                                                            counts, resid, part, meta);
-    else
-        tail_kernel<false><<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out,
-                                                             counts, nullptr, part, meta);
+    const int g = (int)grid;
+#define VQB_TAIL(LPF, J) e = launch_tail_t<LPF, J>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, g, meta, s)
+    if (D <= 32) VQB_TAIL(8, 1);
+    else if (D <= 64) VQB_TAIL(16, 1);
+    else if (D <= 128) VQB_TAIL(32, 1);
+    else if (D <= 256) VQB_TAIL(32, 2);
+    else if (D <= 384) VQB_TAIL(32, 3);
+    else VQB_TAIL(32, 4);
+#undef VQB_TAIL
     note_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 // counts (int) and SSE partials (double) -> the fp32 statistics buffer [counts | resid | SSE | N]
@@ -520,7 +584,8 @@ cudaError_t launch_finalize(const float* stats, int K, int D, float beta, float*
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// dX[b,:,w] = Gq[b,:,w] + g_c * beta * 2 (x - q) / (N D); same transposing tile as the tail kernel.
+constexpr int TL_LD = TL_F + 1;       // [D][33] dim-major tile of the simpler kernels below (scalar, conflict-free)
+// dX[b,:,w] = Gq[b,:,w] + g_c * beta * 2 (x - q) / (N D); transposing tile, warp per frame.
 __global__ void __launch_bounds__(256) backward_dx_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                           const int64_t* __restrict__ idx, const float* __restrict__ Gq,
                                                           const float* __restrict__ g_c, float beta, int D, int64_t W,

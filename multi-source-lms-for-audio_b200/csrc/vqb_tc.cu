@@ -5,9 +5,8 @@
 // replaces `distances` + `argmin` of src/model/components/vector_quantizer.py:32-37.  The N x K score matrix never
 // leaves the SM: tcgen05.mma accumulates a 128-frame x 256-code tile in TMEM, epilogue warps pull it back with
 // tcgen05.ld, add |e_k|^2 and keep, per frame, the codes whose score is within a rigorous guard band of the running
-// minimum.  A shortlist entry is a chunk of 8 consecutive codes (at most 4 chunks per column half); the fused tail kernel
-// then rescores the few shortlisted chunks in fp32 in the reference's operation order, which decides the index.  Frames
-// whose shortlist overflowed go to the exact fp32 search.
+// minimum (at most 6 per column half).  The fused tail kernel then rescores those few codes in fp32 in the reference's
+// operation order, which decides the index; frames whose shortlist overflowed go to the exact fp32 search.
 //
 // Structure (one persistent CTA per SM, 384 threads, warp-specialised):
 //   warp 0      TMA producer: latent tile A (128 frames x D, resident per M tile) and codebook tiles B
@@ -35,7 +34,7 @@ constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 4;
 constexpr int E2_SLOTS = 4;                  // |e|^2 slices ride their own ring so the producer never waits on the epilogue
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4, EPI_THREADS = 256;
-constexpr int MERGE_WORDS = 10;              // per frame and half: 4 scores, 4 codes, dropped-min, pad
+constexpr int MERGE_WORDS = 14;              // per frame of column half 1: 6 scores, 6 codes, dropped-min, pad
 
 struct Barriers {
     unsigned long long b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
@@ -150,37 +149,41 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------------------------------------- shortlist
+constexpr int SL = 6;   // shortlist slots per column half (12 per frame)
+
 struct Shortlist {
-    float v[4];     // ascending scores
-    int   i[4];     // chunk ids = code / 8 (-1 = empty)
+    float v[SL];    // ascending scores
+    int   i[SL];    // codes (-1 = empty)
     float dropped;  // smallest score ever pushed out of / refused by the list
     __device__ __forceinline__ void reset() {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { v[j] = INFINITY; i[j] = -1; }
+        for (int j = 0; j < SL; ++j) { v[j] = INFINITY; i[j] = -1; }
         dropped = INFINITY;
     }
+    // sorted insert without inner branches: position p = first slot with s < v[p]; slots above p shift up by one
     __device__ __forceinline__ void insert(float s, int code) {
-        if (s < v[3]) {
-            dropped = fminf(dropped, v[3]);
-            if (s < v[2]) {
-                v[3] = v[2]; i[3] = i[2];
-                if (s < v[1]) {
-                    v[2] = v[1]; i[2] = i[1];
-                    if (s < v[0]) { v[1] = v[0]; i[1] = i[0]; v[0] = s; i[0] = code; }
-                    else { v[1] = s; i[1] = code; }
-                } else { v[2] = s; i[2] = code; }
-            } else { v[3] = s; i[3] = code; }
-        } else {
-            dropped = fminf(dropped, s);
+        dropped = fminf(dropped, (s < v[SL - 1]) ? v[SL - 1] : s);
+#pragma unroll
+        for (int j = SL - 1; j > 0; --j) {
+            const bool up = s < v[j - 1];
+            const float nv = up ? v[j - 1] : s;
+            const int ni = up ? i[j - 1] : code;
+            const bool take = s < v[j];
+            v[j] = take ? nv : v[j];
+            i[j] = take ? ni : i[j];
         }
+        const bool first = s < v[0];
+        v[0] = first ? s : v[0];
+        i[0] = first ? code : i[0];
     }
 };
 
-// One 32-column slab of scores for this thread's frame.  Shortlist entries are CHUNKS of 8 consecutive codes, keyed by
-// the chunk's minimum score.  Fast path per slab: 32 FFMA + 18 FMNMX3 + one compare; only when the slab minimum is
-// within the band of the running minimum (rare after the first tiles) are the four chunk minima looked at one by one.
-__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int chunk0, float band,
-                                          float& thr, Shortlist& sl) {
+// One 32-column slab of scores for this thread's frame.
+// Fast path per slab: 32 FFMA + 18 FMNMX3 + one compare.  Only when the slab minimum is within the band of the running
+// minimum (rare after the first tiles) are the four 8-code chunk minima checked, and only a chunk that passes is
+// rescanned code by code (its scores go through a per-thread shared-memory scratch so the insert exists once per chunk).
+__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int code0, float band,
+                                          float& thr, Shortlist& sl, float* __restrict__ scratch) {
     float t[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -204,8 +207,16 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* 
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (t[g] < thr) {
-                sl.insert(t[g], chunk0 + g);
-                thr = sl.v[0] + band;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) scratch[j * EPI_THREADS] = fmaf(-2.f, __uint_as_float(r[g * 8 + j]), e2s[g * 8 + j]);
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {
+                    const float sc = scratch[j * EPI_THREADS];
+                    if (sc < thr) {
+                        sl.insert(sc, code0 + g * 8 + j);
+                        thr = sl.v[0] + band;
+                    }
+                }
             }
         }
     }
@@ -227,8 +238,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
     unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB
     float* sE2 = reinterpret_cast<float*>(sB + (size_t)b_stages * B_STAGE_BYTES);   // E2_SLOTS x 256 floats
-    float* sMerge = sE2 + E2_SLOTS * BN;                                 // 2 x 128 x MERGE_WORDS
-    Barriers* bars = reinterpret_cast<Barriers*>(sMerge + 2 * BM * MERGE_WORDS);
+    float* sMerge = sE2 + E2_SLOTS * BN;                                 // 128 x MERGE_WORDS (lists of column half 1)
+    float* sScratch = sMerge + BM * MERGE_WORDS;                         // 8 x 256 floats: one chunk of scores per thread
+    Barriers* bars = reinterpret_cast<Barriers*>(sScratch + 8 * EPI_THREADS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -326,6 +338,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
         const bool force_fallback = meta->cb_nonfinite != 0;
+        float* scratch = sScratch + (threadIdx.x - EPI_WARP0 * 32);
         uint32_t n_it = 0;
         Shortlist sl;
         for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
@@ -358,15 +371,15 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (row < N) dump_slab(rb, e2s + 96, code0 + 96, K, row_out);
                 } else {
                     tmem_ld32(taddr + 32, rb);
-                    scan_slab(ra, e2s, code0 >> 3, band, thr, sl);
+                    scan_slab(ra, e2s, code0, band, thr, sl, scratch);
                     tmem_ld_wait(rb);
                     tmem_ld32(taddr + 64, ra);
-                    scan_slab(rb, e2s + 32, (code0 + 32) >> 3, band, thr, sl);
+                    scan_slab(rb, e2s + 32, code0 + 32, band, thr, sl, scratch);
                     tmem_ld_wait(ra);
                     tmem_ld32(taddr + 96, rb);
-                    scan_slab(ra, e2s + 64, (code0 + 64) >> 3, band, thr, sl);
+                    scan_slab(ra, e2s + 64, code0 + 64, band, thr, sl, scratch);
                     tmem_ld_wait(rb);
-                    scan_slab(rb, e2s + 96, (code0 + 96) >> 3, band, thr, sl);
+                    scan_slab(rb, e2s + 96, code0 + 96, band, thr, sl, scratch);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -376,41 +389,34 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
             // ---- merge the two column halves of this frame and publish the shortlist
-            float* mine = sMerge + ((size_t)half * BM + row_in_tile) * MERGE_WORDS;
+            if (half == 1) {
+                float* mine = sMerge + (size_t)row_in_tile * MERGE_WORDS;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { mine[j] = sl.v[j]; mine[4 + j] = __int_as_float(sl.i[j]); }
-            mine[8] = sl.dropped;
+                for (int j = 0; j < SL; ++j) { mine[j] = sl.v[j]; mine[SL + j] = __int_as_float(sl.i[j]); }
+                mine[2 * SL] = sl.dropped;
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (half == 0 && row < N && !scores_dbg) {
-                const float* other = sMerge + ((size_t)BM + row_in_tile) * MERGE_WORDS;
+                const float* other = sMerge + (size_t)row_in_tile * MERGE_WORDS;
                 const float gmin = fminf(sl.v[0], other[0]);
                 const float cutoff = gmin + band;
+                uint16_t* dst = cand_idx + (size_t)row * kCandMax;
                 int cnt = 0;
-                unsigned long long lo = 0ull, hi = 0ull;   // up to 8 chunk ids of 16 bits, own half first
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (sl.i[j] >= 0 && sl.v[j] <= cutoff) { lo |= (unsigned long long)sl.i[j] << (16 * cnt); ++cnt; }
-                }
-                const int cnt0 = cnt;
+                for (int j = 0; j < SL; ++j)
+                    if (sl.i[j] >= 0 && sl.v[j] <= cutoff) dst[cnt++] = (uint16_t)sl.i[j];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int oi = __float_as_int(other[4 + j]);
-                    if (oi >= 0 && other[j] <= cutoff) { hi |= (unsigned long long)oi << (16 * (cnt - cnt0)); ++cnt; }
+                for (int j = 0; j < SL; ++j) {
+                    const int oi = __float_as_int(other[SL + j]);
+                    if (oi >= 0 && other[j] <= cutoff) dst[cnt++] = (uint16_t)oi;
                 }
-                // close the gap between the two halves: 64-bit funnel of hi into the free slots of lo
-                const unsigned long long hi_lo = cnt0 == 4 ? 0ull : hi << (16 * cnt0);
-                const unsigned long long hi_hi = cnt0 == 0 ? 0ull : (cnt0 == 4 ? hi : hi >> (16 * (4 - cnt0)));
-                lo |= hi_lo;
-                hi = hi_hi;
-                const bool overflow = force_fallback || cnt == 0 || !(band < INFINITY) || fminf(sl.dropped, other[8]) <= cutoff;
+                const bool overflow = force_fallback || cnt == 0 || !(band < INFINITY) || fminf(sl.dropped, other[2 * SL]) <= cutoff;
                 if (overflow) {
                     cand_cnt[row] = kCandFinal;   // the exact search fills in the final code
                     fallback_rows[atomicAdd(&meta->fallback_count, 1)] = (int)row;
                     atomicAdd(&meta->fallback_total, 1ull);
                 } else {
                     cand_cnt[row] = (uint8_t)cnt;
-                    *reinterpret_cast<uint4*>(cand_idx + (size_t)row * kCandMax) =
-                        make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
                 }
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -489,7 +495,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     if ((rc = make_map(&me, eb, (uint64_t)K_pad, (uint64_t)D, BN)) != 0) return rc;
     const int num_kb = (D + BK - 1) / BK;
     const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + 2 * BM * MERGE_WORDS * 4 + sizeof(Barriers) + 1024;
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + BM * MERGE_WORDS * 4 + 8 * EPI_THREADS * 4 + sizeof(Barriers) + 1024;
     int b_stages = (int)((227 * 1024 - fixed) / B_STAGE_BYTES);
     if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
     if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
