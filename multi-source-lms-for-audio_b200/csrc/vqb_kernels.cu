@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ 
     const int sub = lane / LPF, sl = lane % LPF;
     float sse = 0.f, sse_c = 0.f;                 // Kahan-compensated per-thread SSE
     unsigned int n_resc = 0, n_short = 0;
+    const bool resid_v4 = kResid && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;   // stats + K is 16B aligned iff K % 4 == 0
 
     for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x) {
         const int64_t nl = tile * TL_F + lane;
@@ -444,7 +445,11 @@ __global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ 
                         st.x = __fadd_rn(xv[j].x, df.x); st.y = __fadd_rn(xv[j].y, df.y);      // straight-through VALUE (:48)
                         st.z = __fadd_rn(xv[j].z, df.z); st.w = __fadd_rn(xv[j].w, df.w);
                         *reinterpret_cast<float4*>(Xs + f * ld + d) = st;
-                        if (kResid) red_add_v4(resid + (size_t)k * D + d, -df.x, -df.y, -df.z, -df.w);
+                        if (kResid) {
+                            float* rp = resid + (size_t)k * D + d;
+                            if (resid_v4) red_add_v4(rp, -df.x, -df.y, -df.z, -df.w);
+                            else { atomicAdd(rp, -df.x); atomicAdd(rp + 1, -df.y); atomicAdd(rp + 2, -df.z); atomicAdd(rp + 3, -df.w); }
+                        }
                     }
                 }
                 {   // Kahan: sse += fs

@@ -207,14 +207,29 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* 
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (t[g] < thr) {
+                // the chunk's best code enters the list straight from registers; only if a second code of the same
+                // chunk is also inside the band (rare) does the chunk go through the scratch loop
+                float sc[8];
+                int jmin = 7, below = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) scratch[j * EPI_THREADS] = fmaf(-2.f, __uint_as_float(r[g * 8 + j]), e2s[g * 8 + j]);
+                for (int j = 7; j >= 0; --j) {
+                    sc[j] = fmaf(-2.f, __uint_as_float(r[g * 8 + j]), e2s[g * 8 + j]);
+                    jmin = (sc[j] == t[g]) ? j : jmin;
+                    below += (sc[j] < thr) ? 1 : 0;
+                }
+                const float thr_in = thr;
+                sl.insert(t[g], code0 + g * 8 + jmin);
+                thr = sl.v[0] + band;
+                if (below > 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) scratch[j * EPI_THREADS] = sc[j];
 #pragma unroll 1
-                for (int j = 0; j < 8; ++j) {
-                    const float sc = scratch[j * EPI_THREADS];
-                    if (sc < thr) {
-                        sl.insert(sc, code0 + g * 8 + j);
-                        thr = sl.v[0] + band;
+                    for (int j = 0; j < 8; ++j) {
+                        const float v = scratch[j * EPI_THREADS];
+                        if (j != jmin && v < thr_in && v < thr) {
+                            sl.insert(v, code0 + g * 8 + j);
+                            thr = sl.v[0] + band;
+                        }
                     }
                 }
             }
