@@ -258,9 +258,6 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     Barriers* bars = reinterpret_cast<Barriers*>(sScratch + 8 * EPI_THREADS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Every CTA sweeps the codebook tiles in the same cyclic order but starts at a different tile, so that at any moment
-    // the 148 SMs pull different codebook lines out of L2 instead of all hammering the same slices.
-    const int nt0 = (int)((blockIdx.x * 7u) % (unsigned)num_n_tiles);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
@@ -289,8 +286,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ================================================================ TMA producer
         uint32_t a_it = 0, b_it = 0, n_it = 0;
         for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
-            for (int ni = 0; ni < num_n_tiles; ++ni, ++n_it) {
-                const int nt = (ni + nt0) % num_n_tiles;
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t es = n_it % E2_SLOTS;
                 mbar_wait(smem_u32(&bars->e2_empty[es]), ((n_it / E2_SLOTS) & 1) ^ 1);
                 if (lane == 0) {
@@ -298,7 +294,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     bulk_load_1d(smem_u32(sE2 + es * BN), e2 + (size_t)nt * BN, E2_SLICE_BYTES, smem_u32(&bars->e2_full[es]));
                 }
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    if (ni == 0) {
+                    if (nt == 0) {
                         const uint32_t slot = a_it % a_slots, ph = (a_it / a_slots) & 1;
                         mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
                         if (lane == 0) {
@@ -322,14 +318,14 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ================================================================ MMA issuer
         uint32_t a_base = 0, b_it = 0, n_it = 0;   // a_base: A chunk counter at the start of the current M tile
         for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
-            for (int ni = 0; ni < num_n_tiles; ++ni, ++n_it) {
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1;
                 mbar_wait(smem_u32(&bars->tmem_empty[as]), ((n_it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const uint32_t a_idx = a_base + kb, slot = a_idx % a_slots;
-                    if (ni == 0) mbar_wait(smem_u32(&bars->a_full[slot]), (a_idx / a_slots) & 1);
+                    if (nt == 0) mbar_wait(smem_u32(&bars->a_full[slot]), (a_idx / a_slots) & 1);
                     const uint32_t st = b_it % b_stages;
                     mbar_wait(smem_u32(&bars->b_full[st]), (b_it / b_stages) & 1);
                     tc_fence_after();
@@ -340,7 +336,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes per K step inside the swizzle row: +2 in 16-byte units
                             umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
                         umma_commit(smem_u32(&bars->b_empty[st]));
-                        if (ni == num_n_tiles - 1) umma_commit(smem_u32(&bars->a_empty[slot]));
+                        if (nt == num_n_tiles - 1) umma_commit(smem_u32(&bars->a_empty[slot]));
                         if (kb == num_kb - 1) umma_commit(smem_u32(&bars->tmem_full[as]));
                     }
                     __syncwarp();
@@ -365,8 +361,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const float band = (row < N) ? band_g[row] : 0.f;
             float thr = INFINITY;
             sl.reset();
-            for (int ni = 0; ni < num_n_tiles; ++ni, ++n_it) {
-                const int nt = (ni + nt0) % num_n_tiles;
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1, es = n_it % E2_SLOTS;
                 mbar_wait(smem_u32(&bars->e2_full[es]), (n_it / E2_SLOTS) & 1);
                 mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
