@@ -18,6 +18,7 @@
 #include "vqb_internal.h"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace vqb {
 
@@ -86,6 +87,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// same box delivered to the same shared-memory offset of every CTA in `mask`; each destination's barrier gets the bytes
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
@@ -113,6 +129,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
 }
 
 // K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1 (sm_100)
@@ -247,8 +268,8 @@ __device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], const float* 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
                  const float* __restrict__ e2, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
-                 int num_kb, int a_slots, int b_stages, int K, uint8_t* __restrict__ cand_cnt, uint16_t* __restrict__ cand_idx,
-                 int* __restrict__ fallback_rows, WsMeta* meta, float* __restrict__ scores_dbg) {
+                 int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
+                 uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta, float* __restrict__ scores_dbg) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
     unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB
@@ -258,13 +279,22 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     Barriers* bars = reinterpret_cast<Barriers*>(sScratch + 8 * EPI_THREADS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Cluster of `cs` CTAs: every CTA quantises its own 128-frame tile, but each codebook tile is fetched from L2 only
+    // once per cluster - CTA r loads rows [r*256/cs, (r+1)*256/cs) and multicasts them into all cs shared memories.
+    // All CTAs of a cluster therefore walk the same (tile round, codebook tile) sequence; a CTA whose frame tile lies
+    // past the end works on zero-filled rows and publishes nothing.
+    const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+    const int n_clusters = (int)gridDim.x / cs;
+    const int cluster_id = (int)blockIdx.x / cs;
+    const int rounds = (num_m_tiles + n_clusters * cs - 1) / (n_clusters * cs);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_e);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
+        for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), cs); }
         for (int i = 0; i < a_slots; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
         for (int i = 0; i < E2_SLOTS; ++i) {
             mbar_init(smem_u32(&bars->e2_full[i]), 1);
@@ -279,13 +309,15 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();   // peers must see initialised barriers before the first multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
         // ================================================================ TMA producer
         uint32_t a_it = 0, b_it = 0, n_it = 0;
-        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t es = n_it % E2_SLOTS;
                 mbar_wait(smem_u32(&bars->e2_empty[es]), ((n_it / E2_SLOTS) & 1) ^ 1);
@@ -300,15 +332,21 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         if (lane == 0) {
                             mbar_expect_tx(smem_u32(&bars->a_full[slot]), A_CHUNK_BYTES);
                             tma_load_2d(smem_u32(sA + (size_t)slot * A_CHUNK_BYTES), &tmap_x, smem_u32(&bars->a_full[slot]), kb * BK,
-                                        mt * BM);
+                                        (mt < num_m_tiles ? mt : 0) * BM);   // dummy tiles re-read tile 0, nothing is published
                         }
                         ++a_it;
                     }
                     const uint32_t st = b_it % b_stages, ph = (b_it / b_stages) & 1;
                     mbar_wait(smem_u32(&bars->b_empty[st]), ph ^ 1);
                     if (lane == 0) {
-                        mbar_expect_tx(smem_u32(&bars->b_full[st]), B_STAGE_BYTES);
-                        tma_load_2d(smem_u32(sB + (size_t)st * B_STAGE_BYTES), &tmap_e, smem_u32(&bars->b_full[st]), kb * BK, nt * BN);
+                        mbar_expect_tx(smem_u32(&bars->b_full[st]), B_STAGE_BYTES);   // own slice + the peers' slices
+                        if (cs == 1) {
+                            tma_load_2d(smem_u32(sB + (size_t)st * B_STAGE_BYTES), &tmap_e, smem_u32(&bars->b_full[st]), kb * BK, nt * BN);
+                        } else {
+                            const uint32_t slice = (uint32_t)B_STAGE_BYTES / (uint32_t)cs;
+                            tma_load_2d_mc(smem_u32(sB + (size_t)st * B_STAGE_BYTES) + crank * slice, &tmap_e, smem_u32(&bars->b_full[st]),
+                                           kb * BK, nt * BN + (int)crank * (BN / cs), cmask);
+                        }
                     }
                     ++b_it;
                 }
@@ -317,7 +355,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     } else if (warp == 1) {
         // ================================================================ MMA issuer
         uint32_t a_base = 0, b_it = 0, n_it = 0;   // a_base: A chunk counter at the start of the current M tile
-        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1;
                 mbar_wait(smem_u32(&bars->tmem_empty[as]), ((n_it >> 1) & 1) ^ 1);
@@ -335,7 +374,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes per K step inside the swizzle row: +2 in 16-byte units
                             umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
-                        umma_commit(smem_u32(&bars->b_empty[st]));
+                        if (cs == 1) umma_commit(smem_u32(&bars->b_empty[st]));
+                        else umma_commit_mc(smem_u32(&bars->b_empty[st]), cmask);
                         if (nt == num_n_tiles - 1) umma_commit(smem_u32(&bars->a_empty[slot]));
                         if (kb == num_kb - 1) umma_commit(smem_u32(&bars->tmem_full[as]));
                     }
@@ -356,7 +396,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         float* scratch = sScratch + (threadIdx.x - EPI_WARP0 * 32);
         uint32_t n_it = 0;
         Shortlist sl;
-        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             const int64_t row = (int64_t)mt * BM + row_in_tile;
             const float band = (row < N) ? band_g[row] : 0.f;
             float thr = INFINITY;
@@ -440,6 +481,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();   // no CTA may retire while a peer can still multicast into it or arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -504,10 +546,9 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
                      float* scores_dbg, cudaStream_t s) {
     using namespace tc;
-    CUtensorMap mx, me;
+    CUtensorMap mx;
     int rc;
     if ((rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM)) != 0) return rc;
-    if ((rc = make_map(&me, eb, (uint64_t)K_pad, (uint64_t)D, BN)) != 0) return rc;
     const int num_kb = (D + BK - 1) / BK;
     const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
     const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + BM * MERGE_WORDS * 4 + 8 * EPI_THREADS * 4 + sizeof(Barriers) + 1024;
@@ -526,10 +567,30 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int num_m_tiles = (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
-    const int grid = num_m_tiles < sms ? num_m_tiles : sms;
+    int cs = 2;                                   // cluster size for the codebook multicast (VQB_TC_CLUSTER=1|2|4)
+    if (const char* env = getenv("VQB_TC_CLUSTER")) cs = atoi(env);
+    if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+    if (num_m_tiles < 2 * cs) cs = 1;
+    CUtensorMap me_c;
+    if ((rc = make_map(&me_c, eb, (uint64_t)K_pad, (uint64_t)D, BN / cs)) != 0) return rc;
+    int grid = num_m_tiles < sms ? num_m_tiles : sms;
+    grid = grid / cs * cs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     TimingSlot* slot = timing_begin(s);
-    tc_search_kernel<<<grid, NUM_THREADS, smem, s>>>(mx, me, e2, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, K,
-                                                     cand_cnt, cand_idx, fallback_rows, meta, scores_dbg);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_search_kernel, mx, me_c, e2, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs,
+                                        K, cand_cnt, cand_idx, fallback_rows, meta, scores_dbg);
+    if (le != cudaSuccess) return cuda_fail(le, "tc_search_kernel launch");
     cudaError_t e = cudaGetLastError();
     timing_end(slot, s);
     note_launch();
