@@ -28,13 +28,15 @@ struct WsMeta {
 };
 
 struct WsLayout {
-    size_t meta, e2, counts, sse_partials, idx32, cand_cnt, cand_idx, fallback_rows, x2, eb, xb, total;
+    size_t meta, e2, counts, sse_partials, idx32, cand_cnt, cand_idx, fallback_rows, x2, eb, xb, ev, total;
     int    k_pad;
     int64_t n_pad;
     int    n_partials;
 };
 WsLayout ws_layout(int64_t N, int K, int D, int flags);
 
+constexpr int kTcMaxCtas = 160;         // persistent grid bound of the tensor-core search (event scratch is sized for it)
+size_t tc_event_scratch_bytes();
 constexpr int kTailGridMax = 148 * 8;   // persistent grid of the fused tail kernel (sse partial slots)
 
 void set_error(const char* fmt, ...);
@@ -68,6 +70,6 @@ cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int6
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.
 int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const float* e2, const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
-                     float* scores_dbg, cudaStream_t s);
+                     float* scores_dbg, void* ev_scratch, cudaStream_t s);
 
 }  // namespace vqb

@@ -5,7 +5,7 @@
 // replaces `distances` + `argmin` of src/model/components/vector_quantizer.py:32-37.  The N x K score matrix never
 // leaves the SM: tcgen05.mma accumulates a 128-frame x 256-code tile in TMEM, epilogue warps pull it back with
 // tcgen05.ld, add |e_k|^2 and keep, per frame, the codes whose score is within a rigorous guard band of the running
-// minimum (at most 6 per column half).  The fused tail kernel then rescores those few codes in fp32 in the reference's
+// minimum (at most 12 per frame).  The fused tail kernel then rescores those few codes in fp32 in the reference's
 // operation order, which decides the index; frames whose shortlist overflowed go to the exact fp32 search.
 //
 // Structure (one persistent CTA per SM, 384 threads, warp-specialised):
@@ -35,7 +35,7 @@ constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 4;
 constexpr int E2_SLOTS = 4;                  // |e|^2 slices ride their own ring so the producer never waits on the epilogue
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4, EPI_THREADS = 256;
-constexpr int MERGE_WORDS = 14;              // per frame of column half 1: 6 scores, 6 codes, dropped-min, pad
+constexpr int kCandFill = 12;                // shortlist entries published per frame (cand_idx rows hold kCandMax = 16)
 
 struct Barriers {
     unsigned long long b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
@@ -170,41 +170,27 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------------------------------------- shortlist
-constexpr int SL = 6;   // shortlist slots per column half (12 per frame)
+// Per-thread event stack in global (L2-resident) scratch: every code whose score comes within the guard band of the
+// thread's running minimum is appended as (score, code).  Appending is predicated straight-line code - no sorted list, no
+// divergent insert - and the stack is filtered once per frame tile against the final minimum.  EV_CAP events per thread
+// and frame tile; running out (adversarial orderings) only sends that frame to the exact search.
+constexpr int EV_CAP = 48;
 
-struct Shortlist {
-    float v[SL];    // ascending scores
-    int   i[SL];    // codes (-1 = empty)
-    float dropped;  // smallest score ever pushed out of / refused by the list
-    __device__ __forceinline__ void reset() {
-#pragma unroll
-        for (int j = 0; j < SL; ++j) { v[j] = INFINITY; i[j] = -1; }
-        dropped = INFINITY;
-    }
-    // sorted insert without inner branches: position p = first slot with s < v[p]; slots above p shift up by one
-    __device__ __forceinline__ void insert(float s, int code) {
-        dropped = fminf(dropped, (s < v[SL - 1]) ? v[SL - 1] : s);
-#pragma unroll
-        for (int j = SL - 1; j > 0; --j) {
-            const bool up = s < v[j - 1];
-            const float nv = up ? v[j - 1] : s;
-            const int ni = up ? i[j - 1] : code;
-            const bool take = s < v[j];
-            v[j] = take ? nv : v[j];
-            i[j] = take ? ni : i[j];
-        }
-        const bool first = s < v[0];
-        v[0] = first ? s : v[0];
-        i[0] = first ? code : i[0];
+struct EventStack {
+    uint2* base;    // this thread's column: entry e lives at base[e * EPI_THREADS]
+    int    n;       // events appended for the current frame tile (may exceed EV_CAP: overflow)
+    __device__ __forceinline__ void push(float sc, int code) {
+        if (n < EV_CAP) base[(size_t)n * EPI_THREADS] = make_uint2(__float_as_uint(sc), (uint32_t)code);
+        ++n;
     }
 };
 
 // One 32-column slab of scores for this thread's frame.
 // Fast path per slab: 32 FFMA + 18 FMNMX3 + one compare.  Only when the slab minimum is within the band of the running
-// minimum (rare after the first tiles) are the four 8-code chunk minima checked, and only a chunk that passes is
-// rescanned code by code (its scores go through a per-thread shared-memory scratch so the insert exists once per chunk).
+// minimum (rare after the first tiles) are the four 8-code chunk minima checked, and a chunk that passes appends its
+// in-band codes to the event stack with predicated stores.
 __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int code0, float band,
-                                          float& thr, Shortlist& sl, float* __restrict__ scratch) {
+                                          float& thr, EventStack& ev) {
     float t[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -228,31 +214,12 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* 
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (t[g] < thr) {
-                // the chunk's best code enters the list straight from registers; only if a second code of the same
-                // chunk is also inside the band (rare) does the chunk go through the scratch loop
-                float sc[8];
-                int jmin = 7, below = 0;
 #pragma unroll
-                for (int j = 7; j >= 0; --j) {
-                    sc[j] = fmaf(-2.f, __uint_as_float(r[g * 8 + j]), e2s[g * 8 + j]);
-                    jmin = (sc[j] == t[g]) ? j : jmin;
-                    below += (sc[j] < thr) ? 1 : 0;
+                for (int j = 0; j < 8; ++j) {
+                    const float sc = fmaf(-2.f, __uint_as_float(r[g * 8 + j]), e2s[g * 8 + j]);
+                    if (sc < thr) ev.push(sc, code0 + g * 8 + j);
                 }
-                const float thr_in = thr;
-                sl.insert(t[g], code0 + g * 8 + jmin);
-                thr = sl.v[0] + band;
-                if (below > 1) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) scratch[j * EPI_THREADS] = sc[j];
-#pragma unroll 1
-                    for (int j = 0; j < 8; ++j) {
-                        const float v = scratch[j * EPI_THREADS];
-                        if (j != jmin && v < thr_in && v < thr) {
-                            sl.insert(v, code0 + g * 8 + j);
-                            thr = sl.v[0] + band;
-                        }
-                    }
-                }
+                thr = fminf(thr, t[g] + band);
             }
         }
     }
@@ -269,14 +236,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
                  const float* __restrict__ e2, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
-                 uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta, float* __restrict__ scores_dbg) {
+                 uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta, float* __restrict__ scores_dbg,
+                 uint2* __restrict__ ev_scratch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
     unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB
     float* sE2 = reinterpret_cast<float*>(sB + (size_t)b_stages * B_STAGE_BYTES);   // E2_SLOTS x 256 floats
-    float* sMerge = sE2 + E2_SLOTS * BN;                                 // 128 x MERGE_WORDS (lists of column half 1)
-    float* sScratch = sMerge + BM * MERGE_WORDS;                         // 8 x 256 floats: one chunk of scores per thread
-    Barriers* bars = reinterpret_cast<Barriers*>(sScratch + 8 * EPI_THREADS);
+    float* sMin = sE2 + E2_SLOTS * BN;                                   // [2][128] running minima of the two column halves
+    int* sCnt = reinterpret_cast<int*>(sMin + 2 * BM);                   // [128] shortlist fill per frame, [128] overflow flags
+    Barriers* bars = reinterpret_cast<Barriers*>(sCnt + 2 * BM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Cluster of `cs` CTAs: every CTA quantises its own 128-frame tile, but each codebook tile is fetched from L2 only
@@ -393,15 +361,18 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
         const bool force_fallback = meta->cb_nonfinite != 0;
-        float* scratch = sScratch + (threadIdx.x - EPI_WARP0 * 32);
+        const int et = threadIdx.x - EPI_WARP0 * 32;             // 0..255
+        EventStack ev;
+        ev.base = ev_scratch + (size_t)blockIdx.x * EV_CAP * EPI_THREADS + et;
+        ev.n = 0;
+        if (half == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; }
         uint32_t n_it = 0;
-        Shortlist sl;
         for (int rd = 0; rd < rounds; ++rd) {
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             const int64_t row = (int64_t)mt * BM + row_in_tile;
             const float band = (row < N) ? band_g[row] : 0.f;
             float thr = INFINITY;
-            sl.reset();
+            ev.n = 0;
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1, es = n_it % E2_SLOTS;
                 mbar_wait(smem_u32(&bars->e2_full[es]), (n_it / E2_SLOTS) & 1);
@@ -427,15 +398,15 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (row < N) dump_slab(rb, e2s + 96, code0 + 96, K, row_out);
                 } else {
                     tmem_ld32(taddr + 32, rb);
-                    scan_slab(ra, e2s, code0, band, thr, sl, scratch);
+                    scan_slab(ra, e2s, code0, band, thr, ev);
                     tmem_ld_wait(rb);
                     tmem_ld32(taddr + 64, ra);
-                    scan_slab(rb, e2s + 32, code0 + 32, band, thr, sl, scratch);
+                    scan_slab(rb, e2s + 32, code0 + 32, band, thr, ev);
                     tmem_ld_wait(ra);
                     tmem_ld32(taddr + 96, rb);
-                    scan_slab(ra, e2s + 64, code0 + 64, band, thr, sl, scratch);
+                    scan_slab(ra, e2s + 64, code0 + 64, band, thr, ev);
                     tmem_ld_wait(rb);
-                    scan_slab(rb, e2s + 96, code0 + 96, band, thr, sl, scratch);
+                    scan_slab(rb, e2s + 96, code0 + 96, band, thr, ev);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -444,38 +415,39 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     mbar_arrive(smem_u32(&bars->e2_empty[es]));
                 }
             }
-            // ---- merge the two column halves of this frame and publish the shortlist
-            if (half == 1) {
-                float* mine = sMerge + (size_t)row_in_tile * MERGE_WORDS;
-#pragma unroll
-                for (int j = 0; j < SL; ++j) { mine[j] = sl.v[j]; mine[SL + j] = __int_as_float(sl.i[j]); }
-                mine[2 * SL] = sl.dropped;
-            }
+            // ---- filter this thread's events against the frame's final minimum and publish the shortlist
+            sMin[half * BM + row_in_tile] = thr - band;                      // running minimum of this column half
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0 && row < N && !scores_dbg) {
-                const float* other = sMerge + (size_t)row_in_tile * MERGE_WORDS;
-                const float gmin = fminf(sl.v[0], other[0]);
-                const float cutoff = gmin + band;
+            if (row < N && !scores_dbg) {
+                const float cutoff = fminf(sMin[row_in_tile], sMin[BM + row_in_tile]) + band;
                 uint16_t* dst = cand_idx + (size_t)row * kCandMax;
-                int cnt = 0;
-#pragma unroll
-                for (int j = 0; j < SL; ++j)
-                    if (sl.i[j] >= 0 && sl.v[j] <= cutoff) dst[cnt++] = (uint16_t)sl.i[j];
-#pragma unroll
-                for (int j = 0; j < SL; ++j) {
-                    const int oi = __float_as_int(other[SL + j]);
-                    if (oi >= 0 && other[j] <= cutoff) dst[cnt++] = (uint16_t)oi;
+                const int n_ev = ev.n < EV_CAP ? ev.n : EV_CAP;
+                bool lost = ev.n > EV_CAP || !(band < INFINITY);
+                for (int e = 0; e < n_ev; ++e) {
+                    const uint2 en = ev.base[(size_t)e * EPI_THREADS];
+                    if (__uint_as_float(en.x) <= cutoff) {
+                        const int pos = atomicAdd(&sCnt[row_in_tile], 1);
+                        if (pos < kCandFill) dst[pos] = (uint16_t)en.y;
+                        else lost = true;
+                    }
                 }
-                const bool overflow = force_fallback || cnt == 0 || !(band < INFINITY) || fminf(sl.dropped, other[2 * SL]) <= cutoff;
-                if (overflow) {
-                    cand_cnt[row] = kCandFinal;   // the exact search fills in the final code
-                    fallback_rows[atomicAdd(&meta->fallback_count, 1)] = (int)row;
-                    atomicAdd(&meta->fallback_total, 1ull);
-                } else {
-                    cand_cnt[row] = (uint8_t)cnt;
-                }
+                if (lost) sCnt[BM + row_in_tile] = 1;
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (half == 0) {
+                if (row < N && !scores_dbg) {
+                    const int cnt = sCnt[row_in_tile];
+                    if (force_fallback || cnt == 0 || sCnt[BM + row_in_tile]) {
+                        cand_cnt[row] = kCandFinal;   // the exact search fills in the final code
+                        fallback_rows[atomicAdd(&meta->fallback_count, 1)] = (int)row;
+                        atomicAdd(&meta->fallback_total, 1ull);
+                    } else {
+                        cand_cnt[row] = (uint8_t)cnt;
+                    }
+                }
+                sCnt[row_in_tile] = 0;
+                sCnt[BM + row_in_tile] = 0;
+            }
         }
     }
 
@@ -521,6 +493,8 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 
 }  // namespace tc
 
+size_t tc_event_scratch_bytes() { return (size_t)kTcMaxCtas * tc::EV_CAP * tc::EPI_THREADS * sizeof(uint2); }
+
 // ---- optional CUDA-event timing of the dominant kernel, on the launching stream (bench.py's roofline leg) -------
 struct TimingSlot { cudaEvent_t start, stop; };
 static bool g_timing = false;
@@ -544,14 +518,14 @@ static void timing_end(TimingSlot* t, cudaStream_t s) {
 
 int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const float* e2, const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
-                     float* scores_dbg, cudaStream_t s) {
+                     float* scores_dbg, void* ev_scratch, cudaStream_t s) {
     using namespace tc;
     CUtensorMap mx;
     int rc;
     if ((rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM)) != 0) return rc;
     const int num_kb = (D + BK - 1) / BK;
     const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + BM * MERGE_WORDS * 4 + 8 * EPI_THREADS * 4 + sizeof(Barriers) + 1024;
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + 2 * BM * 4 + 2 * BM * 4 + sizeof(Barriers) + 1024;
     int b_stages = (int)((227 * 1024 - fixed) / B_STAGE_BYTES);
     if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
     if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
@@ -573,6 +547,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     if (num_m_tiles < 2 * cs) cs = 1;
     CUtensorMap me_c;
     if ((rc = make_map(&me_c, eb, (uint64_t)K_pad, (uint64_t)D, BN / cs)) != 0) return rc;
+    if (sms > kTcMaxCtas) sms = kTcMaxCtas;
     int grid = num_m_tiles < sms ? num_m_tiles : sms;
     grid = grid / cs * cs;
     cudaLaunchConfig_t cfg{};
@@ -589,7 +564,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     cfg.numAttrs = 1;
     TimingSlot* slot = timing_begin(s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, tc_search_kernel, mx, me_c, e2, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs,
-                                        K, cand_cnt, cand_idx, fallback_rows, meta, scores_dbg);
+                                        K, cand_cnt, cand_idx, fallback_rows, meta, scores_dbg, reinterpret_cast<uint2*>(ev_scratch));
     if (le != cudaSuccess) return cuda_fail(le, "tc_search_kernel launch");
     cudaError_t e = cudaGetLastError();
     timing_end(slot, s);
