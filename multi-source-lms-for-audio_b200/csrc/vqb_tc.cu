@@ -8,13 +8,13 @@
 // minimum (at most 12 per frame).  The fused tail kernel then rescores those few codes in fp32 in the reference's
 // operation order, which decides the index; frames whose shortlist overflowed go to the exact fp32 search.
 //
-// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 640 threads, warp-specialised):
 //   warp 0      TMA producer: latent tile A (128 frames x D, resident per M tile) and codebook tiles B
 //               (256 codes x 64 dims per stage) as 128B-swizzled K-major boxes, |e|^2 slices by bulk copy
 //   warp 1      MMA issuer: one lane issues tcgen05.mma cta_group::1 kind::f16 M128 N256 K16, fp32 accumulate,
 //               two TMEM accumulator stages (2 x 256 columns) so the epilogue of tile j overlaps the MMAs of tile j+1
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).., column half (w-4)/4
+//   warps 4-19  epilogue: warp w owns TMEM lanes 32*(w%4).., column quarter (w-4)/4 (64 of the 256 columns)
 #include "vqb_internal.h"
 
 #include <cuda.h>
@@ -33,8 +33,9 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int E2_SLICE_BYTES = BN * 4;       // 1 KiB
 constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 4;
 constexpr int E2_SLOTS = 4;                  // |e|^2 slices ride their own ring so the producer never waits on the epilogue
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_WARP0 = 4, EPI_THREADS = 256;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;   // 4 warps per TMEM lane quarter: 64 columns each
+constexpr int NUM_THREADS = EPI_WARP0 * 32 + EPI_THREADS;                      // 640
+constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);                            // 64
 constexpr int kCandFill = 12;                // shortlist entries published per frame (cand_idx rows hold kCandMax = 16)
 
 struct Barriers {
@@ -170,26 +171,38 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------------------------------------- shortlist
-// Per-thread event stack in global (L2-resident) scratch: every code whose score comes within the guard band of the
-// thread's running minimum is appended as (score, code).  Appending is predicated straight-line code - no sorted list, no
-// divergent insert - and the stack is filtered once per frame tile against the final minimum.  EV_CAP events per thread
-// and frame tile; running out (adversarial orderings) only sends that frame to the exact search.
-constexpr int EV_CAP = 48;
+// Per-thread event stack in global (L2-resident) scratch.  Whenever an 8-code chunk's minimum score comes within the
+// guard band of the thread's running minimum, the chunk is appended RAW: its 8 accumulators straight from the TMEM
+// registers, its minimum and its id (48 bytes, three predicated 16-byte stores, no arithmetic, no divergent code).
+// Which codes of the surviving chunks are really inside the band is worked out once per frame tile, after the sweep,
+// against the frame's final minimum.  EV_CAP chunks per thread and frame tile; running out (adversarial orderings) only
+// sends that frame to the exact search.
+constexpr int EV_CAP = 24;
+constexpr int EV_WORDS = 12;   // 8 accumulators, chunk minimum, chunk id, 2 pad
 
 struct EventStack {
-    uint2* base;    // this thread's column: entry e lives at base[e * EPI_THREADS]
-    int    n;       // events appended for the current frame tile (may exceed EV_CAP: overflow)
-    __device__ __forceinline__ void push(float sc, int code) {
-        if (n < EV_CAP) base[(size_t)n * EPI_THREADS] = make_uint2(__float_as_uint(sc), (uint32_t)code);
-        ++n;
+    uint32_t* base;   // this thread's EV_CAP x EV_WORDS words
+    int       n;      // chunks appended for the current frame tile (may exceed EV_CAP: overflow)
+    __device__ __forceinline__ void push_if(bool p, float tmin, int chunk, const uint32_t* a) {
+        const bool q = p && n < EV_CAP;
+        uint32_t* dst = base + n * EV_WORDS;
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t"
+            "setp.ne.u32 q, %0, 0;\n\t"
+            "@q st.global.v4.u32 [%1], {%2, %3, %4, %5};\n\t"
+            "@q st.global.v4.u32 [%1+16], {%6, %7, %8, %9};\n\t"
+            "@q st.global.v2.u32 [%1+32], {%10, %11};\n\t}" ::"r"((uint32_t)q),
+            "l"(dst), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(__float_as_uint(tmin)),
+            "r"((uint32_t)chunk)
+            : "memory");
+        n += p ? 1 : 0;
     }
 };
 
 // One 32-column slab of scores for this thread's frame.
-// Fast path per slab: 32 FFMA + 18 FMNMX3 + one compare.  Only when the slab minimum is within the band of the running
-// minimum (rare after the first tiles) are the four 8-code chunk minima checked, and a chunk that passes appends its
-// in-band codes to the event stack with predicated stores.
-__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int code0, float band,
+// Fast path per slab: 32 FFMA + 18 FMNMX3 + one compare.  When the slab minimum is within the band of the running
+// minimum, the four chunks are appended under predicates (straight-line code) and the threshold tightens.
+__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int chunk0, float band,
                                           float& thr, EventStack& ev) {
     float t[4];
 #pragma unroll
@@ -212,16 +225,8 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* 
     const float slab_min = fminf(fminf(fminf(t[0], t[1]), t[2]), t[3]);
     if (slab_min < thr) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            if (t[g] < thr) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float sc = fmaf(-2.f, __uint_as_float(r[g * 8 + j]), e2s[g * 8 + j]);
-                    if (sc < thr) ev.push(sc, code0 + g * 8 + j);
-                }
-                thr = fminf(thr, t[g] + band);
-            }
-        }
+        for (int g = 0; g < 4; ++g) ev.push_if(t[g] < thr, t[g], chunk0 + g, &r[g * 8]);
+        thr = fminf(thr, slab_min + band);
     }
 }
 
@@ -237,13 +242,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  const float* __restrict__ e2, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta, float* __restrict__ scores_dbg,
-                 uint2* __restrict__ ev_scratch) {
+                 uint32_t* __restrict__ ev_scratch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
     unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB
     float* sE2 = reinterpret_cast<float*>(sB + (size_t)b_stages * B_STAGE_BYTES);   // E2_SLOTS x 256 floats
-    float* sMin = sE2 + E2_SLOTS * BN;                                   // [2][128] running minima of the two column halves
-    int* sCnt = reinterpret_cast<int*>(sMin + 2 * BM);                   // [128] shortlist fill per frame, [128] overflow flags
+    float* sMin = sE2 + E2_SLOTS * BN;                                   // [4][128] running minima of the four column quarters
+    int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags
     Barriers* bars = reinterpret_cast<Barriers*>(sCnt + 2 * BM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,15 +362,15 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ================================================================ epilogue
         const int ew = warp - EPI_WARP0;
         const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32*quarter .. +31
-        const int half = ew >> 2;                // column half of every tile
+        const int colq = ew >> 2;                // which 64-column quarter of every tile
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
         const bool force_fallback = meta->cb_nonfinite != 0;
-        const int et = threadIdx.x - EPI_WARP0 * 32;             // 0..255
+        const int et = threadIdx.x - EPI_WARP0 * 32;             // 0..511
         EventStack ev;
-        ev.base = ev_scratch + (size_t)blockIdx.x * EV_CAP * EPI_THREADS + et;
+        ev.base = ev_scratch + ((size_t)blockIdx.x * EPI_THREADS + et) * (EV_CAP * EV_WORDS);
         ev.n = 0;
-        if (half == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; }
+        if (colq == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; }
         uint32_t n_it = 0;
         for (int rd = 0; rd < rounds; ++rd) {
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
@@ -378,35 +383,19 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 mbar_wait(smem_u32(&bars->e2_full[es]), (n_it / E2_SLOTS) & 1);
                 mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + t_lane + as * BN + half * (BN / 2);
-                const float* e2s = sE2 + es * BN + half * (BN / 2);
-                const int code0 = nt * BN + half * (BN / 2);
-                uint32_t ra[32], rb[32];
-                tmem_ld32(taddr, ra);
-                tmem_ld_wait(ra);
-                if (scores_dbg) {
-                    float* row_out = scores_dbg + (size_t)row * K;
-                    tmem_ld32(taddr + 32, rb);
-                    if (row < N) dump_slab(ra, e2s, code0, K, row_out);
-                    tmem_ld_wait(rb);
-                    tmem_ld32(taddr + 64, ra);
-                    if (row < N) dump_slab(rb, e2s + 32, code0 + 32, K, row_out);
+                const uint32_t taddr = tmem_base + t_lane + as * BN + colq * COLS_PER_WARP;
+                const float* e2s = sE2 + es * BN + colq * COLS_PER_WARP;
+                const int code0 = nt * BN + colq * COLS_PER_WARP;
+                uint32_t ra[32];
+#pragma unroll
+                for (int sb = 0; sb < COLS_PER_WARP / 32; ++sb) {
+                    tmem_ld32(taddr + sb * 32, ra);
                     tmem_ld_wait(ra);
-                    tmem_ld32(taddr + 96, rb);
-                    if (row < N) dump_slab(ra, e2s + 64, code0 + 64, K, row_out);
-                    tmem_ld_wait(rb);
-                    if (row < N) dump_slab(rb, e2s + 96, code0 + 96, K, row_out);
-                } else {
-                    tmem_ld32(taddr + 32, rb);
-                    scan_slab(ra, e2s, code0, band, thr, ev);
-                    tmem_ld_wait(rb);
-                    tmem_ld32(taddr + 64, ra);
-                    scan_slab(rb, e2s + 32, code0 + 32, band, thr, ev);
-                    tmem_ld_wait(ra);
-                    tmem_ld32(taddr + 96, rb);
-                    scan_slab(ra, e2s + 64, code0 + 64, band, thr, ev);
-                    tmem_ld_wait(rb);
-                    scan_slab(rb, e2s + 96, code0 + 96, band, thr, ev);
+                    if (scores_dbg) {
+                        if (row < N) dump_slab(ra, e2s + sb * 32, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
+                    } else {
+                        scan_slab(ra, e2s + sb * 32, (code0 + sb * 32) >> 3, band, thr, ev);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -415,26 +404,41 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     mbar_arrive(smem_u32(&bars->e2_empty[es]));
                 }
             }
-            // ---- filter this thread's events against the frame's final minimum and publish the shortlist
-            sMin[half * BM + row_in_tile] = thr - band;                      // running minimum of this column half
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // ---- resolve this thread's chunks against the frame's final minimum and publish the shortlist
+            sMin[colq * BM + row_in_tile] = thr - band;                      // running minimum of this column quarter
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             if (row < N && !scores_dbg) {
-                const float cutoff = fminf(sMin[row_in_tile], sMin[BM + row_in_tile]) + band;
+                const float gmin = fminf(fminf(sMin[row_in_tile], sMin[BM + row_in_tile]),
+                                         fminf(sMin[2 * BM + row_in_tile], sMin[3 * BM + row_in_tile]));
+                const float cutoff = gmin + band;
                 uint16_t* dst = cand_idx + (size_t)row * kCandMax;
                 const int n_ev = ev.n < EV_CAP ? ev.n : EV_CAP;
                 bool lost = ev.n > EV_CAP || !(band < INFINITY);
                 for (int e = 0; e < n_ev; ++e) {
-                    const uint2 en = ev.base[(size_t)e * EPI_THREADS];
-                    if (__uint_as_float(en.x) <= cutoff) {
-                        const int pos = atomicAdd(&sCnt[row_in_tile], 1);
-                        if (pos < kCandFill) dst[pos] = (uint16_t)en.y;
-                        else lost = true;
+                    const uint32_t* en = ev.base + e * EV_WORDS;
+                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 8);
+                    if (__uint_as_float(hd.x) <= cutoff) {
+                        const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 4);
+                        const int k0 = (int)hd.y * 8;
+                        const float4 e0 = *reinterpret_cast<const float4*>(e2 + k0), e1 = *reinterpret_cast<const float4*>(e2 + k0 + 4);
+                        const float sc[8] = {fmaf(-2.f, __uint_as_float(a0.x), e0.x), fmaf(-2.f, __uint_as_float(a0.y), e0.y),
+                                             fmaf(-2.f, __uint_as_float(a0.z), e0.z), fmaf(-2.f, __uint_as_float(a0.w), e0.w),
+                                             fmaf(-2.f, __uint_as_float(a1.x), e1.x), fmaf(-2.f, __uint_as_float(a1.y), e1.y),
+                                             fmaf(-2.f, __uint_as_float(a1.z), e1.z), fmaf(-2.f, __uint_as_float(a1.w), e1.w)};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (sc[j] <= cutoff) {
+                                const int pos = atomicAdd(&sCnt[row_in_tile], 1);
+                                if (pos < kCandFill) dst[pos] = (uint16_t)(k0 + j);
+                                else lost = true;
+                            }
+                        }
                     }
                 }
                 if (lost) sCnt[BM + row_in_tile] = 1;
             }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (half == 0) {
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (colq == 0) {
                 if (row < N && !scores_dbg) {
                     const int cnt = sCnt[row_in_tile];
                     if (force_fallback || cnt == 0 || sCnt[BM + row_in_tile]) {
@@ -442,7 +446,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         fallback_rows[atomicAdd(&meta->fallback_count, 1)] = (int)row;
                         atomicAdd(&meta->fallback_total, 1ull);
                     } else {
-                        cand_cnt[row] = (uint8_t)cnt;
+                        cand_cnt[row] = (uint8_t)(cnt < kCandFill ? cnt : kCandFill);
                     }
                 }
                 sCnt[row_in_tile] = 0;
@@ -493,7 +497,7 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 
 }  // namespace tc
 
-size_t tc_event_scratch_bytes() { return (size_t)kTcMaxCtas * tc::EV_CAP * tc::EPI_THREADS * sizeof(uint2); }
+size_t tc_event_scratch_bytes() { return (size_t)kTcMaxCtas * tc::EPI_THREADS * tc::EV_CAP * tc::EV_WORDS * 4; }
 
 // ---- optional CUDA-event timing of the dominant kernel, on the launching stream (bench.py's roofline leg) -------
 struct TimingSlot { cudaEvent_t start, stop; };
@@ -525,7 +529,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     if ((rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM)) != 0) return rc;
     const int num_kb = (D + BK - 1) / BK;
     const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + 2 * BM * 4 + 2 * BM * 4 + sizeof(Barriers) + 1024;
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + 4 * BM * 4 + 2 * BM * 4 + sizeof(Barriers) + 1024;
     int b_stages = (int)((227 * 1024 - fixed) / B_STAGE_BYTES);
     if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
     if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
@@ -564,7 +568,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     cfg.numAttrs = 1;
     TimingSlot* slot = timing_begin(s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, tc_search_kernel, mx, me_c, e2, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs,
-                                        K, cand_cnt, cand_idx, fallback_rows, meta, scores_dbg, reinterpret_cast<uint2*>(ev_scratch));
+                                        K, cand_cnt, cand_idx, fallback_rows, meta, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
     if (le != cudaSuccess) return cuda_fail(le, "tc_search_kernel launch");
     cudaError_t e = cudaGetLastError();
     timing_end(slot, s);
