@@ -9,12 +9,12 @@
 // operation order, which decides the index; frames whose shortlist overflowed go to the exact fp32 search.
 //
 // Structure (one persistent CTA per SM, 640 threads, warp-specialised):
-//   warp 0      TMA producer: latent tile A (128 frames x D, resident per M tile) and codebook tiles B
+//   warps 0-15  epilogue: warp w owns TMEM lanes 32*(w%4).., column quarter w/4 (64 of the 256 columns)
+//   warp 16     TMA producer (one thread): latent tile A (128 frames x D, resident per M tile) and codebook tiles B
 //               (256 codes x 64 dims per stage) as 128B-swizzled K-major boxes, |e|^2 slices by bulk copy
-//   warp 1      MMA issuer: one lane issues tcgen05.mma cta_group::1 kind::f16 M128 N256 K16, fp32 accumulate,
-//               two TMEM accumulator stages (2 x 256 columns) so the epilogue of tile j overlaps the MMAs of tile j+1
-//   warp 2      TMEM allocator
-//   warps 4-19  epilogue: warp w owns TMEM lanes 32*(w%4).., column quarter (w-4)/4 (64 of the 256 columns)
+//   warp 17     MMA issuer (one thread): tcgen05.mma cta_group::1 kind::f16 M128 N256 K16, fp32 accumulate, two TMEM
+//               accumulator stages (2 x 256 columns) so the epilogue of tile j overlaps the MMAs of tile j+1
+//   warp 18     TMEM allocator
 #include "vqb_internal.h"
 
 #include <cuda.h>
@@ -33,8 +33,10 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int E2_SLICE_BYTES = BN * 4;       // 1 KiB
 constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 4;
 constexpr int E2_SLOTS = 4;                  // |e|^2 slices ride their own ring so the producer never waits on the epilogue
-constexpr int EPI_WARP0 = 4, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;   // 4 warps per TMEM lane quarter: 64 columns each
-constexpr int NUM_THREADS = EPI_WARP0 * 32 + EPI_THREADS;                      // 640
+constexpr int EPI_WARP0 = 0, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;   // 4 warps per TMEM lane quarter: 64 columns each
+// The single-thread producer / MMA loops sit in the HIGHEST warp ids: the scheduler favours them over waiting epilogue warps.
+constexpr int PRODUCER_WARP = 16, MMA_WARP = 17, ALLOC_WARP = 18;
+constexpr int NUM_THREADS = EPI_THREADS + 4 * 32;                              // 640
 constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);                            // 64
 constexpr int kCandFill = 12;                // shortlist entries published per frame (cand_idx rows hold kCandMax = 16)
 
@@ -58,23 +60,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a pipeline bug must become a trapped launch, never a hung GPU.
+// Bounded wait: a pipeline bug must become a trapped launch, never a hung GPU.  try_wait carries a suspend-time hint, so
+// a waiting warp sleeps in hardware (and is woken by the completing arrive) instead of burning issue slots that the
+// single-thread producer / MMA loops on the same scheduler need.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     long long t0 = 0;
     for (uint32_t it = 0;; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
         if (ok) return;
-        if ((it & 1023u) == 1023u) {
+        if ((it & 63u) == 63u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();   // ~2 s
+            else if (now - t0 > 8000000000LL) __trap();   // seconds: only a broken pipeline gets here
         }
     }
 }
@@ -262,11 +266,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int cluster_id = (int)blockIdx.x / cs;
     const int rounds = (num_m_tiles + n_clusters * cs - 1) / (n_clusters * cs);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == PRODUCER_WARP && lane == 0) {
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_e);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == MMA_WARP && lane == 0) {
         for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), cs); }
         for (int i = 0; i < a_slots; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
         for (int i = 0; i < E2_SLOTS; ++i) {
@@ -279,86 +283,83 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    if (warp == ALLOC_WARP) tmem_alloc(smem_u32(&bars->tmem_base), 512);
     tc_fence_before();
     __syncthreads();
     if (cs > 1) cluster_sync_all();   // peers must see initialised barriers before the first multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 0) {
-        // ================================================================ TMA producer
-        uint32_t a_it = 0, b_it = 0, n_it = 0;
-        for (int rd = 0; rd < rounds; ++rd) {
-            const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
-            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
-                const uint32_t es = n_it % E2_SLOTS;
-                mbar_wait(smem_u32(&bars->e2_empty[es]), ((n_it / E2_SLOTS) & 1) ^ 1);
-                if (lane == 0) {
+    if (warp == PRODUCER_WARP) {
+        // ================================================================ TMA producer (one thread)
+        if (lane == 0) {
+            uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, es = 0, e_ph = 0;
+            const uint32_t slice = (uint32_t)B_STAGE_BYTES / (uint32_t)cs;
+            for (int rd = 0; rd < rounds; ++rd) {
+                const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
+                const int a_row = (mt < num_m_tiles ? mt : 0) * BM;               // dummy tiles re-read tile 0, nothing is published
+                for (int nt = 0; nt < num_n_tiles; ++nt) {
+                    mbar_wait(smem_u32(&bars->e2_empty[es]), e_ph ^ 1);
                     mbar_expect_tx(smem_u32(&bars->e2_full[es]), E2_SLICE_BYTES);
                     bulk_load_1d(smem_u32(sE2 + es * BN), e2 + (size_t)nt * BN, E2_SLICE_BYTES, smem_u32(&bars->e2_full[es]));
-                }
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    if (nt == 0) {
-                        const uint32_t slot = a_it % a_slots, ph = (a_it / a_slots) & 1;
-                        mbar_wait(smem_u32(&bars->a_empty[slot]), ph ^ 1);
-                        if (lane == 0) {
+                    if (++es == E2_SLOTS) { es = 0; e_ph ^= 1; }
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        if (nt == 0) {
+                            const uint32_t slot = a_slot0 + kb;
+                            mbar_wait(smem_u32(&bars->a_empty[slot]), a_ph ^ 1);
                             mbar_expect_tx(smem_u32(&bars->a_full[slot]), A_CHUNK_BYTES);
-                            tma_load_2d(smem_u32(sA + (size_t)slot * A_CHUNK_BYTES), &tmap_x, smem_u32(&bars->a_full[slot]), kb * BK,
-                                        (mt < num_m_tiles ? mt : 0) * BM);   // dummy tiles re-read tile 0, nothing is published
+                            tma_load_2d(smem_u32(sA + (size_t)slot * A_CHUNK_BYTES), &tmap_x, smem_u32(&bars->a_full[slot]), kb * BK, a_row);
                         }
-                        ++a_it;
+                        mbar_wait(smem_u32(&bars->b_empty[b_st]), b_ph ^ 1);
+                        mbar_expect_tx(smem_u32(&bars->b_full[b_st]), B_STAGE_BYTES);   // own slice + the peers' slices
+                        if (cs == 1)
+                            tma_load_2d(smem_u32(sB + (size_t)b_st * B_STAGE_BYTES), &tmap_e, smem_u32(&bars->b_full[b_st]), kb * BK, nt * BN);
+                        else
+                            tma_load_2d_mc(smem_u32(sB + (size_t)b_st * B_STAGE_BYTES) + crank * slice, &tmap_e,
+                                           smem_u32(&bars->b_full[b_st]), kb * BK, nt * BN + (int)crank * (BN / cs), cmask);
+                        if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
                     }
-                    const uint32_t st = b_it % b_stages, ph = (b_it / b_stages) & 1;
-                    mbar_wait(smem_u32(&bars->b_empty[st]), ph ^ 1);
-                    if (lane == 0) {
-                        mbar_expect_tx(smem_u32(&bars->b_full[st]), B_STAGE_BYTES);   // own slice + the peers' slices
-                        if (cs == 1) {
-                            tma_load_2d(smem_u32(sB + (size_t)st * B_STAGE_BYTES), &tmap_e, smem_u32(&bars->b_full[st]), kb * BK, nt * BN);
-                        } else {
-                            const uint32_t slice = (uint32_t)B_STAGE_BYTES / (uint32_t)cs;
-                            tma_load_2d_mc(smem_u32(sB + (size_t)st * B_STAGE_BYTES) + crank * slice, &tmap_e, smem_u32(&bars->b_full[st]),
-                                           kb * BK, nt * BN + (int)crank * (BN / cs), cmask);
-                        }
-                    }
-                    ++b_it;
                 }
+                a_slot0 += num_kb;
+                if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ================================================================ MMA issuer
-        uint32_t a_base = 0, b_it = 0, n_it = 0;   // a_base: A chunk counter at the start of the current M tile
-        for (int rd = 0; rd < rounds; ++rd) {
-            const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
-            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
-                const uint32_t as = n_it & 1;
-                mbar_wait(smem_u32(&bars->tmem_empty[as]), ((n_it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const uint32_t a_idx = a_base + kb, slot = a_idx % a_slots;
-                    if (nt == 0) mbar_wait(smem_u32(&bars->a_full[slot]), (a_idx / a_slots) & 1);
-                    const uint32_t st = b_it % b_stages;
-                    mbar_wait(smem_u32(&bars->b_full[st]), (b_it / b_stages) & 1);
+        __syncwarp();
+    } else if (warp == MMA_WARP) {
+        // ================================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, as = 0, t_ph = 0;
+            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            for (int rd = 0; rd < rounds; ++rd) {
+                for (int nt = 0; nt < num_n_tiles; ++nt) {
+                    mbar_wait(smem_u32(&bars->tmem_empty[as]), t_ph ^ 1);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint64_t da = make_desc_sw128(smem_u32(sA + (size_t)slot * A_CHUNK_BYTES));
-                        const uint64_t db = make_desc_sw128(smem_u32(sB + (size_t)st * B_STAGE_BYTES));
+                    const uint32_t tmem_d = tmem_base + as * BN;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        const uint32_t slot = a_slot0 + kb;
+                        if (nt == 0) mbar_wait(smem_u32(&bars->a_full[slot]), a_ph);
+                        mbar_wait(smem_u32(&bars->b_full[b_st]), b_ph);
+                        tc_fence_after();
+                        const uint64_t da = make_desc_sw128(sA_u + slot * A_CHUNK_BYTES);
+                        const uint64_t db = make_desc_sw128(sB_u + b_st * B_STAGE_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes per K step inside the swizzle row: +2 in 16-byte units
                             umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
-                        if (cs == 1) umma_commit(smem_u32(&bars->b_empty[st]));
-                        else umma_commit_mc(smem_u32(&bars->b_empty[st]), cmask);
+                        if (cs == 1) umma_commit(smem_u32(&bars->b_empty[b_st]));
+                        else umma_commit_mc(smem_u32(&bars->b_empty[b_st]), cmask);
                         if (nt == num_n_tiles - 1) umma_commit(smem_u32(&bars->a_empty[slot]));
                         if (kb == num_kb - 1) umma_commit(smem_u32(&bars->tmem_full[as]));
+                        if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
                     }
-                    __syncwarp();
-                    ++b_it;
+                    as ^= 1;
+                    if (as == 0) t_ph ^= 1;
                 }
+                a_slot0 += num_kb;
+                if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
             }
-            a_base += num_kb;
         }
-    } else if (warp >= EPI_WARP0) {
+        __syncwarp();
+    } else if (warp < EPI_WARPS) {
         // ================================================================ epilogue
         const int ew = warp - EPI_WARP0;
         const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32*quarter .. +31
@@ -458,7 +459,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (cs > 1) cluster_sync_all();   // no CTA may retire while a peer can still multicast into it or arrive on its barriers
-    if (warp == 2) {
+    if (warp == ALLOC_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
