@@ -82,6 +82,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// One lane of a converged warp; ptxas recognises the elect.sync predicate and issues the following tcgen05 / TMA
+// instructions directly instead of wrapping each one in an elect-and-retry loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -181,7 +192,7 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 // Which codes of the surviving chunks are really inside the band is worked out once per frame tile, after the sweep,
 // against the frame's final minimum.  EV_CAP chunks per thread and frame tile; running out (adversarial orderings) only
 // sends that frame to the exact search.
-constexpr int EV_CAP = 24;
+constexpr int EV_CAP = 32;
 constexpr int EV_WORDS = 12;   // 8 accumulators, chunk minimum, chunk id, 2 pad
 
 struct EventStack {
@@ -291,74 +302,87 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == PRODUCER_WARP) {
-        // ================================================================ TMA producer (one thread)
-        if (lane == 0) {
-            uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, es = 0, e_ph = 0;
-            const uint32_t slice = (uint32_t)B_STAGE_BYTES / (uint32_t)cs;
-            for (int rd = 0; rd < rounds; ++rd) {
-                const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
-                const int a_row = (mt < num_m_tiles ? mt : 0) * BM;               // dummy tiles re-read tile 0, nothing is published
-                for (int nt = 0; nt < num_n_tiles; ++nt) {
-                    mbar_wait(smem_u32(&bars->e2_empty[es]), e_ph ^ 1);
-                    mbar_expect_tx(smem_u32(&bars->e2_full[es]), E2_SLICE_BYTES);
-                    bulk_load_1d(smem_u32(sE2 + es * BN), e2 + (size_t)nt * BN, E2_SLICE_BYTES, smem_u32(&bars->e2_full[es]));
-                    if (++es == E2_SLOTS) { es = 0; e_ph ^= 1; }
-                    for (int kb = 0; kb < num_kb; ++kb) {
+        // ================================================================ TMA producer (converged warp, one elected lane issues)
+        uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, es = 0, e_ph = 0;
+        const uint32_t slice = (uint32_t)B_STAGE_BYTES / (uint32_t)cs;
+        const int b_row_off = (int)crank * (BN / cs);
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB) + crank * slice, sE_u = smem_u32(sE2);
+        const uint32_t bar_afull = smem_u32(&bars->a_full[0]), bar_aempty = smem_u32(&bars->a_empty[0]);
+        const uint32_t bar_bfull = smem_u32(&bars->b_full[0]), bar_bempty = smem_u32(&bars->b_empty[0]);
+        const uint32_t bar_efull = smem_u32(&bars->e2_full[0]), bar_eempty = smem_u32(&bars->e2_empty[0]);
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
+            const int a_row = (mt < num_m_tiles ? mt : 0) * BM;               // dummy tiles re-read tile 0, nothing is published
+            for (int nt = 0; nt < num_n_tiles; ++nt) {
+                mbar_wait(bar_eempty + es * 8, e_ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_efull + es * 8, E2_SLICE_BYTES);
+                    bulk_load_1d(sE_u + es * E2_SLICE_BYTES, e2 + (size_t)nt * BN, E2_SLICE_BYTES, bar_efull + es * 8);
+                }
+                __syncwarp();
+                if (++es == E2_SLOTS) { es = 0; e_ph ^= 1; }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const uint32_t slot = a_slot0 + kb;
+                    if (nt == 0) mbar_wait(bar_aempty + slot * 8, a_ph ^ 1);
+                    mbar_wait(bar_bempty + b_st * 8, b_ph ^ 1);
+                    if (elect_one()) {
                         if (nt == 0) {
-                            const uint32_t slot = a_slot0 + kb;
-                            mbar_wait(smem_u32(&bars->a_empty[slot]), a_ph ^ 1);
-                            mbar_expect_tx(smem_u32(&bars->a_full[slot]), A_CHUNK_BYTES);
-                            tma_load_2d(smem_u32(sA + (size_t)slot * A_CHUNK_BYTES), &tmap_x, smem_u32(&bars->a_full[slot]), kb * BK, a_row);
+                            mbar_expect_tx(bar_afull + slot * 8, A_CHUNK_BYTES);
+                            tma_load_2d(sA_u + slot * A_CHUNK_BYTES, &tmap_x, bar_afull + slot * 8, kb * BK, a_row);
                         }
-                        mbar_wait(smem_u32(&bars->b_empty[b_st]), b_ph ^ 1);
-                        mbar_expect_tx(smem_u32(&bars->b_full[b_st]), B_STAGE_BYTES);   // own slice + the peers' slices
+                        mbar_expect_tx(bar_bfull + b_st * 8, B_STAGE_BYTES);   // own slice + the peers' slices
                         if (cs == 1)
-                            tma_load_2d(smem_u32(sB + (size_t)b_st * B_STAGE_BYTES), &tmap_e, smem_u32(&bars->b_full[b_st]), kb * BK, nt * BN);
+                            tma_load_2d(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN);
                         else
-                            tma_load_2d_mc(smem_u32(sB + (size_t)b_st * B_STAGE_BYTES) + crank * slice, &tmap_e,
-                                           smem_u32(&bars->b_full[b_st]), kb * BK, nt * BN + (int)crank * (BN / cs), cmask);
-                        if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
+                            tma_load_2d_mc(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN + b_row_off, cmask);
                     }
+                    __syncwarp();
+                    if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
                 }
-                a_slot0 += num_kb;
-                if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
             }
+            a_slot0 += num_kb;
+            if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
         }
-        __syncwarp();
     } else if (warp == MMA_WARP) {
-        // ================================================================ MMA issuer (one thread)
-        if (lane == 0) {
-            uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, as = 0, t_ph = 0;
-            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-            for (int rd = 0; rd < rounds; ++rd) {
-                for (int nt = 0; nt < num_n_tiles; ++nt) {
-                    mbar_wait(smem_u32(&bars->tmem_empty[as]), t_ph ^ 1);
+        // ================================================================ MMA issuer (converged warp, one elected lane issues)
+        uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, as = 0, t_ph = 0;
+        const uint64_t dA0 = make_desc_sw128(smem_u32(sA)), dB0 = make_desc_sw128(smem_u32(sB));
+        const uint32_t bar_afull = smem_u32(&bars->a_full[0]), bar_aempty = smem_u32(&bars->a_empty[0]);
+        const uint32_t bar_bfull = smem_u32(&bars->b_full[0]), bar_bempty = smem_u32(&bars->b_empty[0]);
+        const uint32_t bar_tfull = smem_u32(&bars->tmem_full[0]), bar_tempty = smem_u32(&bars->tmem_empty[0]);
+        for (int rd = 0; rd < rounds; ++rd) {
+            for (int nt = 0; nt < num_n_tiles; ++nt) {
+                mbar_wait(bar_tempty + as * 8, t_ph ^ 1);
+                const uint32_t tmem_d = tmem_base + as * BN;
+                const bool last_nt = nt == num_n_tiles - 1;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const uint32_t slot = a_slot0 + kb;
+                    if (nt == 0) mbar_wait(bar_afull + slot * 8, a_ph);
+                    mbar_wait(bar_bfull + b_st * 8, b_ph);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + as * BN;
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        const uint32_t slot = a_slot0 + kb;
-                        if (nt == 0) mbar_wait(smem_u32(&bars->a_full[slot]), a_ph);
-                        mbar_wait(smem_u32(&bars->b_full[b_st]), b_ph);
-                        tc_fence_after();
-                        const uint64_t da = make_desc_sw128(sA_u + slot * A_CHUNK_BYTES);
-                        const uint64_t db = make_desc_sw128(sB_u + b_st * B_STAGE_BYTES);
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes per K step inside the swizzle row: +2 in 16-byte units
-                            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
-                        if (cs == 1) umma_commit(smem_u32(&bars->b_empty[b_st]));
-                        else umma_commit_mc(smem_u32(&bars->b_empty[b_st]), cmask);
-                        if (nt == num_n_tiles - 1) umma_commit(smem_u32(&bars->a_empty[slot]));
-                        if (kb == num_kb - 1) umma_commit(smem_u32(&bars->tmem_full[as]));
-                        if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
+                    if (elect_one()) {
+                        // descriptors address shared memory in 16-byte units: +1024 per 16 KiB A chunk, +2048 per 32 KiB B stage,
+                        // +2 per K step of 16 bf16 (32 bytes) inside the 128-byte swizzle row
+                        const uint64_t da = dA0 + (uint64_t)(slot * (A_CHUNK_BYTES >> 4));
+                        const uint64_t db = dB0 + (uint64_t)(b_st * (B_STAGE_BYTES >> 4));
+                        umma_bf16(tmem_d, da, db, kIdesc, kb ? 1u : 0u);
+                        umma_bf16(tmem_d, da + 2, db + 2, kIdesc, 1u);
+                        umma_bf16(tmem_d, da + 4, db + 4, kIdesc, 1u);
+                        umma_bf16(tmem_d, da + 6, db + 6, kIdesc, 1u);
+                        if (cs == 1) umma_commit(bar_bempty + b_st * 8);
+                        else umma_commit_mc(bar_bempty + b_st * 8, cmask);
+                        if (last_nt) umma_commit(bar_aempty + slot * 8);
+                        if (kb == num_kb - 1) umma_commit(bar_tfull + as * 8);
                     }
-                    as ^= 1;
-                    if (as == 0) t_ph ^= 1;
+                    __syncwarp();
+                    if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
                 }
-                a_slot0 += num_kb;
-                if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
+                as ^= 1;
+                if (as == 0) t_ph ^= 1;
             }
+            a_slot0 += num_kb;
+            if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
         }
-        __syncwarp();
     } else if (warp < EPI_WARPS) {
         // ================================================================ epilogue
         const int ew = warp - EPI_WARP0;
@@ -415,23 +439,30 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 uint16_t* dst = cand_idx + (size_t)row * kCandMax;
                 const int n_ev = ev.n < EV_CAP ? ev.n : EV_CAP;
                 bool lost = ev.n > EV_CAP || !(band < INFINITY);
-                for (int e = 0; e < n_ev; ++e) {
-                    const uint32_t* en = ev.base + e * EV_WORDS;
-                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 8);
-                    if (__uint_as_float(hd.x) <= cutoff) {
-                        const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 4);
-                        const int k0 = (int)hd.y * 8;
-                        const float4 e0 = *reinterpret_cast<const float4*>(e2 + k0), e1 = *reinterpret_cast<const float4*>(e2 + k0 + 4);
-                        const float sc[8] = {fmaf(-2.f, __uint_as_float(a0.x), e0.x), fmaf(-2.f, __uint_as_float(a0.y), e0.y),
-                                             fmaf(-2.f, __uint_as_float(a0.z), e0.z), fmaf(-2.f, __uint_as_float(a0.w), e0.w),
-                                             fmaf(-2.f, __uint_as_float(a1.x), e1.x), fmaf(-2.f, __uint_as_float(a1.y), e1.y),
-                                             fmaf(-2.f, __uint_as_float(a1.z), e1.z), fmaf(-2.f, __uint_as_float(a1.w), e1.w)};
+                for (int e0 = 0; e0 < n_ev; e0 += 8) {
+                    uint2 hd[8];     // headers (chunk minimum, chunk id) of 8 events fetched together: one L2 latency, not eight
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (sc[j] <= cutoff) {
-                                const int pos = atomicAdd(&sCnt[row_in_tile], 1);
-                                if (pos < kCandFill) dst[pos] = (uint16_t)(k0 + j);
-                                else lost = true;
+                    for (int u = 0; u < 8; ++u)
+                        hd[u] = (e0 + u < n_ev) ? *reinterpret_cast<const uint2*>(ev.base + (e0 + u) * EV_WORDS + 8)
+                                                : make_uint2(0x7f800000u, 0u);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (__uint_as_float(hd[u].x) <= cutoff) {
+                            const uint32_t* en = ev.base + (e0 + u) * EV_WORDS;
+                            const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 4);
+                            const int k0 = (int)hd[u].y * 8;
+                            const float4 e0v = *reinterpret_cast<const float4*>(e2 + k0), e1v = *reinterpret_cast<const float4*>(e2 + k0 + 4);
+                            const float sc[8] = {fmaf(-2.f, __uint_as_float(a0.x), e0v.x), fmaf(-2.f, __uint_as_float(a0.y), e0v.y),
+                                                 fmaf(-2.f, __uint_as_float(a0.z), e0v.z), fmaf(-2.f, __uint_as_float(a0.w), e0v.w),
+                                                 fmaf(-2.f, __uint_as_float(a1.x), e1v.x), fmaf(-2.f, __uint_as_float(a1.y), e1v.y),
+                                                 fmaf(-2.f, __uint_as_float(a1.z), e1v.z), fmaf(-2.f, __uint_as_float(a1.w), e1v.w)};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (sc[j] <= cutoff) {
+                                    const int pos = atomicAdd(&sCnt[row_in_tile], 1);
+                                    if (pos < kCandFill) dst[pos] = (uint16_t)(k0 + j);
+                                    else lost = true;
+                                }
                             }
                         }
                     }
