@@ -40,7 +40,7 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags) {
     L.sse_partials = take((size_t)L.n_partials * 8);
     if (prec == VQB_PREC_FP32) {
         L.idx32 = take((size_t)N * 4);
-        L.cand_cnt = L.cand_idx = L.fallback_rows = L.x2 = L.eb = L.xb = L.ev = 0;
+        L.cand_cnt = L.cand_idx = L.fallback_rows = L.x2 = L.eb = L.eh = L.xb = L.ev = 0;
     } else {
         L.idx32 = 0;
         L.cand_cnt = take((size_t)L.n_pad);
@@ -48,6 +48,7 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags) {
         L.fallback_rows = take((size_t)L.n_pad * 4);
         L.x2 = take((size_t)L.n_pad * 4);
         L.eb = take((size_t)L.k_pad * D * 2);
+        L.eh = take((size_t)L.k_pad * 16);
         L.xb = take((size_t)L.n_pad * D * 2);
         L.ev = take(tc_event_scratch_bytes());
     }
@@ -137,7 +138,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
 
     if (prec == VQB_PREC_FP32) {
         int* idx32 = reinterpret_cast<int*>(ws + L.idx32);
-        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, nullptr, meta, s), "codebook_prep");
+        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, nullptr, nullptr, meta, s), "codebook_prep");
         VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, nullptr, nullptr, idx32, nullptr, nullptr, s), "exact_search");
         VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, idx32, nullptr, nullptr, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
                              counts, resid, part, L.n_partials, meta, s), "tail");
@@ -148,9 +149,10 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         float* x2 = reinterpret_cast<float*>(ws + L.x2);
         __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(ws + L.eb);
         __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + L.xb);
-        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, eb, meta, s), "codebook_prep");
+        __nv_bfloat16* eh = reinterpret_cast<__nv_bfloat16*>(ws + L.eh);
+        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, eb, eh, meta, s), "codebook_prep");
         VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");
-        rc = launch_tc_search(xb, eb, e2, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, scores_dbg, ws + L.ev, s);
+        rc = launch_tc_search(xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, scores_dbg, ws + L.ev, s);
         if (rc != 0) return rc;
         if (scores_dbg) return 0;
         VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, fb_rows, &meta->fallback_count, nullptr, cand_cnt, cand_idx, s),

@@ -28,7 +28,7 @@ struct WsMeta {
 };
 
 struct WsLayout {
-    size_t meta, e2, counts, sse_partials, idx32, cand_cnt, cand_idx, fallback_rows, x2, eb, xb, ev, total;
+    size_t meta, e2, counts, sse_partials, idx32, cand_cnt, cand_idx, fallback_rows, x2, eb, eh, xb, ev, total;
     int    k_pad;
     int64_t n_pad;
     int    n_partials;
@@ -45,7 +45,7 @@ int  cuda_fail(cudaError_t e, const char* what);   // records message, returns (
 
 // ---- launchers (vqb_kernels.cu) -------------------------------------------------------------------------------
 cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb,
-                                 WsMeta* meta, cudaStream_t s);
+                                 __nv_bfloat16* eh, WsMeta* meta, cudaStream_t s);
 cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int64_t N_pad, __nv_bfloat16* xb, float* band,
                                     const WsMeta* meta, cudaStream_t s);
 // rows == nullptr: all N frames -> idx32[n]; else the frames listed in rows[0..*row_count) -> cand_cnt/cand_idx (count 1)
@@ -68,7 +68,7 @@ cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int6
 
 // ---- tensor-core search (vqb_tc.cu) ---------------------------------------------------------------------------
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.
-int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const float* e2, const float* band, int64_t N, int64_t N_pad,
+int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh, const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
                      float* scores_dbg, void* ev_scratch, cudaStream_t s);
 

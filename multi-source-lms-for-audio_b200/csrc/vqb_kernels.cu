@@ -44,7 +44,7 @@ __device__ __forceinline__ float ref_distance(float x2, float e2, float dot) {
 // guard band, non-finite flag.  Rows K..K_pad-1 get e2 = +inf (never shortlisted) and zero operands.
 __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restrict__ E, int K, int K_pad, int D,
                                                             float* __restrict__ e2, __nv_bfloat16* __restrict__ eb,
-                                                            WsMeta* meta) {
+                                                            __nv_bfloat16* __restrict__ eh, WsMeta* meta) {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= K_pad) return;
@@ -77,12 +77,24 @@ __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restr
         } else {
             e2[k] = INFINITY;
         }
+        if (eh) {
+            // three-term bf16 split of |e_k|^2 / 2 (24 bits): the bias operand of the tensor-core contraction.
+            // Padding codes get a huge finite bias so their accumulator can never be the maximum.
+            const float half = (k < K) ? 0.5f * s : 3.0e38f;
+            const __nv_bfloat16 h1 = __float2bfloat16_rn(half);
+            const float r1 = half - __bfloat162float(h1);
+            const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
+            __nv_bfloat16* o = eh + (size_t)k * 8;
+            o[0] = h1; o[1] = (k < K) ? h2 : __float2bfloat16_rn(0.f); o[2] = (k < K) ? h3 : __float2bfloat16_rn(0.f);
+            o[3] = o[4] = o[5] = o[6] = o[7] = __float2bfloat16_rn(0.f);
+        }
     }
 }
 
-cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb, WsMeta* meta,
-                                 cudaStream_t s) {
-    codebook_prep_kernel<<<(K_pad + 7) / 8, 256, 0, s>>>(codebook, K, K_pad, D, e2, eb, meta);
+cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb, __nv_bfloat16* eh,
+                                 WsMeta* meta, cudaStream_t s) {
+    codebook_prep_kernel<<<(K_pad + 7) / 8, 256, 0, s>>>(codebook, K, K_pad, D, e2, eb, eh, meta);
     note_launch();
     return cudaGetLastError();
 }
@@ -128,7 +140,9 @@ __global__ void __launch_bounds__(256) latent_prep_bf16_kernel(const float* __re
         const float etmax = sqrtf(__uint_as_float(meta->etmax2_bits)) * 1.0001f;
         const float demax = sqrtf(__uint_as_float(meta->demax2_bits)) * 1.0001f;
         const float emax = sqrtf(__uint_as_float(meta->emax2_bits)) * 1.0001f;
-        band[n] = 4.0f * (dxn * etmax + xn * demax) * 1.001f + 8.0f * (float)D * 2.3841858e-07f * xn * emax + 1e-30f;
+        // last terms: fp32 accumulation (tensor core and the reference's sgemm), the 3-term bf16 split of |e|^2/2
+        band[n] = 4.0f * (dxn * etmax + xn * demax) * 1.001f + 8.0f * (float)(D + 16) * 2.3841858e-07f * xn * emax +
+                  4.0e-7f * emax * emax + 1e-30f;
     }
     const uint32_t* Xw = reinterpret_cast<const uint32_t*>(Xs);
     const int wstride = stride / 2;

@@ -1,6 +1,11 @@
 // Tensor-core nearest-code shortlist for sm_100a: the fused distance + running-argmin kernel.
 //
 //   score[n, k] = |e_k|^2 - 2 * bf16(x_n) . bf16(e_k)        (the |x_n|^2 term is constant per frame)
+//               = -2 * acc[n, k],   acc = bf16(x_n) . bf16(e_k) - |e_k|^2 / 2
+//
+// The bias is folded INTO the tensor-core contraction: one extra K step per tile multiplies a constant A operand
+// (-1, -1, -1, 0...) with (h1, h2, h3, 0...), the three-term bf16 split of |e_k|^2 / 2, so the accumulator already is the
+// (negated, halved) score and the epilogue is a pure running arg-max - no bias loads, no FMAs.
 //
 // replaces `distances` + `argmin` of src/model/components/vector_quantizer.py:32-37.  The N x K score matrix never
 // leaves the SM: tcgen05.mma accumulates a 128-frame x 256-code tile in TMEM, epilogue warps pull it back with
@@ -11,7 +16,7 @@
 // Structure (one persistent CTA per SM, 640 threads, warp-specialised):
 //   warps 0-15  epilogue: warp w owns TMEM lanes 32*(w%4).., column quarter w/4 (64 of the 256 columns)
 //   warp 16     TMA producer (one thread): latent tile A (128 frames x D, resident per M tile) and codebook tiles B
-//               (256 codes x 64 dims per stage) as 128B-swizzled K-major boxes, |e|^2 slices by bulk copy
+//               (256 codes x 64 dims per stage) as 128B-swizzled K-major boxes, bias-operand slices by bulk copy
 //   warp 17     MMA issuer (one thread): tcgen05.mma cta_group::1 kind::f16 M128 N256 K16, fp32 accumulate, two TMEM
 //               accumulator stages (2 x 256 columns) so the epilogue of tile j overlaps the MMAs of tile j+1
 //   warp 18     TMEM allocator
@@ -30,9 +35,11 @@ constexpr int BK = 64;             // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_CHUNK_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
-constexpr int E2_SLICE_BYTES = BN * 4;       // 1 KiB
+constexpr int EH_SLICE_BYTES = BN * 16;      // 4 KiB: (h1,h2,h3,0,0,0,0,0) bf16 per code = K-half 0 of the bias operand
+constexpr int EH_SLOTS = 2;
+constexpr int AX_BYTES = BM * 16;            // 2 KiB: K-half 0 of the constant A operand
+constexpr int ZERO_BYTES = EH_SLICE_BYTES;   // shared all-zero K-half 1 of both bias operands
 constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 4;
-constexpr int E2_SLOTS = 4;                  // |e|^2 slices ride their own ring so the producer never waits on the epilogue
 constexpr int EPI_WARP0 = 0, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;   // 4 warps per TMEM lane quarter: 64 columns each
 // The single-thread producer / MMA loops sit in the HIGHEST warp ids: the scheduler favours them over waiting epilogue warps.
 constexpr int PRODUCER_WARP = 16, MMA_WARP = 17, ALLOC_WARP = 18;
@@ -43,7 +50,7 @@ constexpr int kCandFill = 12;                // shortlist entries published per 
 struct Barriers {
     unsigned long long b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
     unsigned long long a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
-    unsigned long long e2_full[E2_SLOTS], e2_empty[E2_SLOTS], tmem_full[2], tmem_empty[2];
+    unsigned long long eh_full[EH_SLOTS], eh_empty[EH_SLOTS], tmem_full[2], tmem_empty[2];
     unsigned int tmem_base;
     unsigned int pad;
 };
@@ -156,6 +163,11 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major operand without swizzle, one K step (16 bf16) wide: 8x8 core matrices of 128 contiguous bytes; `sbo` bytes between
+// 8-row groups, `lbo` bytes from K-half 0 to K-half 1
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
 // c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -196,7 +208,7 @@ constexpr int EV_CAP = 32;
 constexpr int EV_WORDS = 12;   // 8 accumulators, chunk minimum, chunk id, 2 pad
 
 struct EventStack {
-    uint32_t* base;   // this thread's EV_CAP x EV_WORDS words
+    uint32_t* base;   // this thread's EV_CAP x EV_WORDS words; an entry = 8 accumulators, chunk maximum, chunk id
     int       n;      // chunks appended for the current frame tile (may exceed EV_CAP: overflow)
     __device__ __forceinline__ void push_if(bool p, float tmin, int chunk, const uint32_t* a) {
         const bool q = p && n < EV_CAP;
@@ -214,55 +226,46 @@ struct EventStack {
     }
 };
 
-// One 32-column slab of scores for this thread's frame.
-// Fast path per slab: 32 FFMA + 18 FMNMX3 + one compare.  When the slab minimum is within the band of the running
-// minimum, the four chunks are appended under predicates (straight-line code) and the threshold tightens.
-__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int chunk0, float band,
-                                          float& thr, EventStack& ev) {
+// One 32-column slab of accumulators (= -score/2) for this thread's frame: a pure running arg-max.
+// Fast path per slab: 16 FMNMX3 + one compare.  When the slab maximum is within the band of the running maximum, the
+// four 8-code chunks are appended under predicates (straight-line code) and the threshold tightens.
+__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, float hband, float& thr, EventStack& ev) {
     float t[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        const float4 ea = *reinterpret_cast<const float4*>(e2s + g * 8);
-        const float4 eb = *reinterpret_cast<const float4*>(e2s + g * 8 + 4);
-        const float s0 = fmaf(-2.f, __uint_as_float(r[g * 8 + 0]), ea.x);
-        const float s1 = fmaf(-2.f, __uint_as_float(r[g * 8 + 1]), ea.y);
-        const float s2 = fmaf(-2.f, __uint_as_float(r[g * 8 + 2]), ea.z);
-        const float s3 = fmaf(-2.f, __uint_as_float(r[g * 8 + 3]), ea.w);
-        const float s4 = fmaf(-2.f, __uint_as_float(r[g * 8 + 4]), eb.x);
-        const float s5 = fmaf(-2.f, __uint_as_float(r[g * 8 + 5]), eb.y);
-        const float s6 = fmaf(-2.f, __uint_as_float(r[g * 8 + 6]), eb.z);
-        const float s7 = fmaf(-2.f, __uint_as_float(r[g * 8 + 7]), eb.w);
-        float m = fminf(fminf(s0, s1), s2);
-        m = fminf(fminf(m, s3), s4);
-        m = fminf(fminf(m, s5), s6);
-        t[g] = fminf(m, s7);
+        float m = fmaxf(fmaxf(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1])), __uint_as_float(r[g * 8 + 2]));
+        m = fmaxf(fmaxf(m, __uint_as_float(r[g * 8 + 3])), __uint_as_float(r[g * 8 + 4]));
+        m = fmaxf(fmaxf(m, __uint_as_float(r[g * 8 + 5])), __uint_as_float(r[g * 8 + 6]));
+        t[g] = fmaxf(m, __uint_as_float(r[g * 8 + 7]));
     }
-    const float slab_min = fminf(fminf(fminf(t[0], t[1]), t[2]), t[3]);
-    if (slab_min < thr) {
+    const float slab_max = fmaxf(fmaxf(fmaxf(t[0], t[1]), t[2]), t[3]);
+    if (slab_max > thr) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) ev.push_if(t[g] < thr, t[g], chunk0 + g, &r[g * 8]);
-        thr = fminf(thr, slab_min + band);
+        for (int g = 0; g < 4; ++g) ev.push_if(t[g] > thr, t[g], chunk0 + g, &r[g * 8]);
+        thr = fmaxf(thr, slab_max - hband);
     }
 }
 
-__device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], const float* __restrict__ e2s, int code0, int K, float* row_out) {
+__device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], int code0, int K, float* row_out) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-        if (code0 + j < K) row_out[code0 + j] = fmaf(-2.f, __uint_as_float(r[j]), e2s[j]);
+        if (code0 + j < K) row_out[code0 + j] = -2.f * __uint_as_float(r[j]);
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
-                 const float* __restrict__ e2, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
+                 const __nv_bfloat16* __restrict__ eh, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta, float* __restrict__ scores_dbg,
                  uint32_t* __restrict__ ev_scratch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
     unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB
-    float* sE2 = reinterpret_cast<float*>(sB + (size_t)b_stages * B_STAGE_BYTES);   // E2_SLOTS x 256 floats
-    float* sMin = sE2 + E2_SLOTS * BN;                                   // [4][128] running minima of the four column quarters
+    unsigned char* sEH = sB + (size_t)b_stages * B_STAGE_BYTES;          // EH_SLOTS x 4 KiB bias operand B (K-half 0)
+    unsigned char* sAX = sEH + EH_SLOTS * EH_SLICE_BYTES;                // 2 KiB constant bias operand A (K-half 0)
+    unsigned char* sZero = sAX + AX_BYTES;                               // 4 KiB of zeros: K-half 1 of both bias operands
+    float* sMin = reinterpret_cast<float*>(sZero + ZERO_BYTES);          // [4][128] running maxima of the four column quarters
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags
     Barriers* bars = reinterpret_cast<Barriers*>(sCnt + 2 * BM);
 
@@ -284,9 +287,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == MMA_WARP && lane == 0) {
         for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), cs); }
         for (int i = 0; i < a_slots; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
-        for (int i = 0; i < E2_SLOTS; ++i) {
-            mbar_init(smem_u32(&bars->e2_full[i]), 1);
-            mbar_init(smem_u32(&bars->e2_empty[i]), EPI_THREADS / 32);
+        for (int i = 0; i < EH_SLOTS; ++i) {
+            mbar_init(smem_u32(&bars->eh_full[i]), 1);
+            mbar_init(smem_u32(&bars->eh_empty[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->tmem_full[i]), 1);
@@ -295,6 +298,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         fence_barrier_init();
     }
     if (warp == ALLOC_WARP) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    {   // constant bias operand A: every frame row is (-1, -1, -1, 0, 0, 0, 0, 0) in K-half 0; K-half 1 is the zero block
+        uint4* ax = reinterpret_cast<uint4*>(sAX);
+        for (int i = threadIdx.x; i < AX_BYTES / 16; i += NUM_THREADS) ax[i] = make_uint4(0xBF80BF80u, 0x0000BF80u, 0u, 0u);
+        uint4* zz = reinterpret_cast<uint4*>(sZero);
+        for (int i = threadIdx.x; i < ZERO_BYTES / 16; i += NUM_THREADS) zz[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+    }
     tc_fence_before();
     __syncthreads();
     if (cs > 1) cluster_sync_all();   // peers must see initialised barriers before the first multicast / remote arrive
@@ -306,21 +316,21 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, es = 0, e_ph = 0;
         const uint32_t slice = (uint32_t)B_STAGE_BYTES / (uint32_t)cs;
         const int b_row_off = (int)crank * (BN / cs);
-        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB) + crank * slice, sE_u = smem_u32(sE2);
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB) + crank * slice, sE_u = smem_u32(sEH);
         const uint32_t bar_afull = smem_u32(&bars->a_full[0]), bar_aempty = smem_u32(&bars->a_empty[0]);
         const uint32_t bar_bfull = smem_u32(&bars->b_full[0]), bar_bempty = smem_u32(&bars->b_empty[0]);
-        const uint32_t bar_efull = smem_u32(&bars->e2_full[0]), bar_eempty = smem_u32(&bars->e2_empty[0]);
+        const uint32_t bar_efull = smem_u32(&bars->eh_full[0]), bar_eempty = smem_u32(&bars->eh_empty[0]);
         for (int rd = 0; rd < rounds; ++rd) {
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             const int a_row = (mt < num_m_tiles ? mt : 0) * BM;               // dummy tiles re-read tile 0, nothing is published
             for (int nt = 0; nt < num_n_tiles; ++nt) {
                 mbar_wait(bar_eempty + es * 8, e_ph ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(bar_efull + es * 8, E2_SLICE_BYTES);
-                    bulk_load_1d(sE_u + es * E2_SLICE_BYTES, e2 + (size_t)nt * BN, E2_SLICE_BYTES, bar_efull + es * 8);
+                    mbar_expect_tx(bar_efull + es * 8, EH_SLICE_BYTES);
+                    bulk_load_1d(sE_u + es * EH_SLICE_BYTES, eh + (size_t)nt * BN * 8, EH_SLICE_BYTES, bar_efull + es * 8);
                 }
                 __syncwarp();
-                if (++es == E2_SLOTS) { es = 0; e_ph ^= 1; }
+                if (++es == EH_SLOTS) { es = 0; e_ph ^= 1; }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const uint32_t slot = a_slot0 + kb;
                     if (nt == 0) mbar_wait(bar_aempty + slot * 8, a_ph ^ 1);
@@ -345,8 +355,12 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     } else if (warp == MMA_WARP) {
         // ================================================================ MMA issuer (converged warp, one elected lane issues)
-        uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, as = 0, t_ph = 0;
+        uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, as = 0, t_ph = 0, es = 0, e_ph = 0;
         const uint64_t dA0 = make_desc_sw128(smem_u32(sA)), dB0 = make_desc_sw128(smem_u32(sB));
+        // bias operands: 8-row groups 128 B apart, K-half 1 = the shared zero block
+        const uint64_t dAX = make_desc_noswz(smem_u32(sAX), smem_u32(sZero) - smem_u32(sAX), 128);
+        const uint32_t sEH_u = smem_u32(sEH), sZero_u = smem_u32(sZero);
+        const uint32_t bar_efull = smem_u32(&bars->eh_full[0]), bar_eempty = smem_u32(&bars->eh_empty[0]);
         const uint32_t bar_afull = smem_u32(&bars->a_full[0]), bar_aempty = smem_u32(&bars->a_empty[0]);
         const uint32_t bar_bfull = smem_u32(&bars->b_full[0]), bar_bempty = smem_u32(&bars->b_empty[0]);
         const uint32_t bar_tfull = smem_u32(&bars->tmem_full[0]), bar_tempty = smem_u32(&bars->tmem_empty[0]);
@@ -372,11 +386,21 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         if (cs == 1) umma_commit(bar_bempty + b_st * 8);
                         else umma_commit_mc(bar_bempty + b_st * 8, cmask);
                         if (last_nt) umma_commit(bar_aempty + slot * 8);
-                        if (kb == num_kb - 1) umma_commit(bar_tfull + as * 8);
                     }
                     __syncwarp();
                     if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
                 }
+                // the bias K step: acc -= |e_k|^2 / 2, then hand the accumulator to the epilogue
+                mbar_wait(bar_efull + es * 8, e_ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t eh_u = sEH_u + es * EH_SLICE_BYTES;
+                    umma_bf16(tmem_d, dAX, make_desc_noswz(eh_u, sZero_u - eh_u, 128), kIdesc, 1u);
+                    umma_commit(bar_eempty + es * 8);
+                    umma_commit(bar_tfull + as * 8);
+                }
+                __syncwarp();
+                if (++es == EH_SLOTS) { es = 0; e_ph ^= 1; }
                 as ^= 1;
                 if (as == 0) t_ph ^= 1;
             }
@@ -401,15 +425,14 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             const int64_t row = (int64_t)mt * BM + row_in_tile;
             const float band = (row < N) ? band_g[row] : 0.f;
-            float thr = INFINITY;
+            const float hband = 0.5f * band;              // the band in accumulator units (acc = -score / 2)
+            float thr = -INFINITY;
             ev.n = 0;
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
-                const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1, es = n_it % E2_SLOTS;
-                mbar_wait(smem_u32(&bars->e2_full[es]), (n_it / E2_SLOTS) & 1);
+                const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1;
                 mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + t_lane + as * BN + colq * COLS_PER_WARP;
-                const float* e2s = sE2 + es * BN + colq * COLS_PER_WARP;
                 const int code0 = nt * BN + colq * COLS_PER_WARP;
                 uint32_t ra[32];
 #pragma unroll
@@ -417,48 +440,41 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tmem_ld32(taddr + sb * 32, ra);
                     tmem_ld_wait(ra);
                     if (scores_dbg) {
-                        if (row < N) dump_slab(ra, e2s + sb * 32, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
+                        if (row < N) dump_slab(ra, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
                     } else {
-                        scan_slab(ra, e2s + sb * 32, (code0 + sb * 32) >> 3, band, thr, ev);
+                        scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(smem_u32(&bars->tmem_empty[as]));
-                    mbar_arrive(smem_u32(&bars->e2_empty[es]));
-                }
+                if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[as]));
             }
-            // ---- resolve this thread's chunks against the frame's final minimum and publish the shortlist
-            sMin[colq * BM + row_in_tile] = thr - band;                      // running minimum of this column quarter
+            // ---- resolve this thread's chunks against the frame's final maximum and publish the shortlist
+            sMin[colq * BM + row_in_tile] = thr + hband;                     // running maximum of this column quarter
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (row < N && !scores_dbg) {
-                const float gmin = fminf(fminf(sMin[row_in_tile], sMin[BM + row_in_tile]),
-                                         fminf(sMin[2 * BM + row_in_tile], sMin[3 * BM + row_in_tile]));
-                const float cutoff = gmin + band;
+                const float gmax = fmaxf(fmaxf(sMin[row_in_tile], sMin[BM + row_in_tile]),
+                                         fmaxf(sMin[2 * BM + row_in_tile], sMin[3 * BM + row_in_tile]));
+                const float cutoff = gmax - hband;
                 uint16_t* dst = cand_idx + (size_t)row * kCandMax;
                 const int n_ev = ev.n < EV_CAP ? ev.n : EV_CAP;
                 bool lost = ev.n > EV_CAP || !(band < INFINITY);
                 for (int e0 = 0; e0 < n_ev; e0 += 8) {
-                    uint2 hd[8];     // headers (chunk minimum, chunk id) of 8 events fetched together: one L2 latency, not eight
+                    uint2 hd[8];     // headers (chunk maximum, chunk id) of 8 events fetched together: one L2 latency, not eight
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         hd[u] = (e0 + u < n_ev) ? *reinterpret_cast<const uint2*>(ev.base + (e0 + u) * EV_WORDS + 8)
-                                                : make_uint2(0x7f800000u, 0u);
+                                                : make_uint2(0xff800000u, 0u);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        if (__uint_as_float(hd[u].x) <= cutoff) {
+                        if (__uint_as_float(hd[u].x) >= cutoff) {
                             const uint32_t* en = ev.base + (e0 + u) * EV_WORDS;
                             const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 4);
                             const int k0 = (int)hd[u].y * 8;
-                            const float4 e0v = *reinterpret_cast<const float4*>(e2 + k0), e1v = *reinterpret_cast<const float4*>(e2 + k0 + 4);
-                            const float sc[8] = {fmaf(-2.f, __uint_as_float(a0.x), e0v.x), fmaf(-2.f, __uint_as_float(a0.y), e0v.y),
-                                                 fmaf(-2.f, __uint_as_float(a0.z), e0v.z), fmaf(-2.f, __uint_as_float(a0.w), e0v.w),
-                                                 fmaf(-2.f, __uint_as_float(a1.x), e1v.x), fmaf(-2.f, __uint_as_float(a1.y), e1v.y),
-                                                 fmaf(-2.f, __uint_as_float(a1.z), e1v.z), fmaf(-2.f, __uint_as_float(a1.w), e1v.w)};
+                            const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                if (sc[j] <= cutoff) {
+                                if (__uint_as_float(av[j]) >= cutoff) {
                                     const int pos = atomicAdd(&sCnt[row_in_tile], 1);
                                     if (pos < kCandFill) dst[pos] = (uint16_t)(k0 + j);
                                     else lost = true;
@@ -552,7 +568,7 @@ static void timing_end(TimingSlot* t, cudaStream_t s) {
     if (t) cudaEventRecord(t->stop, s);
 }
 
-int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const float* e2, const float* band, int64_t N, int64_t N_pad,
+int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh, const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
                      float* scores_dbg, void* ev_scratch, cudaStream_t s) {
     using namespace tc;
@@ -561,7 +577,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     if ((rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM)) != 0) return rc;
     const int num_kb = (D + BK - 1) / BK;
     const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + E2_SLOTS * E2_SLICE_BYTES + 4 * BM * 4 + 2 * BM * 4 + sizeof(Barriers) + 1024;
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 2 * BM * 4 + sizeof(Barriers) + 1024;
     int b_stages = (int)((227 * 1024 - fixed) / B_STAGE_BYTES);
     if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
     if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
@@ -599,7 +615,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const flo
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     TimingSlot* slot = timing_begin(s);
-    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_search_kernel, mx, me_c, e2, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs,
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_search_kernel, mx, me_c, eh, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs,
                                         K, cand_cnt, cand_idx, fallback_rows, meta, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
     if (le != cudaSuccess) return cuda_fail(le, "tc_search_kernel launch");
     cudaError_t e = cudaGetLastError();
