@@ -40,12 +40,13 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags) {
     L.sse_partials = take((size_t)L.n_partials * 8);
     if (prec == VQB_PREC_FP32) {
         L.idx32 = take((size_t)N * 4);
-        L.cand_cnt = L.cand_idx = L.fallback_rows = L.x2 = L.eb = L.eh = L.xb = L.ev = 0;
+        L.cand_cnt = L.cand_idx = L.fallback_rows = L.best64 = L.x2 = L.eb = L.eh = L.xb = L.ev = 0;
     } else {
         L.idx32 = 0;
         L.cand_cnt = take((size_t)L.n_pad);
         L.cand_idx = take((size_t)L.n_pad * kCandMax * 2);
         L.fallback_rows = take((size_t)L.n_pad * 4);
+        L.best64 = take((size_t)L.n_pad * 8);
         L.x2 = take((size_t)L.n_pad * 4);
         L.eb = take((size_t)L.k_pad * D * 2);
         L.eh = take((size_t)L.k_pad * 16);
@@ -139,23 +140,24 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
     if (prec == VQB_PREC_FP32) {
         int* idx32 = reinterpret_cast<int*>(ws + L.idx32);
         VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, nullptr, nullptr, meta, s), "codebook_prep");
-        VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, nullptr, nullptr, idx32, nullptr, nullptr, s), "exact_search");
+        VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, nullptr, nullptr, idx32, nullptr, nullptr, nullptr, s), "exact_search");
         VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, idx32, nullptr, nullptr, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
                              counts, resid, part, L.n_partials, meta, s), "tail");
     } else {
         uint8_t* cand_cnt = reinterpret_cast<uint8_t*>(ws + L.cand_cnt);
         uint16_t* cand_idx = reinterpret_cast<uint16_t*>(ws + L.cand_idx);
         int* fb_rows = reinterpret_cast<int*>(ws + L.fallback_rows);
+        unsigned long long* best64 = reinterpret_cast<unsigned long long*>(ws + L.best64);
         float* x2 = reinterpret_cast<float*>(ws + L.x2);
         __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(ws + L.eb);
         __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + L.xb);
         __nv_bfloat16* eh = reinterpret_cast<__nv_bfloat16*>(ws + L.eh);
         VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, eb, eh, meta, s), "codebook_prep");
         VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");
-        rc = launch_tc_search(xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, scores_dbg, ws + L.ev, s);
+        rc = launch_tc_search(xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, best64, scores_dbg, ws + L.ev, s);
         if (rc != 0) return rc;
         if (scores_dbg) return 0;
-        VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, fb_rows, &meta->fallback_count, nullptr, cand_cnt, cand_idx, s),
+        VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, fb_rows, &meta->fallback_count, nullptr, cand_cnt, cand_idx, best64, s),
                  "exact_search(fallback)");
         VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, nullptr, cand_cnt, cand_idx, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
                              counts, resid, part, L.n_partials, meta, s), "tail");

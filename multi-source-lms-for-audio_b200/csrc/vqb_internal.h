@@ -28,7 +28,7 @@ struct WsMeta {
 };
 
 struct WsLayout {
-    size_t meta, e2, counts, sse_partials, idx32, cand_cnt, cand_idx, fallback_rows, x2, eb, eh, xb, ev, total;
+    size_t meta, e2, counts, sse_partials, idx32, cand_cnt, cand_idx, fallback_rows, best64, x2, eb, eh, xb, ev, total;
     int    k_pad;
     int64_t n_pad;
     int    n_partials;
@@ -51,7 +51,7 @@ cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int
 // rows == nullptr: all N frames -> idx32[n]; else the frames listed in rows[0..*row_count) -> cand_cnt/cand_idx (count 1)
 cudaError_t launch_exact_search(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                                 const int* rows, const int* row_count, int* idx32, uint8_t* cand_cnt, uint16_t* cand_idx,
-                                cudaStream_t s);
+                                unsigned long long* best64, cudaStream_t s);
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                         int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, cudaStream_t s);
@@ -70,6 +70,6 @@ cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int6
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.
 int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh, const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
-                     float* scores_dbg, void* ev_scratch, cudaStream_t s);
+                     unsigned long long* best64, float* scores_dbg, void* ev_scratch, cudaStream_t s);
 
 }  // namespace vqb

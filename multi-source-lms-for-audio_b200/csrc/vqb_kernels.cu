@@ -168,11 +168,19 @@ cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int
 // Block = 64 frames (resident in shared memory) x all K codes in tiles of 64, 4x4 register micro-tiles.
 constexpr int XT_M = 64, XT_N = 64, XT_K = 16, XT_LD = XT_N + 4;
 
+// torch.argmin order as one integer: NaN smallest, then by distance, then by index (atomicMin on it = the argmin)
+__device__ __forceinline__ unsigned long long argmin_key(float d, int i) {
+    const uint32_t b = __float_as_uint(d);
+    const uint32_t hi = isnan(d) ? 0u : (b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u));
+    return ((unsigned long long)hi << 32) | (uint32_t)i;
+}
+
+// Fallback mode (rows != nullptr) splits the codebook over gridDim.y: a handful of frames must not be searched by a
+// handful of blocks.  Slices meet in best64[list position] through atomicMin; fallback_commit_kernel publishes the codes.
 __global__ void __launch_bounds__(256) exact_search_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                            const float* __restrict__ e2, int D, int64_t W, int64_t N, int K,
                                                            const int* __restrict__ rows, const int* __restrict__ row_count,
-                                                           int* __restrict__ idx32, uint8_t* __restrict__ cand_cnt,
-                                                           uint16_t* __restrict__ cand_idx) {
+                                                           int* __restrict__ idx32, unsigned long long* __restrict__ best64) {
     extern __shared__ __align__(16) float smem_f[];
     float* Xs = smem_f;                                   // [D][64]   x tile, d-major
     float* Es = Xs + (size_t)D * XT_M;                    // [16][68]  codebook chunk, d-major
@@ -180,6 +188,14 @@ __global__ void __launch_bounds__(256) exact_search_kernel(const float* __restri
     int* rown = reinterpret_cast<int*>(x2s + XT_M);       // [64] frame id or -1
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t total = rows ? (int64_t)*row_count : N;
+    // many fallback frames (e.g. a NaN codebook sends all of them): re-reading every frame tile once per slice would
+    // cost more than it saves, so slice 0 takes the whole codebook and the others retire
+    const bool split = gridDim.y > 1 && total <= (int64_t)XT_M * gridDim.x * 4;
+    if (!split && blockIdx.y > 0) return;
+    const int tiles_k = (K + XT_N - 1) / XT_N;
+    const int per_slice = split ? (tiles_k + (int)gridDim.y - 1) / (int)gridDim.y : tiles_k;
+    const int k_lo = split ? (int)blockIdx.y * per_slice * XT_N : 0;
+    const int k_hi = min(K, k_lo + per_slice * XT_N);
 
     for (int64_t tile = blockIdx.x; tile * XT_M < total; tile += gridDim.x) {
         __syncthreads();
@@ -207,7 +223,7 @@ __global__ void __launch_bounds__(256) exact_search_kernel(const float* __restri
 #pragma unroll
         for (int i = 0; i < 4; ++i) { bd[i] = 0.f; bi[i] = -1; }
 
-        for (int k0 = 0; k0 < K; k0 += XT_N) {
+        for (int k0 = k_lo; k0 < k_hi; k0 += XT_N) {
             float acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(256) exact_search_kernel(const float* __restri
             if (tx == 0) {
                 const int n = rown[ty * 4 + i];
                 if (n >= 0) {
-                    if (rows) { cand_cnt[n] = kCandFinal; cand_idx[(size_t)n * kCandMax] = (uint16_t)bi[i]; }
+                    if (rows) { if (bi[i] >= 0) atomicMin(best64 + tile * XT_M + ty * 4 + i, argmin_key(bd[i], bi[i])); }
                     else idx32[n] = bi[i];
                 }
             }
@@ -267,9 +283,20 @@ __global__ void __launch_bounds__(256) exact_search_kernel(const float* __restri
     }
 }
 
+__global__ void __launch_bounds__(256) fallback_commit_kernel(const int* __restrict__ rows, const int* __restrict__ row_count,
+                                                              const unsigned long long* __restrict__ best64,
+                                                              uint8_t* __restrict__ cand_cnt, uint16_t* __restrict__ cand_idx) {
+    const int total = *row_count;
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < total; r += gridDim.x * 256) {
+        const int n = rows[r];
+        cand_cnt[n] = kCandFinal;
+        cand_idx[(size_t)n * kCandMax] = (uint16_t)(best64[r] & 0xFFFFu);
+    }
+}
+
 cudaError_t launch_exact_search(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                                 const int* rows, const int* row_count, int* idx32, uint8_t* cand_cnt, uint16_t* cand_idx,
-                                cudaStream_t s) {
+                                unsigned long long* best64, cudaStream_t s) {
     const int64_t N = (int64_t)B * W;
     const size_t smem = ((size_t)D * XT_M + XT_K * XT_LD + XT_M) * 4 + XT_M * 4;
     static bool attr_done = false;
@@ -283,9 +310,18 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
     int64_t grid = 148LL * (per_sm > 4 ? 4 : per_sm);
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
-    exact_search_kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, rows, row_count, idx32, cand_cnt,
-                                                          cand_idx);
-    note_launch();
+    if (!rows) {
+        exact_search_kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, nullptr, nullptr, idx32, nullptr);
+        note_launch();
+        return cudaGetLastError();
+    }
+    int ksplit = (K + XT_N - 1) / XT_N;
+    if (ksplit > 32) ksplit = 32;
+    if (grid > 148) grid = 148;
+    exact_search_kernel<<<dim3((unsigned)grid, (unsigned)ksplit), 256, smem, s>>>(z, codebook, e2, D, W, N, K, rows, row_count, nullptr,
+                                                                                 best64);
+    fallback_commit_kernel<<<148, 256, 0, s>>>(rows, row_count, best64, cand_cnt, cand_idx);
+    note_launch(2);
     return cudaGetLastError();
 }
 

@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
                  const __nv_bfloat16* __restrict__ eh, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
-                 uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta, float* __restrict__ scores_dbg,
-                 uint32_t* __restrict__ ev_scratch) {
+                 uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
+                 unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
     unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB
@@ -491,7 +491,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const int cnt = sCnt[row_in_tile];
                     if (force_fallback || cnt == 0 || sCnt[BM + row_in_tile]) {
                         cand_cnt[row] = kCandFinal;   // the exact search fills in the final code
-                        fallback_rows[atomicAdd(&meta->fallback_count, 1)] = (int)row;
+                        const int fp = atomicAdd(&meta->fallback_count, 1);
+                        fallback_rows[fp] = (int)row;
+                        best64[fp] = ~0ull;                      // the sliced exact search meets here through atomicMin
                         atomicAdd(&meta->fallback_total, 1ull);
                     } else {
                         cand_cnt[row] = (uint8_t)(cnt < kCandFill ? cnt : kCandFill);
@@ -570,7 +572,7 @@ static void timing_end(TimingSlot* t, cudaStream_t s) {
 
 int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh, const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
-                     float* scores_dbg, void* ev_scratch, cudaStream_t s) {
+                     unsigned long long* best64, float* scores_dbg, void* ev_scratch, cudaStream_t s) {
     using namespace tc;
     CUtensorMap mx;
     int rc;
@@ -616,7 +618,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __n
     cfg.numAttrs = 1;
     TimingSlot* slot = timing_begin(s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, tc_search_kernel, mx, me_c, eh, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs,
-                                        K, cand_cnt, cand_idx, fallback_rows, meta, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
+                                        K, cand_cnt, cand_idx, fallback_rows, meta, best64, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
     if (le != cudaSuccess) return cuda_fail(le, "tc_search_kernel launch");
     cudaError_t e = cudaGetLastError();
     timing_end(slot, s);
