@@ -377,13 +377,13 @@ __device__ __forceinline__ void tile_store(const float* Xs, int ld, float* __res
 }
 
 template <int LPF, int J, bool kResid>
-__global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
-                                                   const float* __restrict__ e2, int D, int64_t W, int64_t N, int K,
-                                                   const int* __restrict__ idx32, const uint8_t* __restrict__ cand_cnt,
-                                                   const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
-                                                   float* __restrict__ q_out, int* __restrict__ counts,
-                                                   float* __restrict__ resid, double* __restrict__ sse_partials,
-                                                   WsMeta* meta) {
+__global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                      const float* __restrict__ e2, int D, int64_t W, int64_t N, int K,
+                                                      const int* __restrict__ idx32, const uint8_t* __restrict__ cand_cnt,
+                                                      const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
+                                                      float* __restrict__ q_out, int* __restrict__ counts,
+                                                      float* __restrict__ resid, double* __restrict__ sse_partials,
+                                                      WsMeta* meta) {
     extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
     __shared__ double red[8];
     constexpr int FPW = 32 / LPF;                 // frames a warp works on at once
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ 
         __syncthreads();
         tile_load(Xs, ld, z, col, W, D, valid);
         __syncthreads();
-#pragma unroll 1
+#pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int f = warp * (TL_F / 8) + it * FPW + sub;
             const int64_t n = tile * TL_F + f;
@@ -428,12 +428,8 @@ __global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ 
                 const int d = 4 * sl + 4 * LPF * j;
                 xv[j] = (d < D) ? *reinterpret_cast<const float4*>(Xs + f * ld + d) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            int cnt = cnt_r[0], k = k0_r[0];          // register-resident select instead of dynamic indexing
-#pragma unroll
-            for (int u = 1; u < ITER; ++u) {
-                cnt = (it == u) ? cnt_r[u] : cnt;
-                k = (it == u) ? k0_r[u] : k;
-            }
+            const int cnt = cnt_r[it];
+            int k = k0_r[it];
             const bool need = live && cnt != kCandFinal && cnt > 1;
             if (__any_sync(0xffffffffu, need)) {
                 // fp32 rescoring of the shortlisted codes in the reference's op order (whole warp takes part in shuffles)
@@ -456,17 +452,19 @@ __global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ 
                     const bool act = need && ci < cnt;
                     const int kc = act ? (int)cl[ci] : 0;
                     const float* er = E + (size_t)kc * D;
-                    float dot = 0.f;
+                    float4 ev[J];
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
                         const int d = 4 * sl + 4 * LPF * j;
-                        if (d < D) {
-                            const float4 ev = *reinterpret_cast<const float4*>(er + d);
-                            dot = fmaf(xv[j].x, ev.x, dot);
-                            dot = fmaf(xv[j].y, ev.y, dot);
-                            dot = fmaf(xv[j].z, ev.z, dot);
-                            dot = fmaf(xv[j].w, ev.w, dot);
-                        }
+                        ev[j] = (d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    float dot = 0.f;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        dot = fmaf(xv[j].x, ev[j].x, dot);
+                        dot = fmaf(xv[j].y, ev[j].y, dot);
+                        dot = fmaf(xv[j].z, ev[j].z, dot);
+                        dot = fmaf(xv[j].w, ev[j].w, dot);
                     }
                     dot = group_sum<LPF>(dot);
                     if (act) {
@@ -482,15 +480,20 @@ __global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ 
             if (live && !need && sl == 0) n_short += 1;
             if (live) {
                 const float* er = E + (size_t)k * D;
+                float4 qv[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int d = 4 * sl + 4 * LPF * j;
+                    qv[j] = (d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 float fs = 0.f;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const int d = 4 * sl + 4 * LPF * j;
                     if (d < D) {
-                        const float4 q = *reinterpret_cast<const float4*>(er + d);
                         float4 df, st;
-                        df.x = __fsub_rn(q.x, xv[j].x); df.y = __fsub_rn(q.y, xv[j].y);
-                        df.z = __fsub_rn(q.z, xv[j].z); df.w = __fsub_rn(q.w, xv[j].w);
+                        df.x = __fsub_rn(qv[j].x, xv[j].x); df.y = __fsub_rn(qv[j].y, xv[j].y);
+                        df.z = __fsub_rn(qv[j].z, xv[j].z); df.w = __fsub_rn(qv[j].w, xv[j].w);
                         fs = fmaf(df.x, df.x, fs); fs = fmaf(df.y, df.y, fs); fs = fmaf(df.z, df.z, fs); fs = fmaf(df.w, df.w, fs);
                         st.x = __fadd_rn(xv[j].x, df.x); st.y = __fadd_rn(xv[j].y, df.y);      // straight-through VALUE (:48)
                         st.z = __fadd_rn(xv[j].z, df.z); st.w = __fadd_rn(xv[j].w, df.w);
@@ -534,6 +537,19 @@ __global__ void __launch_bounds__(256, 3) tail_kernel(const float* __restrict__ 
     }
 }
 
+// lanes per frame and float4 groups per lane for a given D: 8 lanes x (D/32) groups up to D = 256, 16 lanes beyond
+#define VQB_DISPATCH_D(D, CALL)                    \
+    do {                                           \
+        if ((D) <= 32) { CALL(8, 1); }             \
+        else if ((D) <= 64) { CALL(8, 2); }        \
+        else if ((D) <= 96) { CALL(8, 3); }        \
+        else if ((D) <= 128) { CALL(8, 4); }       \
+        else if ((D) <= 192) { CALL(8, 6); }       \
+        else if ((D) <= 256) { CALL(8, 8); }       \
+        else if ((D) <= 384) { CALL(16, 6); }      \
+        else { CALL(16, 8); }                      \
+    } while (0)
+
 template <int LPF, int J>
 static cudaError_t launch_tail_t(const float* z, const float* codebook, const float* e2, int D, int64_t W, int64_t N, int K,
                                  const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
@@ -564,12 +580,7 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
     double* part = reinterpret_cast<double*>(sse_partials);
     const int g = (int)grid;
 #define VQB_TAIL(LPF, J) e = launch_tail_t<LPF, J>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, g, meta, s)
-    if (D <= 32) VQB_TAIL(8, 1);
-    else if (D <= 64) VQB_TAIL(16, 1);
-    else if (D <= 128) VQB_TAIL(32, 1);
-    else if (D <= 256) VQB_TAIL(32, 2);
-    else if (D <= 384) VQB_TAIL(32, 3);
-    else VQB_TAIL(32, 4);
+    VQB_DISPATCH_D(D, VQB_TAIL);
 #undef VQB_TAIL
     note_launch();
     return e;
@@ -639,14 +650,19 @@ cudaError_t launch_finalize(const float* stats, int K, int D, float beta, float*
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int TL_LD = TL_F + 1;       // [D][33] dim-major tile of the simpler kernels below (scalar, conflict-free)
-// dX[b,:,w] = Gq[b,:,w] + g_c * beta * 2 (x - q) / (N D); transposing tile, warp per frame.
-__global__ void __launch_bounds__(256) backward_dx_kernel(const float* __restrict__ z, const float* __restrict__ E,
-                                                          const int64_t* __restrict__ idx, const float* __restrict__ Gq,
-                                                          const float* __restrict__ g_c, float beta, int D, int64_t W,
-                                                          int64_t N, float* __restrict__ dX) {
-    extern __shared__ __align__(16) float Xs[];   // [D][33]
+// dX[b,:,w] = Gq[b,:,w] + g_c * beta * 2 (x - q) / (N D); same float4 frame-major tile as the tail kernel: the commitment
+// term is formed per frame (8 or 16 lanes each) in shared memory, the upstream gradient is added on the way out.
+template <int LPF, int J>
+__global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                             const int64_t* __restrict__ idx, const float* __restrict__ Gq,
+                                                             const float* __restrict__ g_c, float beta, int D, int64_t W,
+                                                             int64_t N, float* __restrict__ dX) {
+    extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
+    constexpr int FPW = 32 / LPF;
+    constexpr int ITER = (TL_F / 8) / FPW;
+    const int ld = D + 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPF, sl = lane % LPF;
     const float gc = g_c ? *g_c : 0.f;
     const float coef = gc * beta * (2.0f / ((float)N * (float)D));
     for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x) {
@@ -655,22 +671,46 @@ __global__ void __launch_bounds__(256) backward_dx_kernel(const float* __restric
         int64_t b = 0, w = 0;
         if (valid) { b = nl / W; w = nl - b * W; }
         const size_t col = (size_t)b * D * W + w;
-        __syncthreads();
-        for (int d = warp; d < D; d += 8) Xs[d * TL_LD + lane] = valid ? ld_stream(z + col + (size_t)d * W) : 0.f;
-        __syncthreads();
-        for (int fi = 0; fi < TL_F / 8; ++fi) {
-            const int f = warp * (TL_F / 8) + fi;
-            const int64_t n = tile * TL_F + f;
-            if (n >= N) break;
-            const float* er = E + (size_t)idx[n] * D;
-            for (int d = lane; d < D; d += 32) Xs[d * TL_LD + f] = coef * __fsub_rn(Xs[d * TL_LD + f], er[d]);
+        int64_t k_r[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int64_t n = tile * TL_F + warp * (TL_F / 8) + it * FPW + sub;
+            k_r[it] = (n < N) ? idx[n] : 0;
         }
         __syncthreads();
-        if (valid)
-            for (int d = warp; d < D; d += 8) {
-                const size_t a = col + (size_t)d * W;
-                st_stream(dX + a, (Gq ? ld_stream(Gq + a) : 0.f) + Xs[d * TL_LD + lane]);
+        tile_load(Xs, ld, z, col, W, D, valid);
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int f = warp * (TL_F / 8) + it * FPW + sub;
+            const float* er = E + (size_t)k_r[it] * D;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int d = 4 * sl + 4 * LPF * j;
+                if (d < D) {
+                    const float4 x = *reinterpret_cast<const float4*>(Xs + f * ld + d);
+                    const float4 q = *reinterpret_cast<const float4*>(er + d);
+                    float4 o;
+                    o.x = coef * __fsub_rn(x.x, q.x); o.y = coef * __fsub_rn(x.y, q.y);
+                    o.z = coef * __fsub_rn(x.z, q.z); o.w = coef * __fsub_rn(x.w, q.w);
+                    *reinterpret_cast<float4*>(Xs + f * ld + d) = o;
+                }
             }
+        }
+        __syncthreads();
+        if (valid) {
+            const int f = threadIdx.x & 31;
+            for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
+                const float4 v = *reinterpret_cast<const float4*>(Xs + f * ld + d0);
+                const size_t a = col + (size_t)d0 * W;
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+                if (Gq) { g0 = ld_stream(Gq + a); g1 = ld_stream(Gq + a + W); g2 = ld_stream(Gq + a + 2 * W); g3 = ld_stream(Gq + a + 3 * W); }
+                st_stream(dX + a, g0 + v.x);
+                st_stream(dX + a + W, g1 + v.y);
+                st_stream(dX + a + 2 * W, g2 + v.z);
+                st_stream(dX + a + 3 * W, g3 + v.w);
+            }
+        }
     }
 }
 
@@ -678,17 +718,19 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
                                float beta, int B, int D, int64_t W, int K, float* dX, cudaStream_t s) {
     (void)K;
     const int64_t N = (int64_t)B * W;
-    const size_t smem = (size_t)D * TL_LD * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(backward_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    const size_t smem = (size_t)TL_F * (D + 4) * 4;
     const int64_t tiles = (N + TL_F - 1) / TL_F;
     int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
     if (grid < 1) grid = 1;
-    backward_dx_kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, dX);
+    cudaError_t e = cudaSuccess;
+#define VQB_DX(LPF, J)                                                                                                          \
+    do {                                                                                                                        \
+        e = cudaFuncSetAttribute(backward_dx_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);           \
+        if (e == cudaSuccess) backward_dx_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, dX); \
+    } while (0)
+    VQB_DISPATCH_D(D, VQB_DX);
+#undef VQB_DX
+    if (e != cudaSuccess) return e;
     note_launch();
     return cudaGetLastError();
 }
@@ -726,10 +768,15 @@ cudaError_t launch_onehot(const int64_t* idx, int64_t N, int K, float* out, cuda
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ E, const int64_t* __restrict__ idx, int D,
-                                                     int64_t W, int64_t N, float* __restrict__ out) {
-    extern __shared__ __align__(16) float Xs[];   // [D][33]
+template <int LPF, int J>
+__global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) gather_kernel(const float* __restrict__ E, const int64_t* __restrict__ idx, int D,
+                                                        int64_t W, int64_t N, float* __restrict__ out) {
+    extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
+    constexpr int FPW = 32 / LPF;
+    constexpr int ITER = (TL_F / 8) / FPW;
+    const int ld = D + 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPF, sl = lane % LPF;
     for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x) {
         const int64_t nl = tile * TL_F + lane;
         const bool valid = nl < N;
@@ -737,33 +784,40 @@ __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ E
         if (valid) { b = nl / W; w = nl - b * W; }
         const size_t col = (size_t)b * D * W + w;
         __syncthreads();
-        for (int fi = 0; fi < TL_F / 8; ++fi) {
-            const int f = warp * (TL_F / 8) + fi;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int f = warp * (TL_F / 8) + it * FPW + sub;
             const int64_t n = tile * TL_F + f;
-            if (n >= N) break;
-            const float* er = E + (size_t)idx[n] * D;
-            for (int d = lane; d < D; d += 32) Xs[d * TL_LD + f] = er[d];
+            if (n < N) {
+                const float* er = E + (size_t)idx[n] * D;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int d = 4 * sl + 4 * LPF * j;
+                    if (d < D) *reinterpret_cast<float4*>(Xs + f * ld + d) = *reinterpret_cast<const float4*>(er + d);
+                }
+            }
         }
         __syncthreads();
-        if (valid)
-            for (int d = warp; d < D; d += 8) st_stream(out + col + (size_t)d * W, Xs[d * TL_LD + lane]);
+        tile_store(Xs, ld, out, col, W, D, valid);
     }
 }
 
 cudaError_t launch_gather(const float* codebook, const int64_t* idx, int B, int D, int64_t W, int K, float* out, cudaStream_t s) {
     (void)K;
     const int64_t N = (int64_t)B * W;
-    const size_t smem = (size_t)D * TL_LD * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    const size_t smem = (size_t)TL_F * (D + 4) * 4;
     const int64_t tiles = (N + TL_F - 1) / TL_F;
     int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
     if (grid < 1) grid = 1;
-    gather_kernel<<<(unsigned)grid, 256, smem, s>>>(codebook, idx, D, W, N, out);
+    cudaError_t e = cudaSuccess;
+#define VQB_GA(LPF, J)                                                                                                 \
+    do {                                                                                                               \
+        e = cudaFuncSetAttribute(gather_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);       \
+        if (e == cudaSuccess) gather_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(codebook, idx, D, W, N, out);    \
+    } while (0)
+    VQB_DISPATCH_D(D, VQB_GA);
+#undef VQB_GA
+    if (e != cudaSuccess) return e;
     note_launch();
     return cudaGetLastError();
 }
