@@ -99,6 +99,77 @@ cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D,
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ frame tiles
+// All streaming kernels work on tiles of 32 frames x D held frame-major in shared memory with rows of D+4 floats: the
+// transposing global<->shared phases are coalesced over frames, the per-frame phase reads float4 rows, and LPF lanes
+// cooperate on one frame (32 / LPF frames per warp at a time), each lane owning 4*J dims.
+constexpr int TL_F = 32;              // frames per tile
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <int LPF>
+__device__ __forceinline__ float group_sum(float v) {   // sum over the LPF lanes that share a frame
+#pragma unroll
+    for (int o = LPF / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// coalesced BCW -> frame-major shared tile: thread = (frame = tid & 31, dim group = tid >> 5), 4 dims per access
+__device__ __forceinline__ void tile_load(float* Xs, int ld, const float* __restrict__ z, size_t col, int64_t W, int D, bool valid) {
+    const int f = threadIdx.x & 31;
+    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            const float* p = z + col + (size_t)d0 * W;
+            v.x = ld_stream(p);
+            v.y = ld_stream(p + W);
+            v.z = ld_stream(p + 2 * W);
+            v.w = ld_stream(p + 3 * W);
+        }
+        *reinterpret_cast<float4*>(Xs + f * ld + d0) = v;
+    }
+}
+// Same transposition with cp.async (LDGSTS): no register staging, so every thread has its whole share of the tile
+// (D/8 4-byte copies) in flight at once - the memory-level parallelism a latency-bound streaming kernel needs.
+// Out-of-range frames are zero-filled (src-size 0).  Follow with tile_fetch_wait() + __syncthreads().
+__device__ __forceinline__ void tile_fetch_async(float* Xs, int ld, const float* __restrict__ z, size_t col, int64_t W, int D, bool valid) {
+    const int f = threadIdx.x & 31;
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(Xs + f * ld);
+    const float* src0 = z + (valid ? col : 0);
+    const uint32_t nbytes = valid ? 4u : 0u;
+    for (int d = threadIdx.x >> 5; d < D; d += 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * d), "l"(src0 + (size_t)d * W), "r"(nbytes) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tile_fetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tile_store(const float* Xs, int ld, float* __restrict__ out, size_t col, int64_t W, int D, bool valid) {
+    const int f = threadIdx.x & 31;
+    if (!valid) return;
+    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(Xs + f * ld + d0);
+        float* p = out + col + (size_t)d0 * W;
+        st_stream(p, v.x);
+        st_stream(p + W, v.y);
+        st_stream(p + 2 * W, v.z);
+        st_stream(p + 3 * W, v.w);
+    }
+}
+
+// lanes per frame and float4 groups per lane for a given D: 8 lanes x (D/32) groups up to D = 256, 16 lanes beyond
+#define VQB_DISPATCH_D(D, CALL)                    \
+    do {                                           \
+        if ((D) <= 32) { CALL(8, 1); }             \
+        else if ((D) <= 64) { CALL(8, 2); }        \
+        else if ((D) <= 96) { CALL(8, 3); }        \
+        else if ((D) <= 128) { CALL(8, 4); }       \
+        else if ((D) <= 192) { CALL(8, 6); }       \
+        else if ((D) <= 256) { CALL(8, 8); }       \
+        else if ((D) <= 384) { CALL(16, 6); }      \
+        else { CALL(16, 8); }                      \
+    } while (0)
+
 // ------------------------------------------------------------------------------------------------ latent prep (bf16)
 // z [B, D, W] fp32 -> xb [N_pad, D] bf16 (frame-major = K-major A operand for tcgen05) and the per-frame guard band.
 // One block = 32 frames x all D, transposed through shared memory so both the read and the write are coalesced.
@@ -107,58 +178,80 @@ cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D,
 //   xt.et - x.e = dx.et + x.de,  so  |score_bf16(k) - score(k)| <= 2 (|dx| |et_k| + |x| |de_k|) + accumulation error.
 // Two codes are compared, hence the factor 4; the last term bounds fp32 accumulation in the tensor core and in the
 // reference's own sgemm.  |dx|, |x| are measured per frame here; max|et|, max|de|, max|e| come from codebook_prep.
-__global__ void __launch_bounds__(256) latent_prep_bf16_kernel(const float* __restrict__ z, int D, int64_t W, int64_t N,
-                                                               int64_t N_pad, __nv_bfloat16* __restrict__ xb,
-                                                               float* __restrict__ band, const WsMeta* __restrict__ meta) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int stride = D + 2;                                         // bf16 elements; (D+2)/2 words is odd -> no conflicts
-    __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [32][D+2]
-    float* part = reinterpret_cast<float*>(Xs + 32 * stride);         // [2][8][32]
+template <int LPF, int J>
+__global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) latent_prep_bf16_kernel(const float* __restrict__ z, int D, int64_t W, int64_t N,
+                                                                  int64_t N_pad, __nv_bfloat16* __restrict__ xb,
+                                                                  float* __restrict__ band, const WsMeta* __restrict__ meta) {
+    extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
+    constexpr int FPW = 32 / LPF;
+    constexpr int ITER = (TL_F / 8) / FPW;
+    const int ld = D + 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n = (int64_t)blockIdx.x * 32 + lane;
-    const bool valid = n < N;
-    int64_t b = 0, w = 0;
-    if (valid) { b = n / W; w = n - b * W; }
-    const float* zp = z + (size_t)b * D * W + w;
-    float s = 0.f, sd = 0.f;
-    for (int d = warp; d < D; d += 8) {
-        const float v = valid ? ld_stream(zp + (size_t)d * W) : 0.f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const float dv = v - __bfloat162float(h);
-        s = fmaf(v, v, s);
-        sd = fmaf(dv, dv, sd);
-        Xs[lane * stride + d] = h;
-    }
-    part[warp * 32 + lane] = s;
-    part[256 + warp * 32 + lane] = sd;
-    __syncthreads();
-    if (warp == 0 && valid) {
-        float t = 0.f, td = 0.f;
+    const int sub = lane / LPF, sl = lane % LPF;
+    const float etmax = sqrtf(__uint_as_float(meta->etmax2_bits)) * 1.0001f;
+    const float demax = sqrtf(__uint_as_float(meta->demax2_bits)) * 1.0001f;
+    const float emax = sqrtf(__uint_as_float(meta->emax2_bits)) * 1.0001f;
+    for (int64_t tile = blockIdx.x; tile * TL_F < N_pad; tile += gridDim.x) {
+        const int64_t nl = tile * TL_F + lane;
+        const bool valid = nl < N;
+        int64_t b = 0, w = 0;
+        if (valid) { b = nl / W; w = nl - b * W; }
+        const size_t col = (size_t)b * D * W + w;
+        __syncthreads();
+        tile_fetch_async(Xs, ld, z, col, W, D, valid);
+        tile_fetch_wait();
+        __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { t += part[i * 32 + lane]; td += part[256 + i * 32 + lane]; }
-        const float xn = sqrtf(t) * 1.0001f, dxn = sqrtf(td) * 1.0001f;
-        const float etmax = sqrtf(__uint_as_float(meta->etmax2_bits)) * 1.0001f;
-        const float demax = sqrtf(__uint_as_float(meta->demax2_bits)) * 1.0001f;
-        const float emax = sqrtf(__uint_as_float(meta->emax2_bits)) * 1.0001f;
-        // last terms: fp32 accumulation (tensor core and the reference's sgemm), the 3-term bf16 split of |e|^2/2
-        band[n] = 4.0f * (dxn * etmax + xn * demax) * 1.001f + 8.0f * (float)(D + 16) * 2.3841858e-07f * xn * emax +
-                  4.0e-7f * emax * emax + 1e-30f;
-    }
-    const uint32_t* Xw = reinterpret_cast<const uint32_t*>(Xs);
-    const int wstride = stride / 2;
-    for (int f = warp; f < 32; f += 8) {
-        const int64_t nf = (int64_t)blockIdx.x * 32 + f;
-        if (nf >= N_pad) break;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(xb + (size_t)nf * D);
-        for (int c = lane; c < D / 2; c += 32) dst[c] = Xw[f * wstride + c];
+        for (int it = 0; it < ITER; ++it) {
+            const int f = warp * (TL_F / 8) + it * FPW + sub;
+            const int64_t n = tile * TL_F + f;
+            float s = 0.f, sd = 0.f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int d = 4 * sl + 4 * LPF * j;
+                if (d < D) {
+                    const float4 v = *reinterpret_cast<const float4*>(Xs + f * ld + d);
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+                    const float2 b01 = __bfloat1622float2(h01), b23 = __bfloat1622float2(h23);
+                    const float d0 = v.x - b01.x, d1 = v.y - b01.y, d2 = v.z - b23.x, d3 = v.w - b23.y;
+                    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+                    sd = fmaf(d0, d0, sd); sd = fmaf(d1, d1, sd); sd = fmaf(d2, d2, sd); sd = fmaf(d3, d3, sd);
+                    if (n < N_pad) {
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(xb + (size_t)n * D + d) = pk;     // frames past N are written as zeros
+                    }
+                }
+            }
+            s = group_sum<LPF>(s);
+            sd = group_sum<LPF>(sd);
+            if (sl == 0 && n < N) {
+                const float xn = sqrtf(s) * 1.0001f, dxn = sqrtf(sd) * 1.0001f;
+                // last terms: fp32 accumulation (tensor core and the reference's sgemm), the 3-term bf16 split of |e|^2/2
+                band[n] = 4.0f * (dxn * etmax + xn * demax) * 1.001f + 8.0f * (float)(D + 16) * 2.3841858e-07f * xn * emax +
+                          4.0e-7f * emax * emax + 1e-30f;
+            }
+        }
     }
 }
 
 cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int64_t N_pad, __nv_bfloat16* xb, float* band,
                                     const WsMeta* meta, cudaStream_t s) {
     const int64_t N = (int64_t)B * W;
-    const size_t smem = (size_t)32 * (D + 2) * 2 + 2 * 8 * 32 * 4;
-    latent_prep_bf16_kernel<<<(unsigned)((N_pad + 31) / 32), 256, smem, s>>>(z, D, W, N, N_pad, xb, band, meta);
+    const size_t smem = (size_t)TL_F * (D + 4) * 4;
+    const int64_t tiles = (N_pad + TL_F - 1) / TL_F;
+    int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
+    if (grid < 1) grid = 1;
+    cudaError_t e = cudaSuccess;
+#define VQB_LP(LPF, J)                                                                                                            \
+    do {                                                                                                                          \
+        e = cudaFuncSetAttribute(latent_prep_bf16_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);        \
+        if (e == cudaSuccess) latent_prep_bf16_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, D, W, N, N_pad, xb, band, meta); \
+    } while (0)
+    VQB_DISPATCH_D(D, VQB_LP);
+#undef VQB_LP
+    if (e != cudaSuccess) return e;
     note_launch();
     return cudaGetLastError();
 }
@@ -336,46 +429,6 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
 // move one float4 (4 consecutive dims of one frame) per thread, the per-frame phase reads float4 rows - both are
 // bank-conflict free - and the codebook rows, residual atomics (red.v4) and shared accesses are all 16 bytes wide.
 // LPF lanes cooperate on one frame (32 / LPF frames per warp at a time), each lane owning 4*J dims.
-constexpr int TL_F = 32;              // frames per tile
-
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-template <int LPF>
-__device__ __forceinline__ float group_sum(float v) {   // sum over the LPF lanes that share a frame
-#pragma unroll
-    for (int o = LPF / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// coalesced BCW -> frame-major shared tile: thread = (frame = tid & 31, dim group = tid >> 5), 4 dims per access
-__device__ __forceinline__ void tile_load(float* Xs, int ld, const float* __restrict__ z, size_t col, int64_t W, int D, bool valid) {
-    const int f = threadIdx.x & 31;
-    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-            const float* p = z + col + (size_t)d0 * W;
-            v.x = ld_stream(p);
-            v.y = ld_stream(p + W);
-            v.z = ld_stream(p + 2 * W);
-            v.w = ld_stream(p + 3 * W);
-        }
-        *reinterpret_cast<float4*>(Xs + f * ld + d0) = v;
-    }
-}
-__device__ __forceinline__ void tile_store(const float* Xs, int ld, float* __restrict__ out, size_t col, int64_t W, int D, bool valid) {
-    const int f = threadIdx.x & 31;
-    if (!valid) return;
-    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
-        const float4 v = *reinterpret_cast<const float4*>(Xs + f * ld + d0);
-        float* p = out + col + (size_t)d0 * W;
-        st_stream(p, v.x);
-        st_stream(p + W, v.y);
-        st_stream(p + 2 * W, v.z);
-        st_stream(p + 3 * W, v.w);
-    }
-}
-
 template <int LPF, int J, bool kResid>
 __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                       const float* __restrict__ e2, int D, int64_t W, int64_t N, int K,
@@ -415,7 +468,8 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
             }
         }
         __syncthreads();
-        tile_load(Xs, ld, z, col, W, D, valid);
+        tile_fetch_async(Xs, ld, z, col, W, D, valid);
+        tile_fetch_wait();
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
@@ -537,19 +591,6 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
     }
 }
 
-// lanes per frame and float4 groups per lane for a given D: 8 lanes x (D/32) groups up to D = 256, 16 lanes beyond
-#define VQB_DISPATCH_D(D, CALL)                    \
-    do {                                           \
-        if ((D) <= 32) { CALL(8, 1); }             \
-        else if ((D) <= 64) { CALL(8, 2); }        \
-        else if ((D) <= 96) { CALL(8, 3); }        \
-        else if ((D) <= 128) { CALL(8, 4); }       \
-        else if ((D) <= 192) { CALL(8, 6); }       \
-        else if ((D) <= 256) { CALL(8, 8); }       \
-        else if ((D) <= 384) { CALL(16, 6); }      \
-        else { CALL(16, 8); }                      \
-    } while (0)
-
 template <int LPF, int J>
 static cudaError_t launch_tail_t(const float* z, const float* codebook, const float* e2, int D, int64_t W, int64_t N, int K,
                                  const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
@@ -657,10 +698,11 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(cons
                                                              const int64_t* __restrict__ idx, const float* __restrict__ Gq,
                                                              const float* __restrict__ g_c, float beta, int D, int64_t W,
                                                              int64_t N, float* __restrict__ dX) {
-    extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
+    extern __shared__ __align__(16) float Xs[];   // [32][D + 4] latents, then [32][D + 4] upstream gradient
     constexpr int FPW = 32 / LPF;
     constexpr int ITER = (TL_F / 8) / FPW;
     const int ld = D + 4;
+    float* Gs = Xs + TL_F * ld;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPF, sl = lane % LPF;
     const float gc = g_c ? *g_c : 0.f;
@@ -678,7 +720,9 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(cons
             k_r[it] = (n < N) ? idx[n] : 0;
         }
         __syncthreads();
-        tile_load(Xs, ld, z, col, W, D, valid);
+        tile_fetch_async(Xs, ld, z, col, W, D, valid);
+        if (Gq) tile_fetch_async(Gs, ld, Gq, col, W, D, valid);
+        tile_fetch_wait();
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
@@ -690,27 +734,17 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(cons
                 if (d < D) {
                     const float4 x = *reinterpret_cast<const float4*>(Xs + f * ld + d);
                     const float4 q = *reinterpret_cast<const float4*>(er + d);
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (Gq) g = *reinterpret_cast<const float4*>(Gs + f * ld + d);
                     float4 o;
-                    o.x = coef * __fsub_rn(x.x, q.x); o.y = coef * __fsub_rn(x.y, q.y);
-                    o.z = coef * __fsub_rn(x.z, q.z); o.w = coef * __fsub_rn(x.w, q.w);
+                    o.x = g.x + coef * __fsub_rn(x.x, q.x); o.y = g.y + coef * __fsub_rn(x.y, q.y);
+                    o.z = g.z + coef * __fsub_rn(x.z, q.z); o.w = g.w + coef * __fsub_rn(x.w, q.w);
                     *reinterpret_cast<float4*>(Xs + f * ld + d) = o;
                 }
             }
         }
         __syncthreads();
-        if (valid) {
-            const int f = threadIdx.x & 31;
-            for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
-                const float4 v = *reinterpret_cast<const float4*>(Xs + f * ld + d0);
-                const size_t a = col + (size_t)d0 * W;
-                float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-                if (Gq) { g0 = ld_stream(Gq + a); g1 = ld_stream(Gq + a + W); g2 = ld_stream(Gq + a + 2 * W); g3 = ld_stream(Gq + a + 3 * W); }
-                st_stream(dX + a, g0 + v.x);
-                st_stream(dX + a + W, g1 + v.y);
-                st_stream(dX + a + 2 * W, g2 + v.z);
-                st_stream(dX + a + 3 * W, g3 + v.w);
-            }
-        }
+        tile_store(Xs, ld, dX, col, W, D, valid);
     }
 }
 
@@ -718,14 +752,14 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
                                float beta, int B, int D, int64_t W, int K, float* dX, cudaStream_t s) {
     (void)K;
     const int64_t N = (int64_t)B * W;
-    const size_t smem = (size_t)TL_F * (D + 4) * 4;
+    const size_t smem = (size_t)2 * TL_F * (D + 4) * 4;
     const int64_t tiles = (N + TL_F - 1) / TL_F;
     int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
     if (grid < 1) grid = 1;
     cudaError_t e = cudaSuccess;
 #define VQB_DX(LPF, J)                                                                                                          \
     do {                                                                                                                        \
-        e = cudaFuncSetAttribute(backward_dx_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);           \
+        e = cudaFuncSetAttribute(backward_dx_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);          \
         if (e == cudaSuccess) backward_dx_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, dX); \
     } while (0)
     VQB_DISPATCH_D(D, VQB_DX);
