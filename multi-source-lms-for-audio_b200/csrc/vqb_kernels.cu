@@ -130,24 +130,16 @@ __device__ __forceinline__ void tile_load(float* Xs, int ld, const float* __rest
         *reinterpret_cast<float4*>(Xs + f * ld + d0) = v;
     }
 }
-// Coalesced BCW -> frame-major shared tile with cp.async (LDGSTS): no register staging, so every thread has its whole
-// share of the tile (D/8 4-byte copies) in flight at once - the memory-level parallelism a streaming kernel needs.
-// Within one instruction lane l copies frame l but dim d_base + ((l>>3) + r) & 3: the four 8-lane groups write four
-// different words of the 16-byte chunks, which makes the transposing shared-memory writes bank-conflict free (rows are
-// D+4 floats), while each group still reads a full 32-byte sector of global memory.
+// Same transposition with cp.async (LDGSTS): no register staging, so every thread has its whole share of the tile
+// (D/8 4-byte copies) in flight at once - the memory-level parallelism a latency-bound streaming kernel needs.
 // Out-of-range frames are zero-filled (src-size 0).  Follow with tile_fetch_wait() + __syncthreads().
 __device__ __forceinline__ void tile_fetch_async(float* Xs, int ld, const float* __restrict__ z, size_t col, int64_t W, int D, bool valid) {
-    const int f = threadIdx.x & 31, grp = (threadIdx.x >> 3) & 3;
+    const int f = threadIdx.x & 31;
     const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(Xs + f * ld);
     const float* src0 = z + (valid ? col : 0);
     const uint32_t nbytes = valid ? 4u : 0u;
-    for (int d_base = (threadIdx.x >> 5) * 4; d_base < D; d_base += 32) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int d = d_base + ((grp + r) & 3);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * d), "l"(src0 + (size_t)d * W), "r"(nbytes) : "memory");
-        }
-    }
+    for (int d = threadIdx.x >> 5; d < D; d += 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * d), "l"(src0 + (size_t)d * W), "r"(nbytes) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tile_fetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
