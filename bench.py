@@ -39,6 +39,16 @@ WORKLOADS = {
 BETA = 0.25
 
 
+def load_traffic(workload: str):
+    """DRAM bytes per tc_search_kernel launch from the committed ncu --set full capture of this workload (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "tc_search_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p)).get(workload)
+        if d:
+            return d.get("dram_bytes_per_launch")
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -290,7 +300,8 @@ def main():
         roofline = {"bound": "tensor", "kernel": "tc_search_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] +
                     " bf16 sustained (kernel timed inside a long step)", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
-                    "launches_timed": kn.value, "traffic": None}
+                    "launches_timed": kn.value, "traffic": load_traffic(args.workload),
+                    "algorithmic_flops_per_launch": flops_per_launch, "algorithmic_dram_bytes_per_launch": 2.0 * D * N}
     cpu = None
     if not args.no_cpu:
         n_cpu = cpu_sample_size(K, D)
