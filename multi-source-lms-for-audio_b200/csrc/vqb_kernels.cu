@@ -182,7 +182,7 @@ template <int LPF, int J>
 __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) latent_prep_bf16_kernel(const float* __restrict__ z, int D, int64_t W, int64_t N,
                                                                   int64_t N_pad, __nv_bfloat16* __restrict__ xb,
                                                                   float* __restrict__ band, const WsMeta* __restrict__ meta) {
-    extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
+    extern __shared__ __align__(16) float Xbuf[];   // 2 x [32][D + 4]
     constexpr int FPW = 32 / LPF;
     constexpr int ITER = (TL_F / 8) / FPW;
     const int ld = D + 4;
@@ -191,15 +191,31 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) latent_prep_bf16_kernel
     const float etmax = sqrtf(__uint_as_float(meta->etmax2_bits)) * 1.0001f;
     const float demax = sqrtf(__uint_as_float(meta->demax2_bits)) * 1.0001f;
     const float emax = sqrtf(__uint_as_float(meta->emax2_bits)) * 1.0001f;
-    for (int64_t tile = blockIdx.x; tile * TL_F < N_pad; tile += gridDim.x) {
+    auto tile_col = [&](int64_t tile, bool& valid) -> size_t {
         const int64_t nl = tile * TL_F + lane;
-        const bool valid = nl < N;
+        valid = nl < N;
         int64_t b = 0, w = 0;
         if (valid) { b = nl / W; w = nl - b * W; }
-        const size_t col = (size_t)b * D * W + w;
-        __syncthreads();
-        tile_fetch_async(Xs, ld, z, col, W, D, valid);
-        tile_fetch_wait();
+        return (size_t)b * D * W + w;
+    };
+    int buf = 0;
+    {
+        bool v0;
+        const size_t c0 = tile_col(blockIdx.x, v0);
+        if ((int64_t)blockIdx.x * TL_F < N_pad) tile_fetch_async(Xbuf, ld, z, c0, W, D, v0);
+    }
+    for (int64_t tile = blockIdx.x; tile * TL_F < N_pad; tile += gridDim.x, buf ^= 1) {
+        float* Xs = Xbuf + (size_t)buf * TL_F * ld;
+        __syncthreads();                          // every warp is done reading the other buffer
+        const int64_t next = tile + gridDim.x;
+        if (next * TL_F < N_pad) {
+            bool vn;
+            const size_t cn = tile_col(next, vn);
+            tile_fetch_async(Xbuf + (size_t)(buf ^ 1) * TL_F * ld, ld, z, cn, W, D, vn);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            tile_fetch_wait();
+        }
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
@@ -239,14 +255,14 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) latent_prep_bf16_kernel
 cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int64_t N_pad, __nv_bfloat16* xb, float* band,
                                     const WsMeta* meta, cudaStream_t s) {
     const int64_t N = (int64_t)B * W;
-    const size_t smem = (size_t)TL_F * (D + 4) * 4;
+    const size_t smem = (size_t)2 * TL_F * (D + 4) * 4;
     const int64_t tiles = (N_pad + TL_F - 1) / TL_F;
     int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
     if (grid < 1) grid = 1;
     cudaError_t e = cudaSuccess;
 #define VQB_LP(LPF, J)                                                                                                            \
     do {                                                                                                                          \
-        e = cudaFuncSetAttribute(latent_prep_bf16_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);        \
+        e = cudaFuncSetAttribute(latent_prep_bf16_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);       \
         if (e == cudaSuccess) latent_prep_bf16_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, D, W, N, N_pad, xb, band, meta); \
     } while (0)
     VQB_DISPATCH_D(D, VQB_LP);
@@ -437,7 +453,7 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
                                                       float* __restrict__ q_out, int* __restrict__ counts,
                                                       float* __restrict__ resid, double* __restrict__ sse_partials,
                                                       WsMeta* meta) {
-    extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
+    extern __shared__ __align__(16) float Xbuf[];   // 2 x [32][D + 4]: the next tile streams in while this one is worked on
     __shared__ double red[8];
     constexpr int FPW = 32 / LPF;                 // frames a warp works on at once
     constexpr int ITER = (TL_F / 8) / FPW;        // rounds per warp and tile
@@ -449,13 +465,24 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
     unsigned int n_resc = 0, n_short = 0;
     const bool resid_v4 = kResid && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;   // stats + K is 16B aligned iff K % 4 == 0
 
-    for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x) {
+    auto tile_col = [&](int64_t tile, bool& valid) -> size_t {
         const int64_t nl = tile * TL_F + lane;
-        const bool valid = nl < N;
+        valid = nl < N;
         int64_t b = 0, w = 0;
         if (valid) { b = nl / W; w = nl - b * W; }
-        const size_t col = (size_t)b * D * W + w;
-        // shortlist headers of this warp's frames, requested before the tile load so their latency hides behind it
+        return (size_t)b * D * W + w;
+    };
+    int buf = 0;
+    {
+        bool v0;
+        const size_t c0 = tile_col(blockIdx.x, v0);
+        if ((int64_t)blockIdx.x * TL_F < N) tile_fetch_async(Xbuf, ld, z, c0, W, D, v0);
+    }
+    for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x, buf ^= 1) {
+        float* Xs = Xbuf + (size_t)buf * TL_F * ld;
+        bool valid;
+        const size_t col = tile_col(tile, valid);
+        // shortlist headers of this warp's frames, requested early so their latency hides behind the tile fetch
         int cnt_r[ITER], k0_r[ITER];
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
@@ -467,9 +494,16 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
                 else { cnt_r[it] = cand_cnt[n]; k0_r[it] = cand_idx[(size_t)n * kCandMax]; }
             }
         }
-        __syncthreads();
-        tile_fetch_async(Xs, ld, z, col, W, D, valid);
-        tile_fetch_wait();
+        __syncthreads();                          // the other buffer's previous tile has been stored: it may be refilled
+        const int64_t next = tile + gridDim.x;
+        if (next * TL_F < N) {
+            bool vn;
+            const size_t cn = tile_col(next, vn);
+            tile_fetch_async(Xbuf + (size_t)(buf ^ 1) * TL_F * ld, ld, z, cn, W, D, vn);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile has landed; the next one stays in flight
+        } else {
+            tile_fetch_wait();
+        }
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
@@ -595,14 +629,14 @@ template <int LPF, int J>
 static cudaError_t launch_tail_t(const float* z, const float* codebook, const float* e2, int D, int64_t W, int64_t N, int K,
                                  const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                                  int* counts, float* resid, double* part, int grid, WsMeta* meta, cudaStream_t s) {
-    const size_t smem = (size_t)TL_F * (D + 4) * 4;
+    const size_t smem = (size_t)2 * TL_F * (D + 4) * 4;
     cudaError_t e;
     if (resid) {
-        if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
         tail_kernel<LPF, J, true><<<grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
                                                           resid, part, meta);
     } else {
-        if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
         tail_kernel<LPF, J, false><<<grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
                                                            nullptr, part, meta);
     }
