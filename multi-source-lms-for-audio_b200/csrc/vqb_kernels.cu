@@ -8,6 +8,7 @@
 #include "vqb_internal.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace vqb {
 
@@ -99,6 +100,12 @@ cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D,
     return cudaGetLastError();
 }
 
+static int tile_ldg_mode() {   // experiment switch: VQB_TILE_LDG=1 -> register-staged LDG tile loads instead of cp.async
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("VQB_TILE_LDG"); mode = (e && e[0] == '1') ? 1 : 0; }
+    return mode;
+}
+
 // ------------------------------------------------------------------------------------------------ frame tiles
 // All streaming kernels work on tiles of 32 frames x D held frame-major in shared memory with rows of D+4 floats: the
 // transposing global<->shared phases are coalesced over frames, the per-frame phase reads float4 rows, and LPF lanes
@@ -115,19 +122,31 @@ __device__ __forceinline__ float group_sum(float v) {   // sum over the LPF lane
     return v;
 }
 
-// coalesced BCW -> frame-major shared tile: thread = (frame = tid & 31, dim group = tid >> 5), 4 dims per access
+// coalesced BCW -> frame-major shared tile: thread = (frame = tid & 31, dim group = tid >> 5), 4 dims per access.
+// Scalar LDG (1.8 cycles per warp-instruction) + one conflict-free STS.128 per 4 dims is the cheapest transposition in
+// pipe time; loads are issued in batches of 16 per thread (4 row groups) before any store so enough bytes are in flight.
 __device__ __forceinline__ void tile_load(float* Xs, int ld, const float* __restrict__ z, size_t col, int64_t W, int D, bool valid) {
     const int f = threadIdx.x & 31;
-    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-            const float* p = z + col + (size_t)d0 * W;
-            v.x = ld_stream(p);
-            v.y = ld_stream(p + W);
-            v.z = ld_stream(p + 2 * W);
-            v.w = ld_stream(p + 3 * W);
+    const float* p0 = z + (valid ? col : 0);
+    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 128) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int d = d0 + 32 * u;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && d < D) {
+                const float* p = p0 + (size_t)d * W;
+                v[u].x = ld_stream(p);
+                v[u].y = ld_stream(p + W);
+                v[u].z = ld_stream(p + 2 * W);
+                v[u].w = ld_stream(p + 3 * W);
+            }
         }
-        *reinterpret_cast<float4*>(Xs + f * ld + d0) = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int d = d0 + 32 * u;
+            if (d < D) *reinterpret_cast<float4*>(Xs + f * ld + d) = v[u];
+        }
     }
 }
 // Same transposition with cp.async (LDGSTS): no register staging, so every thread has its whole share of the tile
@@ -181,7 +200,7 @@ __device__ __forceinline__ void tile_store(const float* Xs, int ld, float* __res
 template <int LPF, int J>
 __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) latent_prep_bf16_kernel(const float* __restrict__ z, int D, int64_t W, int64_t N,
                                                                   int64_t N_pad, __nv_bfloat16* __restrict__ xb,
-                                                                  float* __restrict__ band, const WsMeta* __restrict__ meta) {
+                                                                  float* __restrict__ band, const WsMeta* __restrict__ meta, int ldg) {
     extern __shared__ __align__(16) float Xbuf[];   // 2 x [32][D + 4]
     constexpr int FPW = 32 / LPF;
     constexpr int ITER = (TL_F / 8) / FPW;
@@ -202,13 +221,17 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) latent_prep_bf16_kernel
     {
         bool v0;
         const size_t c0 = tile_col(blockIdx.x, v0);
-        if ((int64_t)blockIdx.x * TL_F < N_pad) tile_fetch_async(Xbuf, ld, z, c0, W, D, v0);
+        if (!ldg && (int64_t)blockIdx.x * TL_F < N_pad) tile_fetch_async(Xbuf, ld, z, c0, W, D, v0);
     }
     for (int64_t tile = blockIdx.x; tile * TL_F < N_pad; tile += gridDim.x, buf ^= 1) {
         float* Xs = Xbuf + (size_t)buf * TL_F * ld;
         __syncthreads();                          // every warp is done reading the other buffer
         const int64_t next = tile + gridDim.x;
-        if (next * TL_F < N_pad) {
+        if (ldg) {
+            bool vc;
+            const size_t cc = tile_col(tile, vc);
+            tile_load(Xs, ld, z, cc, W, D, vc);
+        } else if (next * TL_F < N_pad) {
             bool vn;
             const size_t cn = tile_col(next, vn);
             tile_fetch_async(Xbuf + (size_t)(buf ^ 1) * TL_F * ld, ld, z, cn, W, D, vn);
@@ -263,7 +286,7 @@ cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int
 #define VQB_LP(LPF, J)                                                                                                            \
     do {                                                                                                                          \
         e = cudaFuncSetAttribute(latent_prep_bf16_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);       \
-        if (e == cudaSuccess) latent_prep_bf16_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, D, W, N, N_pad, xb, band, meta); \
+        if (e == cudaSuccess) latent_prep_bf16_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, D, W, N, N_pad, xb, band, meta, tile_ldg_mode()); \
     } while (0)
     VQB_DISPATCH_D(D, VQB_LP);
 #undef VQB_LP
@@ -452,7 +475,7 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
                                                       const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
                                                       float* __restrict__ q_out, int* __restrict__ counts,
                                                       float* __restrict__ resid, double* __restrict__ sse_partials,
-                                                      WsMeta* meta) {
+                                                      WsMeta* meta, int ldg) {
     extern __shared__ __align__(16) float Xbuf[];   // 2 x [32][D + 4]: the next tile streams in while this one is worked on
     __shared__ double red[8];
     constexpr int FPW = 32 / LPF;                 // frames a warp works on at once
@@ -476,7 +499,7 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
     {
         bool v0;
         const size_t c0 = tile_col(blockIdx.x, v0);
-        if ((int64_t)blockIdx.x * TL_F < N) tile_fetch_async(Xbuf, ld, z, c0, W, D, v0);
+        if (!ldg && (int64_t)blockIdx.x * TL_F < N) tile_fetch_async(Xbuf, ld, z, c0, W, D, v0);
     }
     for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x, buf ^= 1) {
         float* Xs = Xbuf + (size_t)buf * TL_F * ld;
@@ -496,7 +519,9 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
         }
         __syncthreads();                          // the other buffer's previous tile has been stored: it may be refilled
         const int64_t next = tile + gridDim.x;
-        if (next * TL_F < N) {
+        if (ldg) {
+            tile_load(Xs, ld, z, col, W, D, valid);
+        } else if (next * TL_F < N) {
             bool vn;
             const size_t cn = tile_col(next, vn);
             tile_fetch_async(Xbuf + (size_t)(buf ^ 1) * TL_F * ld, ld, z, cn, W, D, vn);
@@ -634,11 +659,11 @@ static cudaError_t launch_tail_t(const float* z, const float* codebook, const fl
     if (resid) {
         if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
         tail_kernel<LPF, J, true><<<grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
-                                                          resid, part, meta);
+                                                          resid, part, meta, tile_ldg_mode());
     } else {
         if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
         tail_kernel<LPF, J, false><<<grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
-                                                           nullptr, part, meta);
+                                                           nullptr, part, meta, tile_ldg_mode());
     }
     return cudaGetLastError();
 }
@@ -731,7 +756,7 @@ template <int LPF, int J>
 __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                              const int64_t* __restrict__ idx, const float* __restrict__ Gq,
                                                              const float* __restrict__ g_c, float beta, int D, int64_t W,
-                                                             int64_t N, float* __restrict__ dX) {
+                                                             int64_t N, float* __restrict__ dX, int ldg) {
     extern __shared__ __align__(16) float Xs[];   // [32][D + 4] latents, then [32][D + 4] upstream gradient
     constexpr int FPW = 32 / LPF;
     constexpr int ITER = (TL_F / 8) / FPW;
@@ -754,9 +779,14 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(cons
             k_r[it] = (n < N) ? idx[n] : 0;
         }
         __syncthreads();
-        tile_fetch_async(Xs, ld, z, col, W, D, valid);
-        if (Gq) tile_fetch_async(Gs, ld, Gq, col, W, D, valid);
-        tile_fetch_wait();
+        if (ldg) {
+            tile_load(Xs, ld, z, col, W, D, valid);
+            if (Gq) tile_load(Gs, ld, Gq, col, W, D, valid);
+        } else {
+            tile_fetch_async(Xs, ld, z, col, W, D, valid);
+            if (Gq) tile_fetch_async(Gs, ld, Gq, col, W, D, valid);
+            tile_fetch_wait();
+        }
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
@@ -794,7 +824,7 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
 #define VQB_DX(LPF, J)                                                                                                          \
     do {                                                                                                                        \
         e = cudaFuncSetAttribute(backward_dx_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);          \
-        if (e == cudaSuccess) backward_dx_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, dX); \
+        if (e == cudaSuccess) backward_dx_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, dX, tile_ldg_mode()); \
     } while (0)
     VQB_DISPATCH_D(D, VQB_DX);
 #undef VQB_DX
