@@ -100,9 +100,9 @@ cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D,
     return cudaGetLastError();
 }
 
-static int tile_ldg_mode() {   // experiment switch: VQB_TILE_LDG=1 -> register-staged LDG tile loads instead of cp.async
+static int tile_ldg_mode() {   // tile loads: register-staged LDG batches (default, measured faster) or cp.async (VQB_TILE_LDG=0)
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("VQB_TILE_LDG"); mode = (e && e[0] == '1') ? 1 : 0; }
+    if (mode < 0) { const char* e = getenv("VQB_TILE_LDG"); mode = (e && e[0] == '0') ? 0 : 1; }
     return mode;
 }
 

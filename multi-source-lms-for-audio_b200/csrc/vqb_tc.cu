@@ -39,7 +39,7 @@ constexpr int EH_SLICE_BYTES = BN * 16;      // 4 KiB: (h1,h2,h3,0,0,0,0,0) bf16
 constexpr int EH_SLOTS = 2;
 constexpr int AX_BYTES = BM * 16;            // 2 KiB: K-half 0 of the constant A operand
 constexpr int ZERO_BYTES = EH_SLICE_BYTES;   // shared all-zero K-half 1 of both bias operands
-constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 4;
+constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 8;   // 4 whole-tile stages (1-CTA) or 8 half-tile stages (2-CTA)
 constexpr int EPI_WARP0 = 0, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;   // 4 warps per TMEM lane quarter: 64 columns each
 // The single-thread producer / MMA loops sit in the HIGHEST warp ids: the scheduler favours them over waiting epilogue warps.
 constexpr int PRODUCER_WARP = 16, MMA_WARP = 17, ALLOC_WARP = 18;
@@ -117,6 +117,23 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
+// 2-CTA (cta_group::2) variants.  The pair's leader (cluster rank 0) owns the "full" barriers: both CTAs' TMA loads
+// complete their transaction bytes on the leader's barrier (peer bit 24 of the shared-window address cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {   // arrive on the same barrier of CTA `cta`
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -134,6 +151,26 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= [A0; A1] * [B0; B1]^T over the CTA pair: M = 256 (128 frames per CTA), N = 256 (128 codes per CTA)
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -170,6 +207,7 @@ __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo
 }
 // c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 #define VQB_R32(r) \
     "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), \
@@ -253,16 +291,20 @@ __device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], int code0, in
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
+// kTwo = false: cta_group::1 MMAs, every CTA holds whole codebook tiles (optionally multicast inside a cluster).
+// kTwo = true : CTA pairs with cta_group::2 MMAs (M = 256 over the pair): each CTA holds its own 128 frames and HALF of every
+//               codebook tile (128 codes), which halves the per-SM operand ingest and doubles the ring depth (8 stages).
+template <bool kTwo>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
-                 const __nv_bfloat16* __restrict__ eh, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
+                 const __grid_constant__ CUtensorMap tmap_eh, const __nv_bfloat16* __restrict__ eh, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
-    unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB
-    unsigned char* sEH = sB + (size_t)b_stages * B_STAGE_BYTES;          // EH_SLOTS x 4 KiB bias operand B (K-half 0)
+    unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB (16 KiB half tiles in 2-CTA mode)
+    unsigned char* sEH = sB + (size_t)b_stages * (kTwo ? B_STAGE_BYTES / 2 : B_STAGE_BYTES);   // EH_SLOTS x 4 KiB bias operand B (K-half 0)
     unsigned char* sAX = sEH + EH_SLOTS * EH_SLICE_BYTES;                // 2 KiB constant bias operand A (K-half 0)
     unsigned char* sZero = sAX + AX_BYTES;                               // 4 KiB of zeros: K-half 1 of both bias operands
     float* sMin = reinterpret_cast<float*>(sZero + ZERO_BYTES);          // [4][128] running maxima of the four column quarters
@@ -276,6 +318,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // past the end works on zero-filled rows and publishes nothing.
     const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+    constexpr uint32_t kStageBytes = kTwo ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;   // per-CTA bytes of one codebook stage
+    constexpr uint32_t kEhBytes = kTwo ? EH_SLICE_BYTES / 2 : EH_SLICE_BYTES;
+    const bool leader = !kTwo || crank == 0;
     const int n_clusters = (int)gridDim.x / cs;
     const int cluster_id = (int)blockIdx.x / cs;
     const int rounds = (num_m_tiles + n_clusters * cs - 1) / (n_clusters * cs);
@@ -285,7 +330,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         prefetch_tmap(&tmap_e);
     }
     if (warp == MMA_WARP && lane == 0) {
-        for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), cs); }
+        for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), kTwo ? 1 : cs); }
         for (int i = 0; i < a_slots; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
         for (int i = 0; i < EH_SLOTS; ++i) {
             mbar_init(smem_u32(&bars->eh_full[i]), 1);
@@ -293,11 +338,14 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->tmem_full[i]), 1);
-            mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_THREADS / 32);
+            mbar_init(smem_u32(&bars->tmem_empty[i]), (kTwo ? 2 : 1) * EPI_THREADS / 32);   // 2-CTA: both CTAs' epilogues report to the leader
         }
         fence_barrier_init();
     }
-    if (warp == ALLOC_WARP) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    if (warp == ALLOC_WARP) {
+        if (kTwo) tmem_alloc_2sm(smem_u32(&bars->tmem_base), 512);
+        else tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    }
     {   // constant bias operand A: every frame row is (-1, -1, -1, 0, 0, 0, 0, 0) in K-half 0; K-half 1 is the zero block
         uint4* ax = reinterpret_cast<uint4*>(sAX);
         for (int i = threadIdx.x; i < AX_BYTES / 16; i += NUM_THREADS) ax[i] = make_uint4(0xBF80BF80u, 0x0000BF80u, 0u, 0u);
@@ -315,8 +363,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ================================================================ TMA producer (converged warp, one elected lane issues)
         uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, es = 0, e_ph = 0;
         const uint32_t slice = (uint32_t)B_STAGE_BYTES / (uint32_t)cs;
-        const int b_row_off = (int)crank * (BN / cs);
-        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB) + crank * slice, sE_u = smem_u32(sEH);
+        const int b_row_off = kTwo ? (int)crank * (BN / 2) : (int)crank * (BN / cs);
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB) + (kTwo ? 0u : crank * slice), sE_u = smem_u32(sEH);
         const uint32_t bar_afull = smem_u32(&bars->a_full[0]), bar_aempty = smem_u32(&bars->a_empty[0]);
         const uint32_t bar_bfull = smem_u32(&bars->b_full[0]), bar_bempty = smem_u32(&bars->b_empty[0]);
         const uint32_t bar_efull = smem_u32(&bars->eh_full[0]), bar_eempty = smem_u32(&bars->eh_empty[0]);
@@ -326,8 +374,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             for (int nt = 0; nt < num_n_tiles; ++nt) {
                 mbar_wait(bar_eempty + es * 8, e_ph ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(bar_efull + es * 8, EH_SLICE_BYTES);
-                    bulk_load_1d(sE_u + es * EH_SLICE_BYTES, eh + (size_t)nt * BN * 8, EH_SLICE_BYTES, bar_efull + es * 8);
+                    if (kTwo) {   // own half of the bias operand; both halves complete on the leader's barrier
+                        if (leader) mbar_expect_tx(bar_efull + es * 8, EH_SLICE_BYTES);
+                        tma_load_2d_2sm(sE_u + es * kEhBytes, &tmap_eh, bar_efull + es * 8, 0, nt * BN + b_row_off);
+                    } else {
+                        mbar_expect_tx(bar_efull + es * 8, EH_SLICE_BYTES);
+                        bulk_load_1d(sE_u + es * EH_SLICE_BYTES, eh + (size_t)nt * BN * 8, EH_SLICE_BYTES, bar_efull + es * 8);
+                    }
                 }
                 __syncwarp();
                 if (++es == EH_SLOTS) { es = 0; e_ph ^= 1; }
@@ -337,14 +390,24 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     mbar_wait(bar_bempty + b_st * 8, b_ph ^ 1);
                     if (elect_one()) {
                         if (nt == 0) {
-                            mbar_expect_tx(bar_afull + slot * 8, A_CHUNK_BYTES);
-                            tma_load_2d(sA_u + slot * A_CHUNK_BYTES, &tmap_x, bar_afull + slot * 8, kb * BK, a_row);
+                            if (kTwo) {
+                                if (leader) mbar_expect_tx(bar_afull + slot * 8, 2 * A_CHUNK_BYTES);
+                                tma_load_2d_2sm(sA_u + slot * A_CHUNK_BYTES, &tmap_x, bar_afull + slot * 8, kb * BK, a_row);
+                            } else {
+                                mbar_expect_tx(bar_afull + slot * 8, A_CHUNK_BYTES);
+                                tma_load_2d(sA_u + slot * A_CHUNK_BYTES, &tmap_x, bar_afull + slot * 8, kb * BK, a_row);
+                            }
                         }
-                        mbar_expect_tx(bar_bfull + b_st * 8, B_STAGE_BYTES);   // own slice + the peers' slices
-                        if (cs == 1)
-                            tma_load_2d(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN);
-                        else
-                            tma_load_2d_mc(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN + b_row_off, cmask);
+                        if (kTwo) {
+                            if (leader) mbar_expect_tx(bar_bfull + b_st * 8, B_STAGE_BYTES);   // both halves
+                            tma_load_2d_2sm(sB_u + b_st * kStageBytes, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN + b_row_off);
+                        } else {
+                            mbar_expect_tx(bar_bfull + b_st * 8, B_STAGE_BYTES);   // own slice + the peers' slices
+                            if (cs == 1)
+                                tma_load_2d(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN);
+                            else
+                                tma_load_2d_mc(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN + b_row_off, cmask);
+                        }
                     }
                     __syncwarp();
                     if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
@@ -353,8 +416,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             a_slot0 += num_kb;
             if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
         }
-    } else if (warp == MMA_WARP) {
-        // ================================================================ MMA issuer (converged warp, one elected lane issues)
+    } else if (warp == MMA_WARP && leader) {
+        // ================================================================ MMA issuer (converged warp, one elected lane issues;
+        //                                                                   in 2-CTA mode only the pair's leader)
         uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, as = 0, t_ph = 0, es = 0, e_ph = 0;
         const uint64_t dA0 = make_desc_sw128(smem_u32(sA)), dB0 = make_desc_sw128(smem_u32(sB));
         // bias operands: 8-row groups 128 B apart, K-half 1 = the shared zero block
@@ -378,14 +442,23 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         // descriptors address shared memory in 16-byte units: +1024 per 16 KiB A chunk, +2048 per 32 KiB B stage,
                         // +2 per K step of 16 bf16 (32 bytes) inside the 128-byte swizzle row
                         const uint64_t da = dA0 + (uint64_t)(slot * (A_CHUNK_BYTES >> 4));
-                        const uint64_t db = dB0 + (uint64_t)(b_st * (B_STAGE_BYTES >> 4));
-                        umma_bf16(tmem_d, da, db, kIdesc, kb ? 1u : 0u);
-                        umma_bf16(tmem_d, da + 2, db + 2, kIdesc, 1u);
-                        umma_bf16(tmem_d, da + 4, db + 4, kIdesc, 1u);
-                        umma_bf16(tmem_d, da + 6, db + 6, kIdesc, 1u);
-                        if (cs == 1) umma_commit(bar_bempty + b_st * 8);
-                        else umma_commit_mc(bar_bempty + b_st * 8, cmask);
-                        if (last_nt) umma_commit(bar_aempty + slot * 8);
+                        const uint64_t db = dB0 + (uint64_t)(b_st * (kStageBytes >> 4));
+                        if (kTwo) {
+                            umma_bf16_2sm(tmem_d, da, db, kIdesc2, kb ? 1u : 0u);
+                            umma_bf16_2sm(tmem_d, da + 2, db + 2, kIdesc2, 1u);
+                            umma_bf16_2sm(tmem_d, da + 4, db + 4, kIdesc2, 1u);
+                            umma_bf16_2sm(tmem_d, da + 6, db + 6, kIdesc2, 1u);
+                            umma_commit_2sm(bar_bempty + b_st * 8, 3);
+                            if (last_nt) umma_commit_2sm(bar_aempty + slot * 8, 3);
+                        } else {
+                            umma_bf16(tmem_d, da, db, kIdesc, kb ? 1u : 0u);
+                            umma_bf16(tmem_d, da + 2, db + 2, kIdesc, 1u);
+                            umma_bf16(tmem_d, da + 4, db + 4, kIdesc, 1u);
+                            umma_bf16(tmem_d, da + 6, db + 6, kIdesc, 1u);
+                            if (cs == 1) umma_commit(bar_bempty + b_st * 8);
+                            else umma_commit_mc(bar_bempty + b_st * 8, cmask);
+                            if (last_nt) umma_commit(bar_aempty + slot * 8);
+                        }
                     }
                     __syncwarp();
                     if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
@@ -394,10 +467,16 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 mbar_wait(bar_efull + es * 8, e_ph);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t eh_u = sEH_u + es * EH_SLICE_BYTES;
-                    umma_bf16(tmem_d, dAX, make_desc_noswz(eh_u, sZero_u - eh_u, 128), kIdesc, 1u);
-                    umma_commit(bar_eempty + es * 8);
-                    umma_commit(bar_tfull + as * 8);
+                    const uint32_t eh_u = sEH_u + es * kEhBytes;
+                    if (kTwo) {
+                        umma_bf16_2sm(tmem_d, dAX, make_desc_noswz(eh_u, sZero_u - eh_u, 128), kIdesc2, 1u);
+                        umma_commit_2sm(bar_eempty + es * 8, 3);
+                        umma_commit_2sm(bar_tfull + as * 8, 3);
+                    } else {
+                        umma_bf16(tmem_d, dAX, make_desc_noswz(eh_u, sZero_u - eh_u, 128), kIdesc, 1u);
+                        umma_commit(bar_eempty + es * 8);
+                        umma_commit(bar_tfull + as * 8);
+                    }
                 }
                 __syncwarp();
                 if (++es == EH_SLOTS) { es = 0; e_ph ^= 1; }
@@ -447,7 +526,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[as]));
+                if (lane == 0) {
+                    if (kTwo && crank != 0) mbar_arrive_remote(smem_u32(&bars->tmem_empty[as]), 0);   // the leader issues the pair's MMAs
+                    else mbar_arrive(smem_u32(&bars->tmem_empty[as]));
+                }
             }
             // ---- resolve this thread's chunks against the frame's final maximum and publish the shortlist
             sMin[colq * BM + row_in_tile] = thr + hband;                     // running maximum of this column quarter
@@ -510,7 +592,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (cs > 1) cluster_sync_all();   // no CTA may retire while a peer can still multicast into it or arrive on its barriers
     if (warp == ALLOC_WARP) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (kTwo) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -542,6 +625,21 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return 1000 + (int)r; }
+    return 0;
+}
+
+// bias operand [K_pad, 8] bf16 (16-byte rows, no swizzle): box = 128 codes = one CTA's half of a codebook tile
+static int make_map_eh(CUtensorMap* map, const void* base, uint64_t rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VQB_E_DEVICE; }
+    const cuuint64_t dims[2] = {8, rows};
+    const cuuint64_t strides[1] = {16};
+    const cuuint32_t box[2] = {8, (cuuint32_t)(BN / 2)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(eh) failed with CUresult %d", (int)r); return 1000 + (int)r; }
     return 0;
 }
 
@@ -579,29 +677,36 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __n
     if ((rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM)) != 0) return rc;
     const int num_kb = (D + BK - 1) / BK;
     const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 2 * BM * 4 + sizeof(Barriers) + 1024;
-    int b_stages = (int)((227 * 1024 - fixed) / B_STAGE_BYTES);
-    if (b_stages > MAX_B_STAGES) b_stages = MAX_B_STAGES;
-    if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
-    const size_t smem = fixed + (size_t)b_stages * B_STAGE_BYTES;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_search_kernel)");
-        attr_done = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > kTcMaxCtas) sms = kTcMaxCtas;
     const int num_m_tiles = (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
-    int cs = 2;                                   // cluster size for the codebook multicast (VQB_TC_CLUSTER=1|2|4)
+    // VQB_TC_MODE=2: CTA pairs with cta_group::2 MMAs; otherwise cta_group::1 with VQB_TC_CLUSTER-way codebook multicast
+    bool two = false;
+    if (const char* env = getenv("VQB_TC_MODE")) two = env[0] == '2';
+    int cs = 2;
     if (const char* env = getenv("VQB_TC_CLUSTER")) cs = atoi(env);
     if (cs != 1 && cs != 2 && cs != 4) cs = 2;
-    if (num_m_tiles < 2 * cs) cs = 1;
-    CUtensorMap me_c;
-    if ((rc = make_map(&me_c, eb, (uint64_t)K_pad, (uint64_t)D, BN / cs)) != 0) return rc;
-    if (sms > kTcMaxCtas) sms = kTcMaxCtas;
+    if (two) cs = 2;
+    if (num_m_tiles < 2 * cs) { cs = 1; two = false; }
+    const size_t stage_bytes = two ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 2 * BM * 4 + sizeof(Barriers) + 1024;
+    int b_stages = (int)((227 * 1024 - fixed) / stage_bytes);
+    if (b_stages > (two ? 8 : 4)) b_stages = two ? 8 : 4;
+    if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
+    const size_t smem = fixed + (size_t)b_stages * stage_bytes;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_search_kernel)");
+        attr_done = true;
+    }
+    CUtensorMap me_c, meh;
+    if ((rc = make_map(&me_c, eb, (uint64_t)K_pad, (uint64_t)D, two ? BN / 2 : BN / cs)) != 0) return rc;
+    if ((rc = make_map_eh(&meh, eh, (uint64_t)K_pad)) != 0) return rc;
     int grid = num_m_tiles < sms ? num_m_tiles : sms;
     grid = grid / cs * cs;
     cudaLaunchConfig_t cfg{};
@@ -617,8 +722,13 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __n
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     TimingSlot* slot = timing_begin(s);
-    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_search_kernel, mx, me_c, eh, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs,
-                                        K, cand_cnt, cand_idx, fallback_rows, meta, best64, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
+    cudaError_t le;
+    if (two)
+        le = cudaLaunchKernelEx(&cfg, tc_search_kernel<true>, mx, me_c, meh, eh, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages,
+                                cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
+    else
+        le = cudaLaunchKernelEx(&cfg, tc_search_kernel<false>, mx, me_c, meh, eh, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages,
+                                cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
     if (le != cudaSuccess) return cuda_fail(le, "tc_search_kernel launch");
     cudaError_t e = cudaGetLastError();
     timing_end(slot, s);
