@@ -683,9 +683,9 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __n
     if (sms > kTcMaxCtas) sms = kTcMaxCtas;
     const int num_m_tiles = (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
-    // VQB_TC_MODE=2: CTA pairs with cta_group::2 MMAs; otherwise cta_group::1 with VQB_TC_CLUSTER-way codebook multicast
-    bool two = false;
-    if (const char* env = getenv("VQB_TC_MODE")) two = env[0] == '2';
+    // default: CTA pairs with cta_group::2 MMAs; VQB_TC_MODE=1: cta_group::1 with VQB_TC_CLUSTER-way codebook multicast
+    bool two = true;
+    if (const char* env = getenv("VQB_TC_MODE")) two = env[0] != '1';
     int cs = 2;
     if (const char* env = getenv("VQB_TC_CLUSTER")) cs = atoi(env);
     if (cs != 1 && cs != 2 && cs != 4) cs = 2;
