@@ -264,10 +264,18 @@ struct EventStack {
     }
 };
 
+// monotone float <-> int mapping so that a shared running maximum can be kept with an integer atomicMax
+__device__ __forceinline__ int f2ord(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
 // One 32-column slab of accumulators (= -score/2) for this thread's frame: a pure running arg-max.
 // Fast path per slab: 16 FMNMX3 + one compare.  When the slab maximum is within the band of the running maximum, the
 // four 8-code chunks are appended under predicates (straight-line code) and the threshold tightens.
-__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, float hband, float& thr, EventStack& ev) {
+// The four threads that share a frame (one per column quarter, in four different warps) pool their running maximum in
+// shared memory (`smax`): every thread's threshold tracks the best score ANY quarter has seen, which cuts the number of
+// appended chunks per frame from 4 x ln(K/32) to ln(K/8)-ish.
+__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, float hband, float& thr, EventStack& ev, int* smax) {
+    thr = fmaxf(thr, ord2f(*reinterpret_cast<volatile int*>(smax)) - hband);
     float t[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -281,6 +289,7 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, f
 #pragma unroll
         for (int g = 0; g < 4; ++g) ev.push_if(t[g] > thr, t[g], chunk0 + g, &r[g * 8]);
         thr = fmaxf(thr, slab_max - hband);
+        atomicMax(smax, f2ord(slab_max));
     }
 }
 
@@ -308,8 +317,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     unsigned char* sAX = sEH + EH_SLOTS * EH_SLICE_BYTES;                // 2 KiB constant bias operand A (K-half 0)
     unsigned char* sZero = sAX + AX_BYTES;                               // 4 KiB of zeros: K-half 1 of both bias operands
     float* sMin = reinterpret_cast<float*>(sZero + ZERO_BYTES);          // [4][128] running maxima of the four column quarters
-    int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags
-    Barriers* bars = reinterpret_cast<Barriers*>(sCnt + 2 * BM);
+    int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
+    Barriers* bars = reinterpret_cast<Barriers*>(sCnt + 3 * BM);        // [128] pooled running maximum per frame (ordered int)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Cluster of `cs` CTAs: every CTA quantises its own 128-frame tile, but each codebook tile is fetched from L2 only
@@ -498,7 +507,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         EventStack ev;
         ev.base = ev_scratch + ((size_t)blockIdx.x * EPI_THREADS + et) * (EV_CAP * EV_WORDS);
         ev.n = 0;
-        if (colq == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; }
+        if (colq == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; sCnt[2 * BM + row_in_tile] = f2ord(-INFINITY); }
+        int* smax = sCnt + 2 * BM + row_in_tile;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         uint32_t n_it = 0;
         for (int rd = 0; rd < rounds; ++rd) {
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
@@ -521,7 +532,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (scores_dbg) {
                         if (row < N) dump_slab(ra, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
                     } else {
-                        scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev);
+                        scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev, smax);
                     }
                 }
                 tc_fence_before();
@@ -567,6 +578,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
                 if (lost) sCnt[BM + row_in_tile] = 1;
             }
+            if (colq == 0) *smax = f2ord(-INFINITY);       // nobody reads the pooled maximum between the two barriers
             asm volatile("bar.sync 2, 512;" ::: "memory");
             if (colq == 0) {
                 if (row < N && !scores_dbg) {
@@ -692,7 +704,7 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __n
     if (two) cs = 2;
     if (num_m_tiles < 2 * cs) { cs = 1; two = false; }
     const size_t stage_bytes = two ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 2 * BM * 4 + sizeof(Barriers) + 1024;
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 + sizeof(Barriers) + 1024;
     int b_stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (b_stages > (two ? 8 : 4)) b_stages = two ? 8 : 4;
     if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
