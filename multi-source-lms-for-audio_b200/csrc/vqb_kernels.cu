@@ -176,15 +176,14 @@ __device__ __forceinline__ void tile_store(const float* Xs, int ld, float* __res
     }
 }
 
-// lanes per frame and float4 groups per lane for a given D: 8 lanes x (D/32) groups up to D = 256, 16 lanes beyond
+// lanes per frame and float4 groups per lane for a given D: 8 lanes x (D/32) groups up to D = 64, 16 lanes x (D/64) beyond
 #define VQB_DISPATCH_D(D, CALL)                    \
     do {                                           \
         if ((D) <= 32) { CALL(8, 1); }             \
         else if ((D) <= 64) { CALL(8, 2); }        \
-        else if ((D) <= 96) { CALL(8, 3); }        \
-        else if ((D) <= 128) { CALL(8, 4); }       \
-        else if ((D) <= 192) { CALL(8, 6); }       \
-        else if ((D) <= 256) { CALL(8, 8); }       \
+        else if ((D) <= 128) { CALL(16, 2); }      \
+        else if ((D) <= 192) { CALL(16, 3); }      \
+        else if ((D) <= 256) { CALL(16, 4); }      \
         else if ((D) <= 384) { CALL(16, 6); }      \
         else { CALL(16, 8); }                      \
     } while (0)
@@ -506,15 +505,22 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
         bool valid;
         const size_t col = tile_col(tile, valid);
         // shortlist headers of this warp's frames, requested early so their latency hides behind the tile fetch
-        int cnt_r[ITER], k0_r[ITER];
+        int cnt_r[ITER];
+        uint4 cl_lo[ITER], cl_hi[ITER];           // the frame's whole shortlist row (16 x uint16), or the final code in .x
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int64_t n = tile * TL_F + warp * (TL_F / 8) + it * FPW + sub;
             cnt_r[it] = 0;
-            k0_r[it] = 0;
+            cl_lo[it] = make_uint4(0u, 0u, 0u, 0u);
+            cl_hi[it] = make_uint4(0u, 0u, 0u, 0u);
             if (n < N) {
-                if (idx32) { cnt_r[it] = kCandFinal; k0_r[it] = idx32[n]; }
-                else { cnt_r[it] = cand_cnt[n]; k0_r[it] = cand_idx[(size_t)n * kCandMax]; }
+                if (idx32) { cnt_r[it] = kCandFinal; cl_lo[it].x = (uint32_t)idx32[n]; }
+                else {
+                    cnt_r[it] = cand_cnt[n];
+                    const uint4* row = reinterpret_cast<const uint4*>(cand_idx + (size_t)n * kCandMax);
+                    cl_lo[it] = row[0];
+                    cl_hi[it] = row[1];
+                }
             }
         }
         __syncthreads();                          // the other buffer's previous tile has been stored: it may be refilled
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
                 xv[j] = (d < D) ? *reinterpret_cast<const float4*>(Xs + f * ld + d) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             const int cnt = cnt_r[it];
-            int k = k0_r[it];
+            int k = idx32 ? (int)cl_lo[it].x : (int)(cl_lo[it].x & 0xFFFFu);
             const bool need = live && cnt != kCandFinal && cnt > 1;
             if (__any_sync(0xffffffffu, need)) {
                 // fp32 rescoring of the shortlisted codes in the reference's op order (whole warp takes part in shuffles)
@@ -558,18 +564,35 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
                 int cmax = need ? cnt : 0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-                const uint16_t* cl = cand_idx + (size_t)(live ? n : 0) * kCandMax;
+                // shortlist entry ci out of the prefetched row (registers only: no dependent global load per round)
+                const uint32_t w8[8] = {cl_lo[it].x, cl_lo[it].y, cl_lo[it].z, cl_lo[it].w, cl_hi[it].x, cl_hi[it].y, cl_hi[it].z, cl_hi[it].w};
+                auto entry = [&](int ci) -> int {
+                    const int wi = ci >> 1;
+                    const uint32_t a01 = (wi & 1) ? w8[1] : w8[0], a23 = (wi & 1) ? w8[3] : w8[2];
+                    const uint32_t a45 = (wi & 1) ? w8[5] : w8[4], a67 = (wi & 1) ? w8[7] : w8[6];
+                    const uint32_t lo = (wi & 2) ? a23 : a01, hi = (wi & 2) ? a67 : a45;
+                    const uint32_t wv = (wi & 4) ? hi : lo;
+                    return (int)((ci & 1) ? (wv >> 16) : (wv & 0xFFFFu));
+                };
                 float bd = 0.f;
                 int bk = -1;
+                // rounds are software-pipelined: the codeword of round ci+1 is in flight while round ci is reduced
+                float4 ev[J], en[J];
+                int kc = (need && 0 < cnt) ? entry(0) : 0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int d = 4 * sl + 4 * LPF * j;
+                    ev[j] = (d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kc * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 for (int ci = 0; ci < cmax; ++ci) {
                     const bool act = need && ci < cnt;
-                    const int kc = act ? (int)cl[ci] : 0;
-                    const float* er = E + (size_t)kc * D;
-                    float4 ev[J];
+                    const int kn = (need && ci + 1 < cnt) ? entry(ci + 1) : 0;
+                    if (ci + 1 < cmax) {
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        const int d = 4 * sl + 4 * LPF * j;
-                        ev[j] = (d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = 0; j < J; ++j) {
+                            const int d = 4 * sl + 4 * LPF * j;
+                            en[j] = (d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kn * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
                     float dot = 0.f;
 #pragma unroll
@@ -584,6 +607,9 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
                         const float dist = ref_distance(x2, e2[kc], dot);
                         if (better(dist, kc, bd, bk)) { bd = dist; bk = kc; }
                     }
+                    kc = kn;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) ev[j] = en[j];
                 }
                 if (need) {
                     k = bk;
