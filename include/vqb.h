@@ -99,6 +99,12 @@ VQB_API int vqb_gather(const float* codebook, const int64_t* idx, int B, int D, 
 VQB_API int vqb_window_indices(const int64_t* idx, int B, int64_t L, int window, int64_t pad_id,
                        int64_t* tokens_out, float* mask_out, void* stream);
 
+/* EXTENSION, not in the reference (its codebook is trained by Adam, vqvae.py:168-171): exponential-moving-average codebook
+ * update from the same statistics buffer (needs VQB_WANT_RESID).  cluster_size is [K + 1] (slot K receives the running
+ * total), embed_sum is [K, D]; both are state owned by the caller, codebook is updated in place. */
+VQB_API int vqb_ema_update(const float* stats, float* codebook, float* cluster_size, float* embed_sum, int K, int D,
+                           float decay, float eps, void* stream);
+
 /* Host-buffer convenience used for end-to-end timing and by non-torch callers: copies z (pinned or pageable HOST
  * memory) to the device in chunks overlapped with compute, runs vqb_forward per chunk of whole batch items and
  * copies indices (and stats) back.  Allocates its own device scratch on first use (freed by vqb_host_release). */

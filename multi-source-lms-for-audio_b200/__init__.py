@@ -5,6 +5,9 @@ Only the hot path lives here: `csrc/` (CUDA kernels + C ABI -> l
 """
 from ._lib import LIB_PATH, VqbError
 from .quantizer import VectorQuantizer
-from . import functional, distributed
+from .vqvae_step import VQVAEStep
+from .index_export import Quantize, export_windows
+from . import functional, distributed, codebook_io
 
-__all__ = ["VectorQuantizer", "functional", "distributed", "LIB_PATH", "VqbError"]
+__all__ = ["VectorQuantizer", "VQVAEStep", "Quantize", "export_windows", "functional", "distributed", "codebook_io", "LIB_PATH",
+           "VqbError"]

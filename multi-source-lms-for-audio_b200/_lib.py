@@ -27,6 +27,7 @@ _SIGNATURES = {
     "vqb_finalize": (C.c_int, [_c_f32p, C.c_int, C.c_int, C.c_float, _c_f32p, C.c_void_p]),
     "vqb_backward": (C.c_int, [_c_f32p, _c_f32p, C.c_void_p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, C.c_float, C.c_int, C.c_int,
                                C.c_int64, C.c_int, _c_f32p, _c_f32p, C.c_void_p]),
+    "vqb_ema_update": (C.c_int, [_c_f32p, _c_f32p, _c_f32p, _c_f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "vqb_onehot": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _c_f32p, C.c_void_p]),
     "vqb_gather": (C.c_int, [_c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, _c_f32p, C.c_void_p]),
     "vqb_window_indices": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_void_p, _c_f32p, C.c_void_p]),

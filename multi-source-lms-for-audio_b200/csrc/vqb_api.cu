@@ -220,6 +220,16 @@ int vqb_backward(const float* z_bcw, const float* codebook, const int64_t* idx, 
     return 0;
 }
 
+int vqb_ema_update(const float* stats, float* codebook, float* cluster_size, float* embed_sum, int K, int D, float decay, float eps,
+                   void* stream) {
+    int rc;
+    if ((rc = check_device()) != 0) return rc;
+    if (!stats || !codebook || !cluster_size || !embed_sum) { set_error("vqb_ema_update: NULL pointer argument"); return VQB_E_NULL; }
+    if (K < 1 || D < 1 || !(decay >= 0.f && decay <= 1.f)) { set_error("vqb_ema_update: bad K/D/decay"); return VQB_E_SHAPE; }
+    VQB_CUDA(launch_ema_update(stats, codebook, cluster_size, embed_sum, K, D, decay, eps, static_cast<cudaStream_t>(stream)), "ema_update");
+    return 0;
+}
+
 int vqb_onehot(const int64_t* idx, int64_t N, int K, float* encodings_out, void* stream) {
     int rc;
     if ((rc = check_device()) != 0) return rc;

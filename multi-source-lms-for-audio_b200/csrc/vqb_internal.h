@@ -61,6 +61,8 @@ cudaError_t launch_finalize(const float* stats, int K, int D, float beta, float*
 cudaError_t launch_backward_dx(const float* z, const float* codebook, const int64_t* idx, const float* Gq, const float* g_c,
                                float beta, int B, int D, int64_t W, int K, float* dX, cudaStream_t s);
 cudaError_t launch_backward_de(const float* stats, const float* g_e, int K, int D, float* dE, cudaStream_t s);
+cudaError_t launch_ema_update(const float* stats, float* codebook, float* cluster_size, float* embed_sum, int K, int D, float decay,
+                              float eps, cudaStream_t s);
 cudaError_t launch_onehot(const int64_t* idx, int64_t N, int K, float* out, cudaStream_t s);
 cudaError_t launch_gather(const float* codebook, const int64_t* idx, int B, int D, int64_t W, int K, float* out, cudaStream_t s);
 cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int64_t pad_id, int64_t* tokens, float* mask,

@@ -890,6 +890,55 @@ cudaError_t launch_backward_de(const float* stats, const float* g_e, int K, int 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ EMA codebook (extension)
+// Exponential-moving-average codebook update from the SAME statistics buffer (not in the reference, which trains the codebook
+// with Adam; off by default - SURVEY.md row f4):
+//   cluster_size <- g * cluster_size + (1-g) * counts ;  embed_sum <- g * embed_sum + (1-g) * (resid + counts * e)
+//   e_k <- embed_sum_k / ((cluster_size_k + eps) / (n + K eps) * n),  n = sum_k cluster_size_k
+__global__ void __launch_bounds__(1024) ema_cluster_kernel(const float* __restrict__ stats, float* __restrict__ cluster_size, int K,
+                                                           float decay) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < K; k += 1024) {
+        const float c = decay * cluster_size[k] + (1.f - decay) * stats[k];
+        cluster_size[k] = c;
+        s += (double)c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += red[i];
+        cluster_size[K] = (float)t;
+    }
+}
+__global__ void __launch_bounds__(256) ema_codebook_kernel(const float* __restrict__ stats, const float* __restrict__ cluster_size,
+                                                           float* __restrict__ embed_sum, float* __restrict__ E, int K, int D,
+                                                           float decay, float eps) {
+    const size_t total = (size_t)K * D;
+    const float n = cluster_size[K];
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int k = (int)(i / D);
+        const float sumx = stats[K + i] + stats[k] * E[i];                 // sum of the frames assigned to code k
+        const float m = decay * embed_sum[i] + (1.f - decay) * sumx;
+        embed_sum[i] = m;
+        E[i] = m / ((cluster_size[k] + eps) / (n + (float)K * eps) * n);
+    }
+}
+
+cudaError_t launch_ema_update(const float* stats, float* codebook, float* cluster_size, float* embed_sum, int K, int D, float decay,
+                              float eps, cudaStream_t s) {
+    ema_cluster_kernel<<<1, 1024, 0, s>>>(stats, cluster_size, K, decay);
+    const size_t total = (size_t)K * D;
+    size_t grid = (total + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    ema_codebook_kernel<<<(unsigned)grid, 256, 0, s>>>(stats, cluster_size, embed_sum, codebook, K, D, decay, eps);
+    note_launch(2);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ one-hot / gather / windows
 __global__ void __launch_bounds__(256) onehot_kernel(const int64_t* __restrict__ idx, int64_t N, int K, float* __restrict__ out) {
     const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;

@@ -112,6 +112,22 @@ def vq_backward(z: torch.Tensor, codebook: torch.Tensor, idx: torch.Tensor, stat
     return dX, dE
 
 
+def ema_update(stats: torch.Tensor, codebook: torch.Tensor, cluster_size: torch.Tensor, embed_sum: torch.Tensor, decay: float = 0.99,
+               eps: float = 1e-5) -> None:
+    """EXTENSION (not in the reference): in-place EMA codebook update from a statistics buffer produced with want_resid=True.
+    cluster_size is [K + 1] fp32 state (slot K = running total), embed_sum [K, D] fp32 state."""
+    for name, t in (("stats", stats), ("codebook", codebook), ("cluster_size", cluster_size), ("embed_sum", embed_sum)):
+        _require_cuda(name, t, torch.float32)
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+    K, D = codebook.shape
+    if cluster_size.numel() != K + 1 or embed_sum.shape != codebook.shape or stats.numel() != L.stats_len(K, D):
+        raise ValueError("ema_update: shape mismatch")
+    with torch.cuda.device(codebook.device):
+        L.check("vqb_ema_update", L.lib().vqb_ema_update(stats.data_ptr(), codebook.data_ptr(), cluster_size.data_ptr(), embed_sum.data_ptr(),
+                                                         K, D, float(decay), float(eps), _stream_ptr(codebook.device)))
+
+
 def onehot(idx: torch.Tensor, K: int) -> torch.Tensor:
     """Dense `encodings` [N, K] fp32 (vector_quantizer.py:38-39)."""
     _require_cuda("idx", idx, torch.int64)

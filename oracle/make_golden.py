@@ -133,5 +133,48 @@ def main():
     run_case(VQ, "small_norm_k256_d64", seeded(9, (4, 64, 129), 0.05), seeded(10, (256, 64), 0.02), 256, 64, 0.5)
 
 
+def vqvae_case():
+    """BASELINE config 1 in miniature: the reference's Encoder / 1x1 conv / VectorQuantizer / Decoder wired as
+    src/model/vqvae.py:39-53,81-86 with the stage-1 loss of vqvae.py:59-66, seeded weights, batch 2."""
+    sys.path.insert(0, REF)
+    from src.model.components.encoder import Encoder
+    from src.model.components.decoder import Decoder
+    from src.model.components.vector_quantizer import VectorQuantizer
+    from torch import nn
+    import torch.nn.functional as F
+    torch.manual_seed(2024)
+    enc = Encoder(in_channel=4, num_hidden=128, num_residual_layer=2, num_residual_hidden=32)
+    conv = nn.Conv1d(128, 64, kernel_size=1, stride=1)
+    vq = VectorQuantizer(num_embedding=512, embedding_dim=64, commitment_cost=0.25)
+    dec = Decoder(in_channel=64, num_hidden=128, num_residual_layer=2, num_residual_hidden=32)
+    instruments = torch.from_numpy(seeded(11, (2, 4, 4096), 0.1))
+    mixed = instruments.sum(dim=1, keepdim=True).expand(-1, 4, -1).contiguous()      # intent of datamodule.py:118-119
+    with torch.no_grad():                          # codewords drawn from the latents themselves, so that many codes are in use
+        z0 = conv(enc(mixed)).permute(0, 2, 1).reshape(-1, 64)
+        pick = torch.randperm(z0.shape[0], generator=torch.Generator().manual_seed(5))[:512]
+        vq.codebook.weight.copy_(z0[pick] + 0.002 * torch.randn(512, 64, generator=torch.Generator().manual_seed(6)))
+    z = conv(enc(mixed))
+    emb, com, q, ppl, _, idx = vq(z)
+    out = dec(q)
+    loss = emb + com
+    for i in range(4):
+        loss = loss + F.l1_loss(out[:, i, :], instruments[:, i, :])
+    loss.backward()
+    state = {}
+    for prefix, mod in (("encoder.", enc), ("conv.", conv), ("vector_quantizer.", vq), ("decoder.", dec)):
+        for k, v in mod.state_dict().items():
+            state["sd:" + prefix + k] = v.detach().numpy()
+    margin, _ = reference_margins(z.detach(), vq.codebook.weight.detach())
+    path = os.path.join(OUT, "vqvae_step", "vqvae_step_b2_t4096.npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez_compressed(path, instruments=instruments.numpy(), z=z.detach().numpy(), output=out.detach().numpy(),
+                        loss=loss.detach().numpy(), embedding_loss=emb.detach().numpy(), perplexity=ppl.detach().numpy(),
+                        indices=idx.reshape(-1).numpy().astype(np.int32), margin=margin.astype(np.float32),
+                        grad_conv_weight=conv.weight.grad.numpy(), grad_codebook=vq.codebook.weight.grad.numpy(), **state)
+    print(f"vqvae_step: loss={float(loss.detach()):.6g} ppl={float(ppl):.4g} unique codes={idx.unique().numel()} "
+          f"-> {os.path.getsize(path)/1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     main()
+    vqvae_case()
