@@ -271,6 +271,13 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 // One 32-column slab of accumulators (= -score/2) for this thread's frame: a pure running arg-max.
 // Fast path per slab: 16 FMNMX3 + one compare.  When the slab maximum is within the band of the running maximum, the
 // four 8-code chunks are appended under predicates (straight-line code) and the threshold tightens.
+__device__ __forceinline__ float slab_max32(const uint32_t (&r)[32]) {
+    float m = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
+#pragma unroll
+    for (int j = 3; j < 31; j += 2) m = fmaxf(fmaxf(m, __uint_as_float(r[j])), __uint_as_float(r[j + 1]));
+    return fmaxf(m, __uint_as_float(r[31]));
+}
+
 // The four threads that share a frame (one per column quarter, in four different warps) pool their running maximum in
 // shared memory (`smax`): every thread's threshold tracks the best score ANY quarter has seen, which cuts the number of
 // appended chunks per frame from 4 x ln(K/32) to ln(K/8)-ish.
@@ -525,6 +532,19 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t taddr = tmem_base + t_lane + as * BN + colq * COLS_PER_WARP;
                 const int code0 = nt * BN + colq * COLS_PER_WARP;
                 uint32_t ra[32];
+                if (nt == 0 && !scores_dbg) {
+                    // First codebook tile of a frame tile: the threshold is still -inf and everything would be appended.  Take
+                    // the tile's maximum first (the accumulator stays in TMEM), then scan it with a tight threshold.
+                    float pre = -INFINITY;
+#pragma unroll
+                    for (int sb = 0; sb < COLS_PER_WARP / 32; ++sb) {
+                        tmem_ld32(taddr + sb * 32, ra);
+                        tmem_ld_wait(ra);
+                        pre = fmaxf(pre, slab_max32(ra));
+                    }
+                    thr = fmaxf(thr, pre - hband);
+                    atomicMax(smax, f2ord(pre));
+                }
 #pragma unroll
                 for (int sb = 0; sb < COLS_PER_WARP / 32; ++sb) {
                     tmem_ld32(taddr + sb * 32, ra);
