@@ -285,3 +285,39 @@ def test_full_size_properties(B, D, W, K):
     sub = np.ascontiguousarray(rows.T[None])           # [1, D, 2048]
     ref = O.vq_forward(sub, cb.cpu().numpy(), 0.25)
     assert_index_parity(idx_b.cpu().numpy()[pick], sub, cb.cpu().numpy(), ref.indices, ref.margin, ref.eps)
+
+
+def test_forward_backward_are_cuda_graph_capturable():
+    """The C ABI only enqueues work on the caller's stream (no host sync, no hidden streams): a forward + backward captured
+    in a CUDA graph replays to the same results on new data."""
+    B, D, W, K = 4, 64, 2048, 512
+    g = torch.Generator(device=DEV).manual_seed(5)
+    cb = torch.randn(K, D, device=DEV, generator=g)
+    z = torch.randn(B, D, W, device=DEV, generator=g)
+    Gq = torch.randn(B, D, W, device=DEV, generator=g)
+    one = torch.ones((), device=DEV)
+    stats = torch.empty(_lib.stats_len(K, D), device=DEV)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):                                   # warm-up on the capture stream (workspace + attribute setup)
+            idx, q, st = F.vq_forward(z, cb, precision="bf16", want_q=True, want_resid=True, stats=stats)
+            F.vq_backward(z, cb, idx, st, Gq, one, one, 0.25)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        idx, q, st = F.vq_forward(z, cb, precision="bf16", want_q=True, want_resid=True, stats=stats)
+        losses = F.vq_finalize(st, K, D, 0.25)
+        dX, dE = F.vq_backward(z, cb, idx, st, Gq, one, one, 0.25)
+    z2 = torch.randn(B, D, W, device=DEV, generator=g)
+    z.copy_(z2)                                              # new data in the captured input buffer
+    graph.replay()
+    torch.cuda.synchronize()
+    got = (idx.clone(), q.clone(), losses.clone(), dX.clone(), dE.clone())
+    idx_e, q_e, st_e = F.vq_forward(z2, cb, precision="bf16", want_q=True, want_resid=True)
+    losses_e = F.vq_finalize(st_e, K, D, 0.25)
+    dX_e, dE_e = F.vq_backward(z2, cb, idx_e, st_e, Gq, one, one, 0.25)
+    assert torch.equal(got[0], idx_e) and torch.equal(got[1], q_e)
+    torch.testing.assert_close(got[2], losses_e, rtol=1e-6, atol=0)
+    assert torch.equal(got[3], dX_e)
+    torch.testing.assert_close(got[4], dE_e, rtol=1e-4, atol=1e-7)
