@@ -153,8 +153,9 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + L.xb);
         __nv_bfloat16* eh = reinterpret_cast<__nv_bfloat16*>(ws + L.eh);
         VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, eb, eh, meta, s), "codebook_prep");
-        VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");
-        rc = launch_tc_search(xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, best64, scores_dbg, ws + L.ev, s);
+        const bool fuse = tc_can_fuse(z, B, D, W);
+        if (!fuse) VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");
+        rc = launch_tc_search(fuse ? z : nullptr, B, W, xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, best64, scores_dbg, ws + L.ev, s);
         if (rc != 0) return rc;
         if (scores_dbg) return 0;
         VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, fb_rows, &meta->fallback_count, nullptr, cand_cnt, cand_idx, best64, s),

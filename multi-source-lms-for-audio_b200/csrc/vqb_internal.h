@@ -70,7 +70,10 @@ cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int6
 
 // ---- tensor-core search (vqb_tc.cu) ---------------------------------------------------------------------------
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.
-int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh, const float* band, int64_t N, int64_t N_pad,
+bool tc_can_fuse(const float* z, int B, int D, int64_t W);   // can the tensor-core kernel read the fp32 [B, D, W] latents itself?
+// z_fused != nullptr: fused operand preparation (xb / band unused); else xb / band from latent_prep_bf16_kernel
+int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh,
+                     const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
                      unsigned long long* best64, float* scores_dbg, void* ev_scratch, cudaStream_t s);
 

@@ -39,6 +39,10 @@ constexpr int EH_SLICE_BYTES = BN * 16;      // 4 KiB: (h1,h2,h3,0,0,0,0,0) bf16
 constexpr int EH_SLOTS = 2;
 constexpr int AX_BYTES = BM * 16;            // 2 KiB: K-half 0 of the constant A operand
 constexpr int ZERO_BYTES = EH_SLICE_BYTES;   // shared all-zero K-half 1 of both bias operands
+// fused operand preparation: fp32 latents arrive straight from the reference's [B, D, W] layout as 3-D TMA boxes of
+// 16 dims x 128 frames (8 KiB) and are converted to the bf16 K-major swizzled A tile inside the kernel
+constexpr int SUB_DIMS = 16, STG_SLOTS = 4, STG_BYTES = SUB_DIMS * BM * 4;
+constexpr int CONVERT_WARP = 18, ALOAD_WARP = 19;
 constexpr int MAX_A_SLOTS = 8, MAX_B_STAGES = 8;   // 4 whole-tile stages (1-CTA) or 8 half-tile stages (2-CTA)
 constexpr int EPI_WARP0 = 0, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;   // 4 warps per TMEM lane quarter: 64 columns each
 // The single-thread producer / MMA loops sit in the HIGHEST warp ids: the scheduler favours them over waiting epilogue warps.
@@ -51,6 +55,7 @@ struct Barriers {
     unsigned long long b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
     unsigned long long a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
     unsigned long long eh_full[EH_SLOTS], eh_empty[EH_SLOTS], tmem_full[2], tmem_empty[2];
+    unsigned long long stg_full[STG_SLOTS], stg_empty[STG_SLOTS];
     unsigned int tmem_base;
     unsigned int pad;
 };
@@ -115,6 +120,12 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 // 2-CTA (cta_group::2) variants.  The pair's leader (cluster rank 0) owns the "full" barriers: both CTAs' TMA loads
@@ -310,10 +321,15 @@ __device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], int code0, in
 // kTwo = false: cta_group::1 MMAs, every CTA holds whole codebook tiles (optionally multicast inside a cluster).
 // kTwo = true : CTA pairs with cta_group::2 MMAs (M = 256 over the pair): each CTA holds its own 128 frames and HALF of every
 //               codebook tile (128 codes), which halves the per-SM operand ingest and doubles the ring depth (8 stages).
-template <bool kTwo>
+// kFuse = true : the A operand is built in the kernel from the fp32 [B, D, W] latents (tmap_x is then a 3-D fp32 map):
+//               warp 19 streams 16-dim x 128-frame boxes through a small ring, warp 18 converts them to bf16 into the
+//               swizzled A chunks, measures |x| and |x - bf16(x)| per frame and publishes the guard band in shared memory.
+//               Frame tiles then never straddle a batch item (tile = (b, w0 .. w0+127)); no bf16 copy of the latents exists.
+template <bool kTwo, bool kFuse>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
-                 const __grid_constant__ CUtensorMap tmap_eh, const __nv_bfloat16* __restrict__ eh, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
+                 const __grid_constant__ CUtensorMap tmap_eh, const __nv_bfloat16* __restrict__ eh, int64_t W, int tiles_per_item, int D,
+                 const WsMeta* __restrict__ meta_ro, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch) {
@@ -323,7 +339,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     unsigned char* sEH = sB + (size_t)b_stages * (kTwo ? B_STAGE_BYTES / 2 : B_STAGE_BYTES);   // EH_SLOTS x 4 KiB bias operand B (K-half 0)
     unsigned char* sAX = sEH + EH_SLOTS * EH_SLICE_BYTES;                // 2 KiB constant bias operand A (K-half 0)
     unsigned char* sZero = sAX + AX_BYTES;                               // 4 KiB of zeros: K-half 1 of both bias operands
-    float* sMin = reinterpret_cast<float*>(sZero + ZERO_BYTES);          // [4][128] running maxima of the four column quarters
+    unsigned char* sStg = sZero + ZERO_BYTES;                            // fused mode: STG_SLOTS x 8 KiB fp32 boxes [16 dims][128 frames]
+    float* sBand = reinterpret_cast<float*>(sStg + (kFuse ? STG_SLOTS * STG_BYTES : 0));   // fused mode: [2][128] guard bands
+    float* sMin = sBand + (kFuse ? 2 * BM : 0);                          // [4][128] running maxima of the four column quarters
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
     Barriers* bars = reinterpret_cast<Barriers*>(sCnt + 3 * BM);        // [128] pooled running maximum per frame (ordered int)
 
@@ -347,7 +365,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     if (warp == MMA_WARP && lane == 0) {
         for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), kTwo ? 1 : cs); }
-        for (int i = 0; i < a_slots; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+        for (int i = 0; i < a_slots; ++i) {
+            mbar_init(smem_u32(&bars->a_full[i]), (kFuse && kTwo) ? 2 : 1);   // fused 2-CTA: both CTAs' converters report to the leader
+            mbar_init(smem_u32(&bars->a_empty[i]), 1);
+        }
+        for (int i = 0; i < STG_SLOTS; ++i) { mbar_init(smem_u32(&bars->stg_full[i]), 1); mbar_init(smem_u32(&bars->stg_empty[i]), 1); }
         for (int i = 0; i < EH_SLOTS; ++i) {
             mbar_init(smem_u32(&bars->eh_full[i]), 1);
             mbar_init(smem_u32(&bars->eh_empty[i]), 1);
@@ -402,10 +424,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (++es == EH_SLOTS) { es = 0; e_ph ^= 1; }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const uint32_t slot = a_slot0 + kb;
-                    if (nt == 0) mbar_wait(bar_aempty + slot * 8, a_ph ^ 1);
+                    if (nt == 0 && !kFuse) mbar_wait(bar_aempty + slot * 8, a_ph ^ 1);
                     mbar_wait(bar_bempty + b_st * 8, b_ph ^ 1);
                     if (elect_one()) {
-                        if (nt == 0) {
+                        if (nt == 0 && !kFuse) {
                             if (kTwo) {
                                 if (leader) mbar_expect_tx(bar_afull + slot * 8, 2 * A_CHUNK_BYTES);
                                 tma_load_2d_2sm(sA_u + slot * A_CHUNK_BYTES, &tmap_x, bar_afull + slot * 8, kb * BK, a_row);
@@ -502,6 +524,104 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             a_slot0 += num_kb;
             if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
         }
+    } else if (kFuse && warp == ALOAD_WARP) {
+        // ================================================================ latent loader (fused mode): fp32 boxes -> staging ring
+        const int num_sub = D / SUB_DIMS;
+        uint32_t sg = 0, sg_ph = 0;
+        const uint32_t bar_sfull = smem_u32(&bars->stg_full[0]), bar_sempty = smem_u32(&bars->stg_empty[0]), sS_u = smem_u32(sStg);
+        for (int rd = 0; rd < rounds; ++rd) {
+            int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;
+            if (mt >= num_m_tiles) mt = 0;                                     // dummy tile: re-read tile 0, nothing is published
+            const int b = mt / tiles_per_item, w0 = (mt - b * tiles_per_item) * BM;
+            for (int sub = 0; sub < num_sub; ++sub) {
+                mbar_wait(bar_sempty + sg * 8, sg_ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_sfull + sg * 8, STG_BYTES);
+                    tma_load_3d(sS_u + sg * STG_BYTES, &tmap_x, bar_sfull + sg * 8, w0, sub * SUB_DIMS, b);   // frames past W arrive as zeros
+                }
+                __syncwarp();
+                if (++sg == STG_SLOTS) { sg = 0; sg_ph ^= 1; }
+            }
+        }
+    } else if (kFuse && warp == CONVERT_WARP) {
+        // ================================================================ converter (fused mode): staging -> bf16 swizzled A chunks
+        // lane t owns frames 4t .. 4t+3 of the tile
+        const int num_sub = D / SUB_DIMS;
+        uint32_t sg = 0, sg_ph = 0, a_slot0 = 0, a_ph = 0;
+        const uint32_t bar_sfull = smem_u32(&bars->stg_full[0]), bar_sempty = smem_u32(&bars->stg_empty[0]);
+        const uint32_t bar_afull = smem_u32(&bars->a_full[0]), bar_aempty = smem_u32(&bars->a_empty[0]);
+        const float etmax = sqrtf(__uint_as_float(meta_ro->etmax2_bits)) * 1.0001f;
+        const float demax = sqrtf(__uint_as_float(meta_ro->demax2_bits)) * 1.0001f;
+        const float emax = sqrtf(__uint_as_float(meta_ro->emax2_bits)) * 1.0001f;
+        for (int rd = 0; rd < rounds; ++rd) {
+            float s2[4] = {0.f, 0.f, 0.f, 0.f}, sd2[4] = {0.f, 0.f, 0.f, 0.f};   // |x|^2 and |x - bf16(x)|^2 of the 4 frames
+            int sub = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const uint32_t slot = a_slot0 + kb;
+                mbar_wait(bar_aempty + slot * 8, a_ph ^ 1);                      // the previous tile's MMAs are done with this chunk
+                unsigned char* chunk = sA + (size_t)slot * A_CHUNK_BYTES;
+                for (int q = 0; q < BK / SUB_DIMS; ++q, ++sub) {
+                    if (sub < num_sub) {
+                        mbar_wait(bar_sfull + sg * 8, sg_ph);
+                        const float* stg = reinterpret_cast<const float*>(sStg + (size_t)sg * STG_BYTES);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {                             // two 16-byte units (8 dims) per sub-chunk
+                            float4 v[8];
+#pragma unroll
+                            for (int d = 0; d < 8; ++d) v[d] = *reinterpret_cast<const float4*>(stg + (h * 8 + d) * BM + 4 * lane);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float x[8];
+#pragma unroll
+                                for (int d = 0; d < 8; ++d) x[d] = i == 0 ? v[d].x : (i == 1 ? v[d].y : (i == 2 ? v[d].z : v[d].w));
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int d = 0; d < 4; ++d) {
+                                    const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * d], x[2 * d + 1]);
+                                    const float2 bk = __bfloat1622float2(hb);
+                                    const float e0 = x[2 * d] - bk.x, e1 = x[2 * d + 1] - bk.y;
+                                    s2[i] = fmaf(x[2 * d], x[2 * d], s2[i]);
+                                    s2[i] = fmaf(x[2 * d + 1], x[2 * d + 1], s2[i]);
+                                    sd2[i] = fmaf(e0, e0, sd2[i]);
+                                    sd2[i] = fmaf(e1, e1, sd2[i]);
+                                    pk[d] = *reinterpret_cast<const uint32_t*>(&hb);
+                                }
+                                const int r = 4 * lane + i, u = 2 * q + h;
+                                *reinterpret_cast<uint4*>(chunk + (r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4)) =
+                                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_sempty + sg * 8);
+                        if (++sg == STG_SLOTS) { sg = 0; sg_ph ^= 1; }
+                    } else {                                                      // D % 64 != 0: the rest of the last chunk is zero
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = 4 * lane + i, u = 2 * q + h;
+                                *reinterpret_cast<uint4*>(chunk + (r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                            }
+                    }
+                }
+                if (kb == num_kb - 1) {                                           // guard band of this tile's frames (see latent_prep_bf16_kernel)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float xn = sqrtf(s2[i]) * 1.0001f, dxn = sqrtf(sd2[i]) * 1.0001f;
+                        sBand[(rd & 1) * BM + 4 * lane + i] = 4.0f * (dxn * etmax + xn * demax) * 1.001f +
+                                                              8.0f * (float)(D + 16) * 2.3841858e-07f * xn * emax + 4.0e-7f * emax * emax + 1e-30f;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) {
+                    if (kTwo && crank != 0) mbar_arrive_remote(bar_afull + slot * 8, 0);
+                    else mbar_arrive(bar_afull + slot * 8);
+                }
+            }
+            a_slot0 += num_kb;
+            if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
+        }
     } else if (warp < EPI_WARPS) {
         // ================================================================ epilogue
         const int ew = warp - EPI_WARP0;
@@ -520,15 +640,26 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         uint32_t n_it = 0;
         for (int rd = 0; rd < rounds; ++rd) {
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
-            const int64_t row = (int64_t)mt * BM + row_in_tile;
-            const float band = (row < N) ? band_g[row] : 0.f;
-            const float hband = 0.5f * band;              // the band in accumulator units (acc = -score / 2)
+            int64_t row;                                  // global frame index n = b*W + w, or N when this lane has no frame
+            if (kFuse) {
+                const int b = mt / tiles_per_item;
+                const int64_t w = (int64_t)(mt - b * tiles_per_item) * BM + row_in_tile;
+                row = (mt < num_m_tiles && w < W) ? (int64_t)b * W + w : N;
+            } else {
+                row = (int64_t)mt * BM + row_in_tile;
+            }
+            float band = (!kFuse && row < N) ? band_g[row] : 0.f;
+            float hband = 0.5f * band;                    // the band in accumulator units (acc = -score / 2)
             float thr = -INFINITY;
             ev.n = 0;
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1;
                 mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
                 tc_fence_after();
+                if (kFuse && nt == 0) {                   // the converter published this tile's bands before the first MMA could start
+                    band = sBand[(rd & 1) * BM + row_in_tile];
+                    hband = 0.5f * band;
+                }
                 const uint32_t taddr = tmem_base + t_lane + as * BN + colq * COLS_PER_WARP;
                 const int code0 = nt * BN + colq * COLS_PER_WARP;
                 uint32_t ra[32];
@@ -675,7 +806,29 @@ static int make_map_eh(CUtensorMap* map, const void* base, uint64_t rows) {
     return 0;
 }
 
+// fp32 latents in the reference's [B, D, W] layout: box = 128 frames x 16 dims of one batch item, zero fill past W
+static int make_map_z(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VQB_E_DEVICE; }
+    const cuuint64_t dims[3] = {W, D, B};
+    const cuuint64_t strides[2] = {W * 4, D * W * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)BM, (cuuint32_t)SUB_DIMS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(z), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(z) failed with CUresult %d", (int)r); return 1000 + (int)r; }
+    return 0;
+}
+
 }  // namespace tc
+
+bool tc_can_fuse(const float* z, int B, int D, int64_t W) {
+    (void)B;
+    if (const char* env = getenv("VQB_TC_FUSE")) if (env[0] == '0') return false;
+    // 3-D TMA needs 16-byte global strides; short clips would waste most of every 128-frame tile on padding
+    return (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (D % tc::SUB_DIMS) == 0 && (W % 128 == 0 || W >= 1024);
+}
 
 size_t tc_event_scratch_bytes() { return (size_t)kTcMaxCtas * tc::EPI_THREADS * tc::EV_CAP * tc::EV_WORDS * 4; }
 
@@ -700,20 +853,25 @@ static void timing_end(TimingSlot* t, cudaStream_t s) {
     if (t) cudaEventRecord(t->stop, s);
 }
 
-int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh, const float* band, int64_t N, int64_t N_pad,
-                     int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
-                     unsigned long long* best64, float* scores_dbg, void* ev_scratch, cudaStream_t s) {
+int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh,
+                     const float* band, int64_t N, int64_t N_pad, int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx,
+                     int* fallback_rows, WsMeta* meta, unsigned long long* best64, float* scores_dbg, void* ev_scratch,
+                     cudaStream_t s) {
     using namespace tc;
+    const bool fuse = z_fused != nullptr;          // the caller decided with tc_can_fuse(): A operand built in-kernel from fp32 BCW
     CUtensorMap mx;
     int rc;
-    if ((rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM)) != 0) return rc;
+    if (fuse) rc = make_map_z(&mx, z_fused, (uint64_t)B, (uint64_t)D, (uint64_t)W);
+    else rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM);
+    if (rc != 0) return rc;
+    const int tiles_per_item = (int)((W + BM - 1) / BM);
     const int num_kb = (D + BK - 1) / BK;
     const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > kTcMaxCtas) sms = kTcMaxCtas;
-    const int num_m_tiles = (int)(N_pad / BM);
+    const int num_m_tiles = fuse ? B * tiles_per_item : (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
     // default: CTA pairs with cta_group::2 MMAs; VQB_TC_MODE=1: cta_group::1 with VQB_TC_CLUSTER-way codebook multicast
     bool two = true;
@@ -724,15 +882,18 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __n
     if (two) cs = 2;
     if (num_m_tiles < 2 * cs) { cs = 1; two = false; }
     const size_t stage_bytes = two ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 + sizeof(Barriers) + 1024;
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
+                         (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) + sizeof(Barriers) + 1024;
     int b_stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (b_stages > (two ? 8 : 4)) b_stages = two ? 8 : 4;
     if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
     const size_t smem = fixed + (size_t)b_stages * stage_bytes;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_search_kernel)");
         attr_done = true;
     }
@@ -755,12 +916,15 @@ int launch_tc_search(const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __n
     cfg.numAttrs = 1;
     TimingSlot* slot = timing_begin(s);
     cudaError_t le;
-    if (two)
-        le = cudaLaunchKernelEx(&cfg, tc_search_kernel<true>, mx, me_c, meh, eh, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages,
-                                cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
-    else
-        le = cudaLaunchKernelEx(&cfg, tc_search_kernel<false>, mx, me_c, meh, eh, band, N, num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages,
-                                cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64, scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch));
+#define VQB_TC_LAUNCH(TWO, FUSE)                                                                                                       \
+    le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE>, mx, me_c, meh, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
+                            num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,  \
+                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch))
+    if (two && fuse) VQB_TC_LAUNCH(true, true);
+    else if (two) VQB_TC_LAUNCH(true, false);
+    else if (fuse) VQB_TC_LAUNCH(false, true);
+    else VQB_TC_LAUNCH(false, false);
+#undef VQB_TC_LAUNCH
     if (le != cudaSuccess) return cuda_fail(le, "tc_search_kernel launch");
     cudaError_t e = cudaGetLastError();
     timing_end(slot, s);
