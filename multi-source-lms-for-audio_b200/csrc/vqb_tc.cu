@@ -366,10 +366,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == MMA_WARP && lane == 0) {
         for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), kTwo ? 1 : cs); }
         for (int i = 0; i < a_slots; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), (kFuse && kTwo) ? 2 : 1);   // fused 2-CTA: both CTAs' converters report to the leader
+            mbar_init(smem_u32(&bars->a_full[i]), kFuse ? (kTwo ? 4 : 2) : 1);   // fused: two converter warps per CTA (both CTAs in 2-CTA mode)
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
         }
-        for (int i = 0; i < STG_SLOTS; ++i) { mbar_init(smem_u32(&bars->stg_full[i]), 1); mbar_init(smem_u32(&bars->stg_empty[i]), 1); }
+        for (int i = 0; i < STG_SLOTS; ++i) { mbar_init(smem_u32(&bars->stg_full[i]), 1); mbar_init(smem_u32(&bars->stg_empty[i]), 2); }
         for (int i = 0; i < EH_SLOTS; ++i) {
             mbar_init(smem_u32(&bars->eh_full[i]), 1);
             mbar_init(smem_u32(&bars->eh_empty[i]), 1);
@@ -423,8 +423,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 __syncwarp();
                 if (++es == EH_SLOTS) { es = 0; e_ph ^= 1; }
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const uint32_t slot = a_slot0 + kb;
-                    if (nt == 0 && !kFuse) mbar_wait(bar_aempty + slot * 8, a_ph ^ 1);
+                    uint32_t slot = a_slot0 + kb, a_phk = a_ph;          // ring position of chunk kb of this tile
+                    if (slot >= (uint32_t)a_slots) { slot -= a_slots; a_phk ^= 1; }
+                    if (nt == 0 && !kFuse) mbar_wait(bar_aempty + slot * 8, a_phk ^ 1);
                     mbar_wait(bar_bempty + b_st * 8, b_ph ^ 1);
                     if (elect_one()) {
                         if (nt == 0 && !kFuse) {
@@ -452,7 +453,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
             a_slot0 += num_kb;
-            if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
+            if (a_slot0 >= (uint32_t)a_slots) { a_slot0 -= a_slots; a_ph ^= 1; }
         }
     } else if (warp == MMA_WARP && leader) {
         // ================================================================ MMA issuer (converged warp, one elected lane issues;
@@ -472,8 +473,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t tmem_d = tmem_base + as * BN;
                 const bool last_nt = nt == num_n_tiles - 1;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const uint32_t slot = a_slot0 + kb;
-                    if (nt == 0) mbar_wait(bar_afull + slot * 8, a_ph);
+                    uint32_t slot = a_slot0 + kb, a_phk = a_ph;
+                    if (slot >= (uint32_t)a_slots) { slot -= a_slots; a_phk ^= 1; }
+                    if (nt == 0) mbar_wait(bar_afull + slot * 8, a_phk);
                     mbar_wait(bar_bfull + b_st * 8, b_ph);
                     tc_fence_after();
                     if (elect_one()) {
@@ -522,94 +524,100 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (as == 0) t_ph ^= 1;
             }
             a_slot0 += num_kb;
-            if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
+            if (a_slot0 >= (uint32_t)a_slots) { a_slot0 -= a_slots; a_ph ^= 1; }
         }
-    } else if (kFuse && warp == ALOAD_WARP) {
-        // ================================================================ latent loader (fused mode): fp32 boxes -> staging ring
+    } else if (kFuse && (warp == CONVERT_WARP || warp == ALOAD_WARP)) {
+        // ================================================================ fused operand preparation: two converter warps.
+        // Warp 18 owns frames 0..63 of the tile, warp 19 frames 64..127 (two frames per lane).  Warp 19 is also the loader:
+        // before it touches sub-chunk g it makes sure the TMA loads up to g + STG_SLOTS - 1 are issued.  A load waits only
+        // for BOTH converters to have released its ring slot, so the loader never waits on its own future work.
         const int num_sub = D / SUB_DIMS;
-        uint32_t sg = 0, sg_ph = 0;
+        const int half_row0 = (warp == CONVERT_WARP) ? 0 : BM / 2;
+        const bool is_loader = warp == ALOAD_WARP;
+        const long long total_sub = (long long)rounds * num_sub;
+        long long issued = 0, g = 0;                                             // sub-chunk counters over all tiles of this CTA
+        uint32_t a_slot0 = 0, a_ph = 0;
         const uint32_t bar_sfull = smem_u32(&bars->stg_full[0]), bar_sempty = smem_u32(&bars->stg_empty[0]), sS_u = smem_u32(sStg);
-        for (int rd = 0; rd < rounds; ++rd) {
-            int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;
-            if (mt >= num_m_tiles) mt = 0;                                     // dummy tile: re-read tile 0, nothing is published
-            const int b = mt / tiles_per_item, w0 = (mt - b * tiles_per_item) * BM;
-            for (int sub = 0; sub < num_sub; ++sub) {
-                mbar_wait(bar_sempty + sg * 8, sg_ph ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(bar_sfull + sg * 8, STG_BYTES);
-                    tma_load_3d(sS_u + sg * STG_BYTES, &tmap_x, bar_sfull + sg * 8, w0, sub * SUB_DIMS, b);   // frames past W arrive as zeros
-                }
-                __syncwarp();
-                if (++sg == STG_SLOTS) { sg = 0; sg_ph ^= 1; }
-            }
-        }
-    } else if (kFuse && warp == CONVERT_WARP) {
-        // ================================================================ converter (fused mode): staging -> bf16 swizzled A chunks
-        // lane t owns frames 4t .. 4t+3 of the tile
-        const int num_sub = D / SUB_DIMS;
-        uint32_t sg = 0, sg_ph = 0, a_slot0 = 0, a_ph = 0;
-        const uint32_t bar_sfull = smem_u32(&bars->stg_full[0]), bar_sempty = smem_u32(&bars->stg_empty[0]);
         const uint32_t bar_afull = smem_u32(&bars->a_full[0]), bar_aempty = smem_u32(&bars->a_empty[0]);
         const float etmax = sqrtf(__uint_as_float(meta_ro->etmax2_bits)) * 1.0001f;
         const float demax = sqrtf(__uint_as_float(meta_ro->demax2_bits)) * 1.0001f;
         const float emax = sqrtf(__uint_as_float(meta_ro->emax2_bits)) * 1.0001f;
+        auto ensure_issued = [&](long long upto) {
+            while (issued <= upto && issued < total_sub) {
+                const uint32_t sl_ = (uint32_t)(issued % STG_SLOTS), ph_ = (uint32_t)((issued / STG_SLOTS) & 1);
+                mbar_wait(bar_sempty + sl_ * 8, ph_ ^ 1);
+                const int rd_ = (int)(issued / num_sub), sub_ = (int)(issued - (long long)rd_ * num_sub);
+                int mt_ = (rd_ * n_clusters + cluster_id) * cs + (int)crank;
+                if (mt_ >= num_m_tiles) mt_ = 0;                                 // dummy tile: re-read tile 0, nothing is published
+                const int b_ = mt_ / tiles_per_item, w0_ = (mt_ - b_ * tiles_per_item) * BM;
+                if (elect_one()) {
+                    mbar_expect_tx(bar_sfull + sl_ * 8, STG_BYTES);
+                    tma_load_3d(sS_u + sl_ * STG_BYTES, &tmap_x, bar_sfull + sl_ * 8, w0_, sub_ * SUB_DIMS, b_);   // frames past W arrive as zeros
+                }
+                __syncwarp();
+                ++issued;
+            }
+        };
         for (int rd = 0; rd < rounds; ++rd) {
-            float s2[4] = {0.f, 0.f, 0.f, 0.f}, sd2[4] = {0.f, 0.f, 0.f, 0.f};   // |x|^2 and |x - bf16(x)|^2 of the 4 frames
+            float s2[2] = {0.f, 0.f}, sd2[2] = {0.f, 0.f};                       // |x|^2 and |x - bf16(x)|^2 of this lane's 2 frames
+            const int r0 = half_row0 + 2 * lane;
             int sub = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const uint32_t slot = a_slot0 + kb;
-                mbar_wait(bar_aempty + slot * 8, a_ph ^ 1);                      // the previous tile's MMAs are done with this chunk
+                uint32_t slot = a_slot0 + kb, a_phk = a_ph;
+                if (slot >= (uint32_t)a_slots) { slot -= a_slots; a_phk ^= 1; }
+                if (is_loader) ensure_issued(g + STG_SLOTS - 1);
+                mbar_wait(bar_aempty + slot * 8, a_phk ^ 1);                     // the MMAs that read this ring slot last are done
                 unsigned char* chunk = sA + (size_t)slot * A_CHUNK_BYTES;
                 for (int q = 0; q < BK / SUB_DIMS; ++q, ++sub) {
                     if (sub < num_sub) {
+                        if (is_loader) ensure_issued(g + STG_SLOTS - 1);
+                        const uint32_t sg = (uint32_t)(g % STG_SLOTS), sg_ph = (uint32_t)((g / STG_SLOTS) & 1);
                         mbar_wait(bar_sfull + sg * 8, sg_ph);
-                        const float* stg = reinterpret_cast<const float*>(sStg + (size_t)sg * STG_BYTES);
+                        const float* stg = reinterpret_cast<const float*>(sStg + (size_t)sg * STG_BYTES) + r0;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {                             // two 16-byte units (8 dims) per sub-chunk
-                            float4 v[8];
+                            float2 v[8];
 #pragma unroll
-                            for (int d = 0; d < 8; ++d) v[d] = *reinterpret_cast<const float4*>(stg + (h * 8 + d) * BM + 4 * lane);
+                            for (int d = 0; d < 8; ++d) v[d] = *reinterpret_cast<const float2*>(stg + (h * 8 + d) * BM);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                float x[8];
-#pragma unroll
-                                for (int d = 0; d < 8; ++d) x[d] = i == 0 ? v[d].x : (i == 1 ? v[d].y : (i == 2 ? v[d].z : v[d].w));
+                            for (int i = 0; i < 2; ++i) {
                                 uint32_t pk[4];
 #pragma unroll
                                 for (int d = 0; d < 4; ++d) {
-                                    const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * d], x[2 * d + 1]);
+                                    const float xa = i ? v[2 * d].y : v[2 * d].x, xb_ = i ? v[2 * d + 1].y : v[2 * d + 1].x;
+                                    const __nv_bfloat162 hb = __floats2bfloat162_rn(xa, xb_);
                                     const float2 bk = __bfloat1622float2(hb);
-                                    const float e0 = x[2 * d] - bk.x, e1 = x[2 * d + 1] - bk.y;
-                                    s2[i] = fmaf(x[2 * d], x[2 * d], s2[i]);
-                                    s2[i] = fmaf(x[2 * d + 1], x[2 * d + 1], s2[i]);
+                                    const float e0 = xa - bk.x, e1 = xb_ - bk.y;
+                                    s2[i] = fmaf(xa, xa, s2[i]);
+                                    s2[i] = fmaf(xb_, xb_, s2[i]);
                                     sd2[i] = fmaf(e0, e0, sd2[i]);
                                     sd2[i] = fmaf(e1, e1, sd2[i]);
                                     pk[d] = *reinterpret_cast<const uint32_t*>(&hb);
                                 }
-                                const int r = 4 * lane + i, u = 2 * q + h;
+                                const int r = r0 + i, u = 2 * q + h;
                                 *reinterpret_cast<uint4*>(chunk + (r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4)) =
                                     make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_sempty + sg * 8);
-                        if (++sg == STG_SLOTS) { sg = 0; sg_ph ^= 1; }
+                        ++g;
                     } else {                                                      // D % 64 != 0: the rest of the last chunk is zero
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int r = 4 * lane + i, u = 2 * q + h;
+                            for (int i = 0; i < 2; ++i) {
+                                const int r = r0 + i, u = 2 * q + h;
                                 *reinterpret_cast<uint4*>(chunk + (r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                             }
                     }
                 }
                 if (kb == num_kb - 1) {                                           // guard band of this tile's frames (see latent_prep_bf16_kernel)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 2; ++i) {
                         const float xn = sqrtf(s2[i]) * 1.0001f, dxn = sqrtf(sd2[i]) * 1.0001f;
-                        sBand[(rd & 1) * BM + 4 * lane + i] = 4.0f * (dxn * etmax + xn * demax) * 1.001f +
-                                                              8.0f * (float)(D + 16) * 2.3841858e-07f * xn * emax + 4.0e-7f * emax * emax + 1e-30f;
+                        sBand[(rd & 1) * BM + r0 + i] = 4.0f * (dxn * etmax + xn * demax) * 1.001f +
+                                                         8.0f * (float)(D + 16) * 2.3841858e-07f * xn * emax + 4.0e-7f * emax * emax + 1e-30f;
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
@@ -620,7 +628,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
             a_slot0 += num_kb;
-            if (a_slot0 == (uint32_t)a_slots) { a_slot0 = 0; a_ph ^= 1; }
+            if (a_slot0 >= (uint32_t)a_slots) { a_slot0 -= a_slots; a_ph ^= 1; }
         }
     } else if (warp < EPI_WARPS) {
         // ================================================================ epilogue
@@ -866,7 +874,9 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     if (rc != 0) return rc;
     const int tiles_per_item = (int)((W + BM - 1) / BM);
     const int num_kb = (D + BK - 1) / BK;
-    const int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
+    // A ring: double-buffered for small D; fused mode keeps two spare chunks so that half of the next tile is converted ahead
+    int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
+    if (z_fused != nullptr && num_kb > 2 && num_kb + 2 <= 6) a_slots = num_kb + 2;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -886,6 +896,7 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
                          (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) + sizeof(Barriers) + 1024;
     int b_stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (b_stages > (two ? 8 : 4)) b_stages = two ? 8 : 4;
+    if (const char* env = getenv("VQB_TC_STAGES")) { const int v = atoi(env); if (v >= 2 && v < b_stages) b_stages = v; }   // experiments
     if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
     const size_t smem = fixed + (size_t)b_stages * stage_bytes;
     static bool attr_done = false;
