@@ -125,14 +125,15 @@ __device__ __forceinline__ float group_sum(float v) {   // sum over the LPF lane
 // coalesced BCW -> frame-major shared tile: thread = (frame = tid & 31, dim group = tid >> 5), 4 dims per access.
 // Scalar LDG (1.8 cycles per warp-instruction) + one conflict-free STS.128 per 4 dims is the cheapest transposition in
 // pipe time; loads are issued in batches of 16 per thread (4 row groups) before any store so enough bytes are in flight.
+template <int NW = 8>
 __device__ __forceinline__ void tile_load(float* Xs, int ld, const float* __restrict__ z, size_t col, int64_t W, int D, bool valid) {
     const int f = threadIdx.x & 31;
     const float* p0 = z + (valid ? col : 0);
-    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 128) {
+    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 16 * NW) {
         float4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int d = d0 + 32 * u;
+            const int d = d0 + 4 * NW * u;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid && d < D) {
                 const float* p = p0 + (size_t)d * W;
@@ -144,7 +145,7 @@ __device__ __forceinline__ void tile_load(float* Xs, int ld, const float* __rest
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int d = d0 + 32 * u;
+            const int d = d0 + 4 * NW * u;
             if (d < D) *reinterpret_cast<float4*>(Xs + f * ld + d) = v[u];
         }
     }
@@ -152,21 +153,23 @@ __device__ __forceinline__ void tile_load(float* Xs, int ld, const float* __rest
 // Same transposition with cp.async (LDGSTS): no register staging, so every thread has its whole share of the tile
 // (D/8 4-byte copies) in flight at once - the memory-level parallelism a latency-bound streaming kernel needs.
 // Out-of-range frames are zero-filled (src-size 0).  Follow with tile_fetch_wait() + __syncthreads().
+template <int NW = 8>
 __device__ __forceinline__ void tile_fetch_async(float* Xs, int ld, const float* __restrict__ z, size_t col, int64_t W, int D, bool valid) {
     const int f = threadIdx.x & 31;
     const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(Xs + f * ld);
     const float* src0 = z + (valid ? col : 0);
     const uint32_t nbytes = valid ? 4u : 0u;
-    for (int d = threadIdx.x >> 5; d < D; d += 8)
+    for (int d = threadIdx.x >> 5; d < D; d += NW)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * d), "l"(src0 + (size_t)d * W), "r"(nbytes) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tile_fetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+template <int NW = 8>
 __device__ __forceinline__ void tile_store(const float* Xs, int ld, float* __restrict__ out, size_t col, int64_t W, int D, bool valid) {
     const int f = threadIdx.x & 31;
     if (!valid) return;
-    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 32) {
+    for (int d0 = (threadIdx.x >> 5) * 4; d0 < D; d0 += 4 * NW) {
         const float4 v = *reinterpret_cast<const float4*>(Xs + f * ld + d0);
         float* p = out + col + (size_t)d0 * W;
         st_stream(p, v.x);
@@ -467,8 +470,10 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
 // move one float4 (4 consecutive dims of one frame) per thread, the per-frame phase reads float4 rows - both are
 // bank-conflict free - and the codebook rows, residual atomics (red.v4) and shared accesses are all 16 bytes wide.
 // LPF lanes cooperate on one frame (32 / LPF frames per warp at a time), each lane owning 4*J dims.
+constexpr int TAIL_WARPS = 4;   // 128-thread blocks: more independent blocks per SM hide the load / barrier / gather latencies
+
 template <int LPF, int J, bool kResid>
-__global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
+__global__ void __launch_bounds__(32 * TAIL_WARPS, (J >= 6) ? 4 : 6) tail_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                       const float* __restrict__ e2, int D, int64_t W, int64_t N, int K,
                                                       const int* __restrict__ idx32, const uint8_t* __restrict__ cand_cnt,
                                                       const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
@@ -476,9 +481,9 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
                                                       float* __restrict__ resid, double* __restrict__ sse_partials,
                                                       WsMeta* meta, int ldg) {
     extern __shared__ __align__(16) float Xbuf[];   // 2 x [32][D + 4]: the next tile streams in while this one is worked on
-    __shared__ double red[8];
+    __shared__ double red[TAIL_WARPS];
     constexpr int FPW = 32 / LPF;                 // frames a warp works on at once
-    constexpr int ITER = (TL_F / 8) / FPW;        // rounds per warp and tile
+    constexpr int ITER = (TL_F / TAIL_WARPS) / FPW;   // rounds per warp and tile
     static_assert(ITER >= 1, "a warp must own at least FPW frames of the tile");
     const int ld = D + 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -498,10 +503,10 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
     {
         bool v0;
         const size_t c0 = tile_col(blockIdx.x, v0);
-        if (!ldg && (int64_t)blockIdx.x * TL_F < N) tile_fetch_async(Xbuf, ld, z, c0, W, D, v0);
+        if (!ldg && (int64_t)blockIdx.x * TL_F < N) tile_fetch_async<TAIL_WARPS>(Xbuf, ld, z, c0, W, D, v0);
     }
     for (int64_t tile = blockIdx.x; tile * TL_F < N; tile += gridDim.x, buf ^= 1) {
-        float* Xs = Xbuf + (size_t)buf * TL_F * ld;
+        float* Xs = Xbuf + (size_t)(ldg ? 0 : buf) * TL_F * ld;   // register-staged loads need one buffer only
         bool valid;
         const size_t col = tile_col(tile, valid);
         // shortlist headers of this warp's frames, requested early so their latency hides behind the tile fetch
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
         uint4 cl_lo[ITER], cl_hi[ITER];           // the frame's whole shortlist row (16 x uint16), or the final code in .x
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
-            const int64_t n = tile * TL_F + warp * (TL_F / 8) + it * FPW + sub;
+            const int64_t n = tile * TL_F + warp * (TL_F / TAIL_WARPS) + it * FPW + sub;
             cnt_r[it] = 0;
             cl_lo[it] = make_uint4(0u, 0u, 0u, 0u);
             cl_hi[it] = make_uint4(0u, 0u, 0u, 0u);
@@ -526,11 +531,11 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
         __syncthreads();                          // the other buffer's previous tile has been stored: it may be refilled
         const int64_t next = tile + gridDim.x;
         if (ldg) {
-            tile_load(Xs, ld, z, col, W, D, valid);
+            tile_load<TAIL_WARPS>(Xs, ld, z, col, W, D, valid);
         } else if (next * TL_F < N) {
             bool vn;
             const size_t cn = tile_col(next, vn);
-            tile_fetch_async(Xbuf + (size_t)(buf ^ 1) * TL_F * ld, ld, z, cn, W, D, vn);
+            tile_fetch_async<TAIL_WARPS>(Xbuf + (size_t)(buf ^ 1) * TL_F * ld, ld, z, cn, W, D, vn);
             asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile has landed; the next one stays in flight
         } else {
             tile_fetch_wait();
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
-            const int f = warp * (TL_F / 8) + it * FPW + sub;
+            const int f = warp * (TL_F / TAIL_WARPS) + it * FPW + sub;
             const int64_t n = tile * TL_F + f;
             const bool live = n < N;
             float4 xv[J];
@@ -657,7 +662,7 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
         }
         if (q_out) {
             __syncthreads();
-            tile_store(Xs, ld, q_out, col, W, D, valid);
+            tile_store<TAIL_WARPS>(Xs, ld, q_out, col, W, D, valid);
         }
     }
     double t = (double)sse - (double)sse_c;
@@ -667,7 +672,7 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) tail_kernel(const float
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
-        for (int i = 0; i < 8; ++i) s += red[i];
+        for (int i = 0; i < TAIL_WARPS; ++i) s += red[i];
         sse_partials[blockIdx.x] = s;
     }
     if (n_resc | n_short) {
@@ -692,15 +697,15 @@ template <int LPF, int J>
 static cudaError_t launch_tail_t(const float* z, const float* codebook, const float* e2, int D, int64_t W, int64_t N, int K,
                                  const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                                  int* counts, float* resid, double* part, int grid, WsMeta* meta, cudaStream_t s) {
-    const size_t smem = (size_t)2 * TL_F * (D + 4) * 4;
+    const size_t smem = (size_t)(tile_ldg_mode() ? 1 : 2) * TL_F * (D + 4) * 4;   // the second buffer only serves the cp.async pipeline
     cudaError_t e;
     if (resid) {
         if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
-        tail_kernel<LPF, J, true><<<grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
+        tail_kernel<LPF, J, true><<<grid, 32 * TAIL_WARPS, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
                                                           resid, part, meta, tile_ldg_mode());
     } else {
         if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
-        tail_kernel<LPF, J, false><<<grid, 256, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
+        tail_kernel<LPF, J, false><<<grid, 32 * TAIL_WARPS, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
                                                            nullptr, part, meta, tile_ldg_mode());
     }
     return cudaGetLastError();
