@@ -49,6 +49,11 @@ def load_traffic(workload: str):
     return None
 
 
+def fused_operands(W: int) -> bool:
+    """Mirror of tc_can_fuse() in csrc/vqb_tc.cu: does the tensor-core kernel read the fp32 [B, D, W] latents itself?"""
+    return os.environ.get("VQB_TC_FUSE", "1") != "0" and W % 4 == 0 and (W % 128 == 0 or W >= 1024)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -301,7 +306,9 @@ def main():
                     "frac": achieved / peak, "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] +
                     " bf16 sustained (kernel timed inside a long step)", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                     "launches_timed": kn.value, "traffic": load_traffic(args.workload),
-                    "algorithmic_flops_per_launch": flops_per_launch, "algorithmic_dram_bytes_per_launch": 2.0 * D * N}
+                    "algorithmic_flops_per_launch": flops_per_launch,
+                    # fused operand preparation reads the fp32 latents once (4 D bytes per frame); the unfused path reads a bf16 copy
+                    "algorithmic_dram_bytes_per_launch": (4.0 if fused_operands(W) else 2.0) * D * N}
     cpu = None
     if not args.no_cpu:
         n_cpu = cpu_sample_size(K, D)
