@@ -154,14 +154,26 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         __nv_bfloat16* eh = reinterpret_cast<__nv_bfloat16*>(ws + L.eh);
         VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, eb, eh, meta, s), "codebook_prep");
         const bool fuse = tc_can_fuse(z, B, D, W);
+        // fused tail: the search kernel finishes the frames itself (index, quantized, statistics); only the frames it
+        // sends to the exact search are finished by a small list kernel.  Otherwise the stand-alone tail kernel runs.
+        const bool fused_tail = fuse && !scores_dbg && tc_fused_tail_enabled() && (reinterpret_cast<uintptr_t>(codebook) & 31) == 0;
+        double* part_d = reinterpret_cast<double*>(part);
+        TailArgs targs{z, codebook, e2, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr, counts, resid, part_d};
         if (!fuse) VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");
-        rc = launch_tc_search(fuse ? z : nullptr, B, W, xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, best64, scores_dbg, ws + L.ev, s);
+        if (fused_tail) VQB_CUDA(cudaMemsetAsync(part, 0, (size_t)L.n_partials * sizeof(double), s), "memset sse partials");
+        rc = launch_tc_search(fuse ? z : nullptr, B, W, xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, best64,
+                              scores_dbg, ws + L.ev, fused_tail ? &targs : nullptr, s);
         if (rc != 0) return rc;
         if (scores_dbg) return 0;
         VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, fb_rows, &meta->fallback_count, nullptr, cand_cnt, cand_idx, best64, s),
                  "exact_search(fallback)");
-        VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, nullptr, cand_cnt, cand_idx, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
-                             counts, resid, part, L.n_partials, meta, s), "tail");
+        if (fused_tail) {
+            VQB_CUDA(launch_fallback_tail(z, codebook, B, D, W, K, fb_rows, &meta->fallback_count, best64, idx_out, targs.q_out, counts, resid,
+                                          part_d + kTcMaxCtas, s), "fallback_tail");
+        } else {
+            VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, nullptr, cand_cnt, cand_idx, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
+                                 counts, resid, part, L.n_partials, meta, s), "tail");
+        }
     }
     VQB_CUDA(launch_pack_stats(counts, part, L.n_partials, N, K, D, stats_out, accumulate, s), "pack_stats");
     return 0;

@@ -38,10 +38,43 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags);
 constexpr int kTcMaxCtas = 160;         // persistent grid bound of the tensor-core search (event scratch is sized for it)
 size_t tc_event_scratch_bytes();
 constexpr int kTailGridMax = 148 * 8;   // persistent grid of the fused tail kernel (sse partial slots)
+constexpr int kFallbackTailGrid = 148;  // fused-tail mode: sse slots [kTcMaxCtas, kTcMaxCtas + kFallbackTailGrid) belong to fallback_tail_kernel
 
 void set_error(const char* fmt, ...);
 void note_launch(int n = 1);                       // counts this library's kernel launches (vqb_debug_launch_count)
 int  cuda_fail(cudaError_t e, const char* what);   // records message, returns (int)e
+
+#ifdef __CUDACC__
+// torch.argmin ordering (vector_quantizer.py:37): NaN beats everything, otherwise smaller distance, ties -> lower index.
+__device__ __forceinline__ bool better(float d, int i, float bd, int bi) {
+    if (bi < 0) return true;
+    const bool dn = isnan(d), bn = isnan(bd);
+    if (dn) return !bn || i < bi;
+    if (bn) return false;
+    return d < bd || (d == bd && i < bi);
+}
+// The reference's distance in its association order (vector_quantizer.py:32-33):
+//   fl(|x|^2 + fl(|e|^2 - fl(2 * dot)));  2*dot is exact, so fma(-2, dot, e2) is the same single rounding.
+__device__ __forceinline__ float ref_distance(float x2, float e2, float dot) {
+    return __fadd_rn(x2, __fmaf_rn(-2.0f, dot, e2));
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+#endif
+
+// What the tensor-core search needs to finish frames itself (fused tail, see vqb_tc.cu): everything the stand-alone
+// tail kernel would have read or written.  q_out / resid may be null.
+struct TailArgs {
+    const float* z;           // [B, D, W] fp32 latents
+    const float* codebook;    // [K, D] fp32
+    const float* e2;          // [K_pad] |e_k|^2
+    int64_t*     idx_out;     // [N]
+    float*       q_out;       // [B, D, W] straight-through value, or null
+    int*         counts;      // [K]
+    float*       resid;       // [K, D] sum of (x - e_k) over the frames of code k, or null
+    double*      sse_partials;   // one slot per CTA of the search kernel
+};
 
 // ---- launchers (vqb_kernels.cu) -------------------------------------------------------------------------------
 cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb,
@@ -55,6 +88,10 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                         int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, cudaStream_t s);
+// fused-tail mode: finishes the (rare) frames the exact fallback search decided - one warp per frame of the list
+cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, int D, int64_t W, int K, const int* rows,
+                                 const int* row_count, const unsigned long long* best64, int64_t* idx_out, float* q_out, int* counts,
+                                 float* resid, double* sse_partials, cudaStream_t s);
 cudaError_t launch_pack_stats(const int* counts, const float* sse_partials, int n_partials, int64_t N, int K, int D,
                               float* stats, bool accumulate, cudaStream_t s);
 cudaError_t launch_finalize(const float* stats, int K, int D, float beta, float* losses, cudaStream_t s);
@@ -71,10 +108,11 @@ cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int6
 // ---- tensor-core search (vqb_tc.cu) ---------------------------------------------------------------------------
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.
 bool tc_can_fuse(const float* z, int B, int D, int64_t W);   // can the tensor-core kernel read the fp32 [B, D, W] latents itself?
+bool tc_fused_tail_enabled();                               // VQB_TC_TAIL=0 keeps the stand-alone tail kernel (experiments)
 // z_fused != nullptr: fused operand preparation (xb / band unused); else xb / band from latent_prep_bf16_kernel
 int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh,
                      const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
-                     unsigned long long* best64, float* scores_dbg, void* ev_scratch, cudaStream_t s);
+                     unsigned long long* best64, float* scores_dbg, void* ev_scratch, const TailArgs* tail, cudaStream_t s);
 
 }  // namespace vqb

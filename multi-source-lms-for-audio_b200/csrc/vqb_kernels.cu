@@ -26,19 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// torch.argmin ordering (vector_quantizer.py:37): NaN beats everything, otherwise smaller distance, ties -> lower index.
-__device__ __forceinline__ bool better(float d, int i, float bd, int bi) {
-    if (bi < 0) return true;
-    const bool dn = isnan(d), bn = isnan(bd);
-    if (dn) return !bn || i < bi;
-    if (bn) return false;
-    return d < bd || (d == bd && i < bi);
-}
-// The reference's distance in its association order (vector_quantizer.py:32-33):
-//   fl(|x|^2 + fl(|e|^2 - fl(2 * dot)));  2*dot is exact, so fma(-2, dot, e2) is the same single rounding.
-__device__ __forceinline__ float ref_distance(float x2, float e2, float dot) {
-    return __fadd_rn(x2, __fmaf_rn(-2.0f, dot, e2));
-}
+// better() / ref_distance() / red_add_v4(): vqb_internal.h (shared with the fused tail of the tensor-core kernel)
 
 // ------------------------------------------------------------------------------------------------ codebook prep
 // One warp per code: |e_k|^2 in fp32 (vector_quantizer.py:33), bf16 copy for the tensor-core tiles, max |e|^2 for the
@@ -112,9 +100,6 @@ static int tile_ldg_mode() {   // tile loads: register-staged LDG batches (defau
 // cooperate on one frame (32 / LPF frames per warp at a time), each lane owning 4*J dims.
 constexpr int TL_F = 32;              // frames per tile
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 template <int LPF>
 __device__ __forceinline__ float group_sum(float v) {   // sum over the LPF lanes that share a frame
 #pragma unroll
@@ -456,6 +441,58 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
                                                                                  best64);
     fallback_commit_kernel<<<148, 256, 0, s>>>(rows, row_count, best64, cand_cnt, cand_idx);
     note_launch(2);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ fallback tail
+// Fused-tail mode (the tensor-core kernel finishes every frame whose shortlist held): the few frames that went to the
+// exact search are finished here, one warp per frame of the list - codeword gather, straight-through value, SSE,
+// histogram, residual sums, index.  Strided (uncoalesced) latent accesses are fine for a list this short.
+__global__ void __launch_bounds__(256) fallback_tail_kernel(const float* __restrict__ z, const float* __restrict__ E, int D, int64_t W,
+                                                            const int* __restrict__ rows, const int* __restrict__ row_count,
+                                                            const unsigned long long* __restrict__ best64,
+                                                            int64_t* __restrict__ idx_out, float* __restrict__ q_out,
+                                                            int* __restrict__ counts, float* __restrict__ resid,
+                                                            double* __restrict__ sse_partials) {
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = *row_count;
+    double sse = 0.0;
+    for (int r = blockIdx.x * 8 + warp; r < total; r += gridDim.x * 8) {
+        const int n = rows[r];
+        const int k = (int)(uint32_t)(best64[r] & 0xFFFFFFFFull);     // argmin_key: the low word is the code
+        const int64_t b = n / W, w = n - b * W;
+        const float* xp = z + (size_t)b * D * W + w;
+        float fs = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float x = xp[(size_t)d * W];
+            const float df = __fsub_rn(E[(size_t)k * D + d], x);
+            fs = fmaf(df, df, fs);
+            if (q_out) q_out[(size_t)b * D * W + (size_t)d * W + w] = __fadd_rn(x, df);   // straight-through VALUE (:48)
+            if (resid) atomicAdd(resid + (size_t)k * D + d, -df);
+        }
+        sse += (double)warp_sum(fs);
+        if (lane == 0) {
+            atomicAdd(counts + k, 1);
+            idx_out[n] = (int64_t)k;
+        }
+    }
+    if (lane == 0) red[warp] = sse;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        sse_partials[blockIdx.x] = s;
+    }
+}
+
+cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, int D, int64_t W, int K, const int* rows,
+                                 const int* row_count, const unsigned long long* best64, int64_t* idx_out, float* q_out, int* counts,
+                                 float* resid, double* sse_partials, cudaStream_t s) {
+    (void)B; (void)K;
+    fallback_tail_kernel<<<kFallbackTailGrid, 256, 0, s>>>(z, codebook, D, W, rows, row_count, best64, idx_out, q_out, counts, resid,
+                                                           sse_partials);
+    note_launch();
     return cudaGetLastError();
 }
 

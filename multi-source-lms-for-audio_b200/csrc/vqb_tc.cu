@@ -48,6 +48,16 @@ constexpr int EPI_WARP0 = 0, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;   // 
 // The single-thread producer / MMA loops sit in the HIGHEST warp ids: the scheduler favours them over waiting epilogue warps.
 constexpr int PRODUCER_WARP = 16, MMA_WARP = 17, ALLOC_WARP = 18;
 constexpr int NUM_THREADS = EPI_THREADS + 4 * 32;                              // 640
+// fused tail (kTail): four more warps finish the frames of the PREVIOUS tile while the tensor core sweeps the next one
+// (warps 20-23; lane = frame).  The tile's fp32 latents stream back in as 3-D TMA boxes of TAIL_CHUNK dims x 128 frames
+// through a TX_SLOTS-deep shared-memory ring (issued by the first tail warp, a few boxes ahead of its own consumption):
+// DRAM latency is hidden by the ring, not by registers.  A fifth warp would cost every thread 8 registers (warps are
+// allocated four at a time).
+constexpr int TAIL_WARP0 = 20, TAIL_WARPS = 4;
+constexpr int NUM_THREADS_TAIL = NUM_THREADS + TAIL_WARPS * 32;   // 768
+constexpr int TAIL_CHUNK = 8;                // dims per box
+constexpr int TX_SLOTS = 6, TX_BYTES = TAIL_CHUNK * BM * 4;   // 6 x 4 KiB
+constexpr int TAIL_EQ = 2;                   // codebook-row chunks a lane keeps in flight (registers; these gathers hit L2)
 constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);                            // 64
 constexpr int kCandFill = 12;                // shortlist entries published per frame (cand_idx rows hold kCandMax = 16)
 
@@ -56,6 +66,8 @@ struct Barriers {
     unsigned long long a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
     unsigned long long eh_full[EH_SLOTS], eh_empty[EH_SLOTS], tmem_full[2], tmem_empty[2];
     unsigned long long stg_full[STG_SLOTS], stg_empty[STG_SLOTS];
+    unsigned long long tail_full[2], tail_empty[2];
+    unsigned long long tx_full[TX_SLOTS], tx_empty[TX_SLOTS];
     unsigned int tmem_base;
     unsigned int pad;
 };
@@ -317,6 +329,137 @@ __device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], int code0, in
         if (code0 + j < K) row_out[code0 + j] = -2.f * __uint_as_float(r[j]);
 }
 
+// ---------------------------------------------------------------------------------------------- fused tail helpers
+// L2 policy for the straight-through output (written once, never read by this kernel): evict first, so that it does
+// not push the codebook, the event stacks or the residual sums out of L2
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void stg_once(float* p, float v, uint64_t) {   // written once, never read by this kernel
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// 32 bytes of a codebook row per lane and request: each lane gathers from its own row, so every request costs one L1 tag
+// lookup per lane whatever its width - 256-bit loads halve that cost against 128-bit ones (the pointer is 32-byte aligned)
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+// How many pair sweeps the slowest tail warp needs for this tile: every tail warp deals the (frame, code) pairs of its 32
+// frames out one per lane, 32 per sweep.  The tail warps and their loader all evaluate this on the same counts, so they
+// agree on the number of latent streams without talking to each other.
+__device__ __forceinline__ int tail_max_sweeps(const uint8_t* cnts, int lane) {
+    const uint32_t c4 = reinterpret_cast<const uint32_t*>(cnts)[lane];   // frames 4*lane .. 4*lane+3: tail warp lane / 8
+    int np = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = (int)((c4 >> (8 * j)) & 0xFFu);
+        np += c > 1 ? c : 0;
+    }
+    np += __shfl_xor_sync(0xffffffffu, np, 1);
+    np += __shfl_xor_sync(0xffffffffu, np, 2);
+    np += __shfl_xor_sync(0xffffffffu, np, 4);
+    int sw = (np + 31) >> 5;
+    sw = max(sw, __shfl_xor_sync(0xffffffffu, sw, 8));
+    sw = max(sw, __shfl_xor_sync(0xffffffffu, sw, 16));
+    return sw;
+}
+// One pass of a tail warp over the tile's latents as they stream through the ring: box g holds dims [8g, 8g+8) of all 128
+// frames, [dim][frame] fp32.  Each active lane reads column `xcol` of every box and the same dims of codebook row `ep`
+// (two 16-byte gathers per box, kept TAIL_EQ boxes ahead in registers).
+//   kFinal = false: accumulates x.e and |x|^2 (fp32 rescoring of one (frame, code) pair)
+//   kFinal = true : codeword gather, straight-through value fl(x + fl(e - x)) -> qp, SSE -> fs, residual sums -> rp
+// All four tail warps consume every box in the same order; `it` counts boxes since the kernel started.
+// Position of a tail warp in the ring: the slot it consumes next and the fill parity of that slot.
+struct RingPos {
+    uint32_t slot, ph;
+    __device__ __forceinline__ void advance() { if (++slot == TX_SLOTS) { slot = 0; ph ^= 1u; } }
+};
+constexpr int TX_AHEAD = TX_SLOTS - 2;   // boxes the loader keeps in flight ahead of its own consumption
+// The first tail warp doubles as the loader of the ring and keeps no state for it: the box that is TX_AHEAD positions ahead of
+// the one it consumes next lands TX_AHEAD slots further on, and its slot is free once all four warps released the box that was
+// there before (so the other warps may lag one box behind without stalling the loader).
+__device__ __forceinline__ void tail_issue(const RingPos& pos, int ahead, int dim0, int b, int w0, uint32_t sTx_u, uint32_t bar_full,
+                                           uint32_t bar_empty, const CUtensorMap* map) {
+    uint32_t sl = pos.slot + (uint32_t)ahead, ph = pos.ph;
+    if (sl >= (uint32_t)TX_SLOTS) { sl -= TX_SLOTS; ph ^= 1u; }
+    mbar_wait(bar_empty + sl * 8, ph ^ 1u);
+    if (elect_one()) {
+        if (b < 0) mbar_arrive(bar_full + sl * 8);   // experiment: no load at all
+        else {
+        mbar_expect_tx(bar_full + sl * 8, TX_BYTES);
+        tma_load_3d(sTx_u + sl * TX_BYTES, map, bar_full + sl * 8, w0, dim0, b);
+        }
+    }
+    __syncwarp();
+}
+
+// `more` = boxes of this tile that follow this pass (the loader runs ahead across pass boundaries, never across tiles).
+template <bool kFinal>
+__device__ __forceinline__ void tail_stream(const unsigned char* sTx, uint32_t bar_full, uint32_t bar_empty, RingPos& pos, int nbox,
+                                            bool act, int xcol, const float* __restrict__ ep, int lane, float& acc0, float& acc1,
+                                            int64_t W, float* qp, float* rp, bool resid_v4, uint64_t pol, bool loader, int more, int b,
+                                            int w0, const CUtensorMap* map) {
+    float eq[TAIL_EQ][TAIL_CHUNK];
+#pragma unroll
+    for (int u = 0; u < TAIL_EQ; ++u)
+        if (act && u < nbox) ldg256(ep + u * TAIL_CHUNK, eq[u]);
+    for (int g0 = 0; g0 < nbox; g0 += TAIL_EQ) {
+#pragma unroll
+        for (int u = 0; u < TAIL_EQ; ++u) {
+            const int g = g0 + u;
+            if (g < nbox) {
+                if (loader && g + TX_AHEAD < nbox + more) {
+                    int gi = g + TX_AHEAD;
+                    while (gi >= nbox) gi -= nbox;
+                    tail_issue(pos, TX_AHEAD, gi * TAIL_CHUNK, b, w0, smem_u32(sTx), bar_full, bar_empty, map);
+                }
+                mbar_wait(bar_full + pos.slot * 8, pos.ph);
+                if (act) {
+                    const float* bx = reinterpret_cast<const float*>(sTx + (size_t)pos.slot * TX_BYTES) + xcol;
+                    float x[TAIL_CHUNK];
+#pragma unroll
+                    for (int i = 0; i < TAIL_CHUNK; ++i) x[i] = bx[i * BM];
+                    const float (&ev)[TAIL_CHUNK] = eq[u];
+                    if (!kFinal) {
+                        float cd = 0.f, cx = 0.f;         // blocked summation: box sums first, then the running totals
+#pragma unroll
+                        for (int i = 0; i < TAIL_CHUNK; ++i) { cd = fmaf(x[i], ev[i], cd); cx = fmaf(x[i], x[i], cx); }
+                        acc0 += cd;
+                        acc1 += cx;
+                    } else {
+                        float df[TAIL_CHUNK], cs = 0.f;
+#pragma unroll
+                        for (int i = 0; i < TAIL_CHUNK; ++i) { df[i] = __fsub_rn(ev[i], x[i]); cs = fmaf(df[i], df[i], cs); }
+                        acc0 += cs;
+                        if (qp) {
+                            float* q = qp + (size_t)g * TAIL_CHUNK * W;
+#pragma unroll
+                            for (int i = 0; i < TAIL_CHUNK; ++i) stg_once(q + (size_t)i * W, __fadd_rn(x[i], df[i]), pol);   // vector_quantizer.py:48
+                        }
+                        if (rp) {
+                            float* r = rp + g * TAIL_CHUNK;
+                            if (resid_v4) {
+                                red_add_v4(r, -df[0], -df[1], -df[2], -df[3]);
+                                red_add_v4(r + 4, -df[4], -df[5], -df[6], -df[7]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < TAIL_CHUNK; ++i) atomicAdd(r + i, -df[i]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + pos.slot * 8);
+                if (act && g + TAIL_EQ < nbox) ldg256(ep + (g + TAIL_EQ) * TAIL_CHUNK, eq[u]);
+                pos.advance();
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
 // kTwo = false: cta_group::1 MMAs, every CTA holds whole codebook tiles (optionally multicast inside a cluster).
 // kTwo = true : CTA pairs with cta_group::2 MMAs (M = 256 over the pair): each CTA holds its own 128 frames and HALF of every
@@ -325,14 +468,20 @@ __device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], int code0, in
 //               warp 19 streams 16-dim x 128-frame boxes through a small ring, warp 18 converts them to bf16 into the
 //               swizzled A chunks, measures |x| and |x - bf16(x)| per frame and publishes the guard band in shared memory.
 //               Frame tiles then never straddle a batch item (tile = (b, w0 .. w0+127)); no bf16 copy of the latents exists.
-template <bool kTwo, bool kFuse>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// kTail = true (needs kFuse): warps 20-23 finish every frame whose shortlist held - fp32 rescoring in the reference's op order,
+//               codeword gather, straight-through value, SSE, histogram, residual sums, index - one tile behind the tensor
+//               core.  The tile's latents are read a second time while they are still in L2, so the forward pass touches
+//               HBM once for the latents and once for `quantized`; no stand-alone tail kernel runs.
+template <bool kTwo, bool kFuse, bool kTail>
+__global__ void __launch_bounds__(kTail ? NUM_THREADS_TAIL : NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
-                 const __grid_constant__ CUtensorMap tmap_eh, const __nv_bfloat16* __restrict__ eh, int64_t W, int tiles_per_item, int D,
+                 const __grid_constant__ CUtensorMap tmap_eh, const __grid_constant__ CUtensorMap tmap_xt, const __nv_bfloat16* __restrict__ eh, int64_t W, int tiles_per_item, int D,
                  const WsMeta* __restrict__ meta_ro, const float* __restrict__ band_g, int64_t N, int num_m_tiles, int num_n_tiles,
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
-                 unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch) {
+                 unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
+                 const TailArgs tail, const int tail_dbg) {
+    static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
     unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB (16 KiB half tiles in 2-CTA mode)
@@ -343,9 +492,18 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     float* sBand = reinterpret_cast<float*>(sStg + (kFuse ? STG_SLOTS * STG_BYTES : 0));   // fused mode: [2][128] guard bands
     float* sMin = sBand + (kFuse ? 2 * BM : 0);                          // [4][128] running maxima of the four column quarters
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
-    Barriers* bars = reinterpret_cast<Barriers*>(sCnt + 3 * BM);        // [128] pooled running maximum per frame (ordered int)
+    // fused tail: the shortlists of two frame tiles (the epilogue fills one while the tail warps consume the other)
+    uint16_t* sCand = reinterpret_cast<uint16_t*>(sCnt + 3 * BM);        // [2][128][kCandFill] codes
+    uint8_t* sCandCnt = reinterpret_cast<uint8_t*>(sCand + (kTail ? 2 * BM * kCandFill : 0));   // [2][128] 0 = not for the tail
+    float2* sPair = reinterpret_cast<float2*>(sCandCnt + (kTail ? 2 * BM : 0));                  // [4][32] (distance, code) hand-back
+    unsigned char* sTx = reinterpret_cast<unsigned char*>(sPair + (kTail ? TAIL_WARPS * 32 + 16 : 0));   // (+128 B of per-warp totals) TX_SLOTS x 4 KiB latent boxes
+    Barriers* bars = reinterpret_cast<Barriers*>(sTx + (kTail ? TX_SLOTS * TX_BYTES : 0));          // sCnt: [128] pooled running maximum per frame (ordered int)
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Logical warp id = role.  With the fused tail the roles are rotated so that the tail warps are the four LOWEST hardware
+    // warps: the scheduler favours high warp ids, and the tail must never win an issue slot against the MMA / TMA / epilogue warps.
+    // (Hardware warp = logical warp + 4 mod 24: the TMEM lane quarter warp % 4 of the epilogue warps is unchanged.)
+    const int lane = threadIdx.x & 31;
+    const int warp = kTail ? (int)(((threadIdx.x >> 5) + (unsigned)TAIL_WARP0) % (unsigned)(TAIL_WARP0 + TAIL_WARPS)) : (int)(threadIdx.x >> 5);
     // Cluster of `cs` CTAs: every CTA quantises its own 128-frame tile, but each codebook tile is fetched from L2 only
     // once per cluster - CTA r loads rows [r*256/cs, (r+1)*256/cs) and multicasts them into all cs shared memories.
     // All CTAs of a cluster therefore walk the same (tile round, codebook tile) sequence; a CTA whose frame tile lies
@@ -375,6 +533,14 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_init(smem_u32(&bars->eh_empty[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bars->tail_full[i]), 4);                 // the four epilogue warps that publish the counts
+            mbar_init(smem_u32(&bars->tail_empty[i]), TAIL_WARPS);
+        }
+        for (int i = 0; i < TX_SLOTS; ++i) {
+            mbar_init(smem_u32(&bars->tx_full[i]), 1);
+            mbar_init(smem_u32(&bars->tx_empty[i]), TAIL_WARPS);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->tmem_full[i]), 1);
             mbar_init(smem_u32(&bars->tmem_empty[i]), (kTwo ? 2 : 1) * EPI_THREADS / 32);   // 2-CTA: both CTAs' epilogues report to the leader
         }
@@ -386,9 +552,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     {   // constant bias operand A: every frame row is (-1, -1, -1, 0, 0, 0, 0, 0) in K-half 0; K-half 1 is the zero block
         uint4* ax = reinterpret_cast<uint4*>(sAX);
-        for (int i = threadIdx.x; i < AX_BYTES / 16; i += NUM_THREADS) ax[i] = make_uint4(0xBF80BF80u, 0x0000BF80u, 0u, 0u);
+        for (int i = threadIdx.x; i < AX_BYTES / 16; i += (int)blockDim.x) ax[i] = make_uint4(0xBF80BF80u, 0x0000BF80u, 0u, 0u);
         uint4* zz = reinterpret_cast<uint4*>(sZero);
-        for (int i = threadIdx.x; i < ZERO_BYTES / 16; i += NUM_THREADS) zz[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < ZERO_BYTES / 16; i += (int)blockDim.x) zz[i] = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     }
     tc_fence_before();
@@ -455,9 +621,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             a_slot0 += num_kb;
             if (a_slot0 >= (uint32_t)a_slots) { a_slot0 -= a_slots; a_ph ^= 1; }
         }
-    } else if (warp == MMA_WARP && leader) {
+    } else if (warp == MMA_WARP) {
         // ================================================================ MMA issuer (converged warp, one elected lane issues;
         //                                                                   in 2-CTA mode only the pair's leader)
+        if (leader) {
         uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, as = 0, t_ph = 0, es = 0, e_ph = 0;
         const uint64_t dA0 = make_desc_sw128(smem_u32(sA)), dB0 = make_desc_sw128(smem_u32(sB));
         // bias operands: 8-row groups 128 B apart, K-half 1 = the shared zero block
@@ -525,6 +692,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             a_slot0 += num_kb;
             if (a_slot0 >= (uint32_t)a_slots) { a_slot0 -= a_slots; a_ph ^= 1; }
+        }
         }
     } else if (kFuse && (warp == CONVERT_WARP || warp == ALOAD_WARP)) {
         // ================================================================ fused operand preparation: two converter warps.
@@ -630,6 +798,115 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             a_slot0 += num_kb;
             if (a_slot0 >= (uint32_t)a_slots) { a_slot0 -= a_slots; a_ph ^= 1; }
         }
+    } else if (kTail && warp >= TAIL_WARP0) {
+        // ================================================================ fused tail: lane = frame, one tile behind the epilogue.
+        // Pair sweeps settle the index of the frames with more than one shortlisted code: the warp's (frame, code) pairs are
+        // dealt out one per lane (no divergence over shortlist lengths), each lane evaluates the reference's fp32 distance
+        // fl(|x|^2 + fl(|e|^2 - 2 x.e)) of its pair and hands it back through shared memory; ties -> lowest index.
+        // The final pass gathers the codeword, writes the straight-through value and accumulates SSE / histogram /
+        // residual sums.  Every pass reads the tile's latents from the ring (see tail_stream).
+        const int tw = warp - TAIL_WARP0;
+        const int f = tw * 32 + lane;
+        const int nbox = D / TAIL_CHUNK;
+        const bool resid_v4 = tail.resid && (reinterpret_cast<uintptr_t>(tail.resid) & 15) == 0;
+        float2* pair = sPair + tw * 32;
+        double* acc_sse = reinterpret_cast<double*>(sPair + TAIL_WARPS * 32) + tw;          // per-warp running SSE (lane 0)
+        unsigned int* acc_cnt = reinterpret_cast<unsigned int*>(sPair + TAIL_WARPS * 32 + 4) + 2 * tw;   // rescored / shortlisted
+        if (lane == 0) { *acc_sse = 0.0; acc_cnt[0] = 0u; acc_cnt[1] = 0u; }
+        const uint64_t pol_once = 0;
+        const uint32_t bar_full = smem_u32(&bars->tx_full[0]), bar_empty = smem_u32(&bars->tx_empty[0]);
+        const bool loader = tw == 0;
+        RingPos pos{0u, 0u};
+        if (loader && lane == 0) prefetch_tmap(&tmap_xt);
+        const int mt_step = n_clusters * cs;
+        int mt = cluster_id * cs + (int)crank;
+        for (int rd = 0; rd < rounds; ++rd, mt += mt_step) {
+            const int tbuf = rd & 1;
+            mbar_wait(smem_u32(&bars->tail_full[tbuf]), (rd >> 1) & 1);
+            if (mt < num_m_tiles) {
+                const int b = mt / tiles_per_item, w0 = (mt - b * tiles_per_item) * BM;
+                const int cnt = sCandCnt[tbuf * BM + f];
+                const uint16_t* cl = sCand + (tbuf * BM + tw * 32) * kCandFill;   // this warp's 32 shortlists
+                const int sweeps = (tail_dbg & 1) ? 0 : tail_max_sweeps(sCandCnt + tbuf * BM, lane);
+                if (loader) {                                // prime the ring: the first TX_AHEAD boxes of this tile
+                    const int total_boxes = (sweeps + 1) * nbox;
+                    for (int a = 0; a < TX_AHEAD && a < total_boxes; ++a) {
+                        int gi = a;
+                        while (gi >= nbox) gi -= nbox;
+                        tail_issue(pos, a, gi * TAIL_CHUNK, (tail_dbg & 64) ? -1 : b, w0, smem_u32(sTx), bar_full, bar_empty, &tmap_xt);
+                    }
+                }
+                int k = cnt ? (int)cl[lane * kCandFill] : 0;
+                const bool need = cnt > 1 && sweeps > 0;
+                const int np = need ? cnt : 0;
+                int incl = np;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int excl = incl - np, total = __shfl_sync(0xffffffffu, incl, 31);
+                float bd = 0.f;
+                int bk = -1;
+                for (int sw = 0; sw < sweeps; ++sw) {
+                    const int s0 = sw * 32, p = s0 + lane;
+                    const bool act = p < total;
+                    int fl = 0;                              // pair p belongs to the frame whose [excl, incl) holds it
+#pragma unroll
+                    for (int st = 16; st > 0; st >>= 1) {
+                        const int t = __shfl_sync(0xffffffffu, incl, fl + st - 1);
+                        if (t <= p) fl += st;
+                    }
+                    const int ci = p - __shfl_sync(0xffffffffu, excl, fl);
+                    const int kc = act ? (int)cl[fl * kCandFill + ci] : 0;
+                    float dot = 0.f, x2 = 0.f;
+                    tail_stream<false>(sTx, bar_full, bar_empty, pos, nbox, act, tw * 32 + fl,
+                                       tail.codebook + (size_t)kc * D, lane, dot, x2, W, nullptr, nullptr,
+                                       false, pol_once, loader, (sweeps - sw) * nbox, (tail_dbg & 64) ? -1 : b, w0, &tmap_xt);
+                    const float dist = act ? ref_distance(x2, tail.e2[kc], dot) : 0.f;
+                    pair[lane] = make_float2(dist, __int_as_float(kc));
+                    __syncwarp();
+                    if (need) {
+                        const int lo = max(excl, s0), hi = min(incl, s0 + 32);
+                        for (int pp = lo; pp < hi; ++pp) {
+                            const float2 v = pair[pp - s0];
+                            const int kk = __float_as_int(v.y);
+                            if (better(v.x, kk, bd, bk)) { bd = v.x; bk = kk; }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (need) k = bk;
+                const size_t at = (size_t)b * D * W + (size_t)(w0 + f);   // element (b, 0, w) of the [B, D, W] tensors
+                if (cnt) {
+                    tail.idx_out[(int64_t)b * W + w0 + f] = (int64_t)k;
+                    atomicAdd(tail.counts + k, 1);
+                }
+                float fs = 0.f, unused = 0.f;
+                tail_stream<true>(sTx, bar_full, bar_empty, pos, nbox, cnt != 0 && !(tail_dbg & 16), f,
+                                  tail.codebook + (size_t)k * D, lane, fs, unused, W,
+                                  (tail.q_out && !(tail_dbg & 2)) ? tail.q_out + at : nullptr,
+                                  (tail.resid && !(tail_dbg & 4)) ? tail.resid + (size_t)k * D : nullptr, resid_v4, pol_once, loader, 0, (tail_dbg & 64) ? -1 : b,
+                                  w0, &tmap_xt);
+                // per-warp running totals live in shared memory (lane 0 only): registers are scarce in this kernel
+                fs = cnt ? fs : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
+                const unsigned int n_resc = __popc(__ballot_sync(0xffffffffu, need));
+                const unsigned int n_short = __reduce_add_sync(0xffffffffu, (unsigned int)cnt);
+                if (lane == 0) { *acc_sse += (double)fs; acc_cnt[0] += n_resc; acc_cnt[1] += n_short; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->tail_empty[tbuf]));
+        }
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (tw == 0 && lane == 0) {
+            const double* a = reinterpret_cast<const double*>(sPair + TAIL_WARPS * 32);
+            tail.sse_partials[blockIdx.x] = (a[0] + a[1]) + (a[2] + a[3]);
+            const unsigned int* c = reinterpret_cast<const unsigned int*>(sPair + TAIL_WARPS * 32 + 4);
+            atomicAdd(&meta->rescored, (unsigned long long)(c[0] + c[2] + c[4] + c[6]));
+            atomicAdd(&meta->shortlisted, (unsigned long long)(c[1] + c[3] + c[5] + c[7]));
+        }
     } else if (warp < EPI_WARPS) {
         // ================================================================ epilogue
         const int ew = warp - EPI_WARP0;
@@ -638,7 +915,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
         const bool force_fallback = meta->cb_nonfinite != 0;
-        const int et = threadIdx.x - EPI_WARP0 * 32;             // 0..511
+        const int et = (warp - EPI_WARP0) * 32 + lane;           // 0..511
         EventStack ev;
         ev.base = ev_scratch + ((size_t)blockIdx.x * EPI_THREADS + et) * (EV_CAP * EV_WORDS);
         ev.n = 0;
@@ -703,12 +980,14 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             // ---- resolve this thread's chunks against the frame's final maximum and publish the shortlist
             sMin[colq * BM + row_in_tile] = thr + hband;                     // running maximum of this column quarter
+            const int tbuf = rd & 1;
+            if (kTail) mbar_wait(smem_u32(&bars->tail_empty[tbuf]), ((rd >> 1) & 1) ^ 1);   // the tail is done with the tile before last
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (row < N && !scores_dbg) {
                 const float gmax = fmaxf(fmaxf(sMin[row_in_tile], sMin[BM + row_in_tile]),
                                          fmaxf(sMin[2 * BM + row_in_tile], sMin[3 * BM + row_in_tile]));
                 const float cutoff = gmax - hband;
-                uint16_t* dst = cand_idx + (size_t)row * kCandMax;
+                uint16_t* dst = kTail ? sCand + (tbuf * BM + row_in_tile) * kCandFill : cand_idx + (size_t)row * kCandMax;
                 const int n_ev = ev.n < EV_CAP ? ev.n : EV_CAP;
                 bool lost = ev.n > EV_CAP || !(band < INFINITY);
                 for (int e0 = 0; e0 < n_ev; e0 += 8) {
@@ -740,20 +1019,27 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (colq == 0) *smax = f2ord(-INFINITY);       // nobody reads the pooled maximum between the two barriers
             asm volatile("bar.sync 2, 512;" ::: "memory");
             if (colq == 0) {
+                int tcnt = 0;                                    // what the tail warps get: 0 = frame is not theirs
                 if (row < N && !scores_dbg) {
                     const int cnt = sCnt[row_in_tile];
                     if (force_fallback || cnt == 0 || sCnt[BM + row_in_tile]) {
-                        cand_cnt[row] = kCandFinal;   // the exact search fills in the final code
+                        if (!kTail) cand_cnt[row] = kCandFinal;   // the exact search fills in the final code
                         const int fp = atomicAdd(&meta->fallback_count, 1);
                         fallback_rows[fp] = (int)row;
                         best64[fp] = ~0ull;                      // the sliced exact search meets here through atomicMin
                         atomicAdd(&meta->fallback_total, 1ull);
                     } else {
-                        cand_cnt[row] = (uint8_t)(cnt < kCandFill ? cnt : kCandFill);
+                        tcnt = cnt < kCandFill ? cnt : kCandFill;
+                        if (!kTail) cand_cnt[row] = (uint8_t)tcnt;
                     }
                 }
                 sCnt[row_in_tile] = 0;
                 sCnt[BM + row_in_tile] = 0;
+                if (kTail) {
+                    sCandCnt[tbuf * BM + row_in_tile] = (uint8_t)tcnt;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->tail_full[tbuf]));   // release: the shortlists were written before bar 2
+                }
             }
         }
     }
@@ -815,12 +1101,12 @@ static int make_map_eh(CUtensorMap* map, const void* base, uint64_t rows) {
 }
 
 // fp32 latents in the reference's [B, D, W] layout: box = 128 frames x 16 dims of one batch item, zero fill past W
-static int make_map_z(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W) {
+static int make_map_z(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_dims = SUB_DIMS) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VQB_E_DEVICE; }
     const cuuint64_t dims[3] = {W, D, B};
     const cuuint64_t strides[2] = {W * 4, D * W * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)BM, (cuuint32_t)SUB_DIMS, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)BM, box_dims, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(z), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -836,6 +1122,15 @@ bool tc_can_fuse(const float* z, int B, int D, int64_t W) {
     if (const char* env = getenv("VQB_TC_FUSE")) if (env[0] == '0') return false;
     // 3-D TMA needs 16-byte global strides; short clips would waste most of every 128-frame tile on padding
     return (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (D % tc::SUB_DIMS) == 0 && (W % 128 == 0 || W >= 1024);
+}
+
+// Opt-in (VQB_TC_TAIL=1).  Measured on B200 at BASELINE config 3: the fused tail makes the whole forward 68.5 ms instead of
+// 74.3 ms with the round-1 stand-alone tail, but the search kernel itself slows from 50.9 to 68.5 ms - the epilogue already
+// keeps the SM's non-tensor resources busy, so the tail's work costs about as much inside the kernel as outside it.
+// A stand-alone tail at HBM speed beats it, hence off by default.
+bool tc_fused_tail_enabled() {
+    if (const char* env = getenv("VQB_TC_TAIL")) return env[0] == '1';
+    return false;
 }
 
 size_t tc_event_scratch_bytes() { return (size_t)kTcMaxCtas * tc::EPI_THREADS * tc::EV_CAP * tc::EV_WORDS * 4; }
@@ -864,9 +1159,15 @@ static void timing_end(TimingSlot* t, cudaStream_t s) {
 int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh,
                      const float* band, int64_t N, int64_t N_pad, int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx,
                      int* fallback_rows, WsMeta* meta, unsigned long long* best64, float* scores_dbg, void* ev_scratch,
-                     cudaStream_t s) {
+                     const TailArgs* tail_args, cudaStream_t s) {
     using namespace tc;
     const bool fuse = z_fused != nullptr;          // the caller decided with tc_can_fuse(): A operand built in-kernel from fp32 BCW
+    const bool with_tail = tail_args != nullptr;   // the kernel also finishes the frames (needs the fused operand preparation)
+    if (with_tail && (!fuse || scores_dbg)) { set_error("tc_search: the fused tail needs the fused operand preparation"); return VQB_E_FLAGS; }
+    if (with_tail && ((reinterpret_cast<uintptr_t>(tail_args->codebook) & 31) || (D % 8))) {
+        set_error("tc_search: the fused tail gathers codebook rows with 32-byte loads; the codebook must be 32-byte aligned");
+        return VQB_E_ALIGN;
+    }
     CUtensorMap mx;
     int rc;
     if (fuse) rc = make_map_z(&mx, z_fused, (uint64_t)B, (uint64_t)D, (uint64_t)W);
@@ -893,7 +1194,8 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     if (num_m_tiles < 2 * cs) { cs = 1; two = false; }
     const size_t stage_bytes = two ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
     const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
-                         (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) + sizeof(Barriers) + 1024;
+                         (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
+                         (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES : 0) + sizeof(Barriers) + 256;
     int b_stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (b_stages > (two ? 8 : 4)) b_stages = two ? 8 : 4;
     if (const char* env = getenv("VQB_TC_STAGES")) { const int v = atoi(env); if (v >= 2 && v < b_stages) b_stages = v; }   // experiments
@@ -901,21 +1203,25 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     const size_t smem = fixed + (size_t)b_stages * stage_bytes;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc_search_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_search_kernel)");
         attr_done = true;
     }
-    CUtensorMap me_c, meh;
+    CUtensorMap me_c, meh, mxt;
+    if (with_tail) { if ((rc = make_map_z(&mxt, z_fused, (uint64_t)B, (uint64_t)D, (uint64_t)W, TAIL_CHUNK)) != 0) return rc; }
+    else mxt = mx;
     if ((rc = make_map(&me_c, eb, (uint64_t)K_pad, (uint64_t)D, two ? BN / 2 : BN / cs)) != 0) return rc;
     if ((rc = make_map_eh(&meh, eh, (uint64_t)K_pad)) != 0) return rc;
     int grid = num_m_tiles < sms ? num_m_tiles : sms;
     grid = grid / cs * cs;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(with_tail ? NUM_THREADS_TAIL : NUM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -927,14 +1233,19 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     cfg.numAttrs = 1;
     TimingSlot* slot = timing_begin(s);
     cudaError_t le;
-#define VQB_TC_LAUNCH(TWO, FUSE)                                                                                                       \
-    le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE>, mx, me_c, meh, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
-                            num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,  \
-                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch))
-    if (two && fuse) VQB_TC_LAUNCH(true, true);
-    else if (two) VQB_TC_LAUNCH(true, false);
-    else if (fuse) VQB_TC_LAUNCH(false, true);
-    else VQB_TC_LAUNCH(false, false);
+    const TailArgs targs = with_tail ? *tail_args : TailArgs{};
+    int tail_dbg = 0;                              // experiments only: switch parts of the fused tail off (results are then wrong)
+    if (const char* env = getenv("VQB_TAIL_DBG")) tail_dbg = atoi(env);
+#define VQB_TC_LAUNCH(TWO, FUSE, TAIL)                                                                                                       \
+    le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
+                            num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \
+                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, tail_dbg)
+    if (two && with_tail) VQB_TC_LAUNCH(true, true, true);
+    else if (with_tail) VQB_TC_LAUNCH(false, true, true);
+    else if (two && fuse) VQB_TC_LAUNCH(true, true, false);
+    else if (two) VQB_TC_LAUNCH(true, false, false);
+    else if (fuse) VQB_TC_LAUNCH(false, true, false);
+    else VQB_TC_LAUNCH(false, false, false);
 #undef VQB_TC_LAUNCH
     if (le != cudaSuccess) return cuda_fail(le, "tc_search_kernel launch");
     cudaError_t e = cudaGetLastError();

@@ -141,6 +141,30 @@ def test_oracle_parity(B, D, W, K, cb_scale, z_scale, precision):
     np.testing.assert_allclose(vq.codebook.weight.grad.cpu().numpy(), dE, rtol=1e-4, atol=1e-6 * np.abs(dE).max())
 
 
+@pytest.mark.parametrize("B,D,W,K,cb_scale", [(2, 64, 11000, 512, None), (1, 256, 3000, 8192, 1.0), (3, 128, 1280, 700, 1.0),
+                                              (2, 16, 1100, 40, 1.0)])
+def test_fused_tail_variant_matches_oracle(B, D, W, K, cb_scale, monkeypatch):
+    """VQB_TC_TAIL=1: the search kernel finishes the frames itself (rescoring, gather, straight-through value, statistics)
+    and only the exact-search fallback frames go through the list kernel.  Same parity bar as the default path."""
+    monkeypatch.setenv("VQB_TC_TAIL", "1")
+    z = seeded(300 + D + K, (B, D, W))
+    cb = (np.random.default_rng(5).uniform(-1 / K, 1 / K, (K, D)).astype(np.float32) if cb_scale is None
+          else seeded(400 + D + K, (K, D), cb_scale))
+    beta = 0.25
+    ref = O.vq_forward(z, cb, beta)
+    Gq = seeded(7, z.shape, 1e-3)
+    vq, zt, (emb, com, q, ppl, enc, idx) = run_module(z, cb, beta, "bf16", Gq=Gq)
+    got = idx.reshape(-1).cpu().numpy()
+    n_bad = assert_index_parity(got, z, cb, ref.indices, ref.margin, ref.eps)
+    np.testing.assert_allclose(emb.item(), ref.embedding_loss, rtol=LOSS_RTOL)
+    if n_bad == 0:
+        np.testing.assert_allclose(ppl.item(), ref.perplexity, rtol=LOSS_RTOL)
+        assert np.array_equal(q.detach().cpu().numpy(), ref.quantized)
+    dX, dE = O.vq_backward(z, cb, got, beta, 1.0, 1.0, Gq)
+    np.testing.assert_allclose(zt.grad.cpu().numpy(), dX, rtol=1e-5, atol=1e-7 * np.abs(dX).max())
+    np.testing.assert_allclose(vq.codebook.weight.grad.cpu().numpy(), dE, rtol=1e-4, atol=1e-6 * np.abs(dE).max())
+
+
 def test_trained_like_latents_use_single_candidate_shortlists():
     """Clustered latents (codeword + noise): the shortlist is a single code for almost every frame and nothing falls back."""
     K, D = 2048, 128
