@@ -225,6 +225,11 @@ def main():
     launches = int(lib.vqb_debug_launch_count(0))
     kt, kn = C.c_double(0), C.c_int(0)
     _lib.check("vqb_debug_kernel_time_ms", lib.vqb_debug_kernel_time_ms(C.byref(kt), C.byref(kn)))
+    stages = {}
+    for sid, sname in enumerate(("search", "prep", "fallback", "tail", "pack_stats")):   # VQB_STAGE_* in include/vqb.h
+        st_ms, st_n = C.c_double(0), C.c_int(0)
+        _lib.check("vqb_debug_stage_time_ms", lib.vqb_debug_stage_time_ms(sid, C.byref(st_ms), C.byref(st_n)))
+        stages[sname] = st_ms.value / max(1, args.steps)
     lib.vqb_debug_kernel_timing(0)
     clocks = sampler.stop() if rank == 0 else None
     counters = F.debug_counters(dev)
@@ -323,6 +328,7 @@ def main():
                        "l2": "inputs (>=268 MB per step) larger than the 126 MB L2; no explicit flush",
                        "step": "training-mode forward (indices + quantized + stats + losses)"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "train_step": train,
+            "stage_ms_per_step": stages,
             "shortlist": {"rescored_frames_per_step": counters["rescored"], "fallback_frames_per_step": counters["fallback"],
                           "mean_candidates": counters["shortlisted"] / max(1, N)},
             "losses": {"embedding": loss_vals[0], "commitment": loss_vals[1], "perplexity": loss_vals[2]}}

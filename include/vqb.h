@@ -130,10 +130,18 @@ VQB_API int vqb_debug_tc_scores(const float* z_bcw, const float* codebook, int B
 
 /* Number of this library's kernel launches since the last reset (bench.py's `gpu_launches`). */
 VQB_API long long vqb_debug_launch_count(int reset);
-/* CUDA-event timing of the dominant kernel (tc_search_kernel) on its launching stream: enable, run, then read the summed
- * duration and launch count (bench.py's roofline leg).  At most 512 launches are recorded per enable. */
+/* CUDA-event timing of the stages of vqb_forward on its launching stream: enable, run, then read the summed duration and
+ * launch count of a stage (bench.py's roofline leg).  At most 2048 stage launches are recorded per enable.
+ * vqb_debug_kernel_time_ms reads VQB_STAGE_SEARCH, the dominant kernel (tc_search_kernel). */
+#define VQB_STAGE_SEARCH   0   /* tc_search_kernel (bf16) or exact_search_kernel over all frames (fp32) */
+#define VQB_STAGE_PREP     1   /* memsets, codebook_prep, latent_prep (unfused operand preparation only) */
+#define VQB_STAGE_FALLBACK 2   /* exact search of the frames whose shortlist overflowed + commit / list tail */
+#define VQB_STAGE_TAIL     3   /* rescoring, gather, straight-through value, statistics */
+#define VQB_STAGE_PACK     4   /* pack_stats */
+#define VQB_N_STAGES       5
 VQB_API int vqb_debug_kernel_timing(int enable);
 VQB_API int vqb_debug_kernel_time_ms(double* total_ms, int* launches);
+VQB_API int vqb_debug_stage_time_ms(int stage, double* total_ms, int* launches);
 
 #ifdef __cplusplus
 }

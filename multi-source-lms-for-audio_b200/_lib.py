@@ -41,6 +41,7 @@ _SIGNATURES = {
     "vqb_debug_launch_count": (C.c_longlong, [C.c_int]),
     "vqb_debug_kernel_timing": (C.c_int, [C.c_int]),
     "vqb_debug_kernel_time_ms": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "vqb_debug_stage_time_ms": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "vqb_debug_tc_scores": (C.c_int, [_c_f32p, _c_f32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _c_f32p, C.c_void_p,
                                       C.c_size_t, C.c_void_p]),
 }

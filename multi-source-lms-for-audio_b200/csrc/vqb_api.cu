@@ -129,6 +129,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
     float* part = reinterpret_cast<float*>(ws + L.sse_partials);
     float* resid = (flags & VQB_WANT_RESID) ? stats_out + K : nullptr;
 
+    void* tprep = stage_timing_begin(s, VQB_STAGE_PREP);
     if (!accumulate) {
         VQB_CUDA(cudaMemsetAsync(meta, 0, sizeof(WsMeta), s), "memset meta");
         VQB_CUDA(cudaMemsetAsync(counts, 0, (size_t)K * 4, s), "memset counts");
@@ -140,9 +141,14 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
     if (prec == VQB_PREC_FP32) {
         int* idx32 = reinterpret_cast<int*>(ws + L.idx32);
         VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, nullptr, nullptr, meta, s), "codebook_prep");
+        stage_timing_end(tprep, s);
+        void* t0 = stage_timing_begin(s, VQB_STAGE_SEARCH);
         VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, nullptr, nullptr, idx32, nullptr, nullptr, nullptr, s), "exact_search");
+        stage_timing_end(t0, s);
+        void* t1 = stage_timing_begin(s, VQB_STAGE_TAIL);
         VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, idx32, nullptr, nullptr, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
                              counts, resid, part, L.n_partials, meta, s), "tail");
+        stage_timing_end(t1, s);
     } else {
         uint8_t* cand_cnt = reinterpret_cast<uint8_t*>(ws + L.cand_cnt);
         uint16_t* cand_idx = reinterpret_cast<uint16_t*>(ws + L.cand_idx);
@@ -161,21 +167,29 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         TailArgs targs{z, codebook, e2, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr, counts, resid, part_d};
         if (!fuse) VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");
         if (fused_tail) VQB_CUDA(cudaMemsetAsync(part, 0, (size_t)L.n_partials * sizeof(double), s), "memset sse partials");
+        stage_timing_end(tprep, s);
         rc = launch_tc_search(fuse ? z : nullptr, B, W, xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, best64,
                               scores_dbg, ws + L.ev, fused_tail ? &targs : nullptr, s);
         if (rc != 0) return rc;
         if (scores_dbg) return 0;
+        void* tfb = stage_timing_begin(s, VQB_STAGE_FALLBACK);
         VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, fb_rows, &meta->fallback_count, nullptr, cand_cnt, cand_idx, best64, s),
                  "exact_search(fallback)");
         if (fused_tail) {
             VQB_CUDA(launch_fallback_tail(z, codebook, B, D, W, K, fb_rows, &meta->fallback_count, best64, idx_out, targs.q_out, counts, resid,
                                           part_d + kTcMaxCtas, s), "fallback_tail");
+            stage_timing_end(tfb, s);
         } else {
+            stage_timing_end(tfb, s);
+            void* tt = stage_timing_begin(s, VQB_STAGE_TAIL);
             VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, nullptr, cand_cnt, cand_idx, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
                                  counts, resid, part, L.n_partials, meta, s), "tail");
+            stage_timing_end(tt, s);
         }
     }
+    void* tpk = stage_timing_begin(s, VQB_STAGE_PACK);
     VQB_CUDA(launch_pack_stats(counts, part, L.n_partials, N, K, D, stats_out, accumulate, s), "pack_stats");
+    stage_timing_end(tpk, s);
     return 0;
 }
 

@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libvqb_b200.so (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stddef.h>
@@ -39,6 +40,10 @@ constexpr int kTcMaxCtas = 160;         // persistent grid bound of the tensor-c
 size_t tc_event_scratch_bytes();
 constexpr int kTailGridMax = 148 * 8;   // persistent grid of the fused tail kernel (sse partial slots)
 constexpr int kFallbackTailGrid = 148;  // fused-tail mode: sse slots [kTcMaxCtas, kTcMaxCtas + kFallbackTailGrid) belong to fallback_tail_kernel
+
+// CUDA-event pair around one stage of vqb_forward when vqb_debug_kernel_timing(1) is on (else begin returns null, end is a no-op)
+void* stage_timing_begin(cudaStream_t s, int stage);
+void  stage_timing_end(void* slot, cudaStream_t s);
 
 void set_error(const char* fmt, ...);
 void note_launch(int n = 1);                       // counts this library's kernel launches (vqb_debug_launch_count)
@@ -104,6 +109,9 @@ cudaError_t launch_onehot(const int64_t* idx, int64_t N, int K, float* out, cuda
 cudaError_t launch_gather(const float* codebook, const int64_t* idx, int B, int D, int64_t W, int K, float* out, cudaStream_t s);
 cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int64_t pad_id, int64_t* tokens, float* mask,
                           cudaStream_t s);
+
+// 3-D TMA view of a [B, D, W] fp32 tensor (vqb_tc.cu): box = box_frames x box_dims of one batch item
+int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims);
 
 // ---- tensor-core search (vqb_tc.cu) ---------------------------------------------------------------------------
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.

@@ -6,6 +6,7 @@
 // All of these are HBM-bound: they read latents straight from the reference's [B, D, W] layout with frame-contiguous
 // (coalesced) accesses, transpose through padded shared memory, and touch every latent byte once per kernel.
 #include "vqb_internal.h"
+#include "vqb_ptx.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -507,6 +508,139 @@ cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, i
 // move one float4 (4 consecutive dims of one frame) per thread, the per-frame phase reads float4 rows - both are
 // bank-conflict free - and the codebook rows, residual atomics (red.v4) and shared accesses are all 16 bytes wide.
 // LPF lanes cooperate on one frame (32 / LPF frames per warp at a time), each lane owning 4*J dims.
+// One frame of a frame-major shared tile (LPF lanes cooperate, lane `sl` of the group owns dims 4*sl + 4*LPF*j): settle the
+// index (rescoring in fp32 in the reference's op order when more than one code is shortlisted), gather the codeword, write the
+// straight-through value back into the tile, accumulate SSE / histogram / residual sums, publish the index.
+// `given`: cl_lo.x already is the final code (exact search).  All 32 lanes of the warp must call this together.
+struct TailAcc { float sse, sse_c; unsigned int n_resc, n_short; };
+
+template <int LPF, int J, bool kResid>
+__device__ __forceinline__ void tail_frame(float* Xs, int ld, int f, int64_t n, bool live, int cnt_in, uint4 cl_lo, uint4 cl_hi, bool given,
+                                           const float* __restrict__ E, const float* __restrict__ e2, int D,
+                                           int64_t* __restrict__ idx_out, int* __restrict__ counts, float* __restrict__ resid,
+                                           bool resid_v4, int sl, TailAcc& acc) {
+    float& sse = acc.sse;
+    float& sse_c = acc.sse_c;
+    unsigned int& n_resc = acc.n_resc;
+    unsigned int& n_short = acc.n_short;
+    float4 xv[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int d = 4 * sl + 4 * LPF * j;
+        xv[j] = (d < D) ? *reinterpret_cast<const float4*>(Xs + f * ld + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int cnt = cnt_in;
+    int k = given ? (int)cl_lo.x : (int)(cl_lo.x & 0xFFFFu);
+    const bool need = live && cnt != kCandFinal && cnt > 1;
+    if (__any_sync(0xffffffffu, need)) {
+        // fp32 rescoring of the shortlisted codes in the reference's op order (whole warp takes part in shuffles)
+        float x2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            x2 = __fadd_rn(x2, __fmul_rn(xv[j].x, xv[j].x));
+            x2 = __fadd_rn(x2, __fmul_rn(xv[j].y, xv[j].y));
+            x2 = __fadd_rn(x2, __fmul_rn(xv[j].z, xv[j].z));
+            x2 = __fadd_rn(x2, __fmul_rn(xv[j].w, xv[j].w));
+        }
+        x2 = group_sum<LPF>(x2);
+        int cmax = need ? cnt : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        // shortlist entry ci out of the prefetched row (registers only: no dependent global load per round)
+        const uint32_t w8[8] = {cl_lo.x, cl_lo.y, cl_lo.z, cl_lo.w, cl_hi.x, cl_hi.y, cl_hi.z, cl_hi.w};
+        auto entry = [&](int ci) -> int {
+            const int wi = ci >> 1;
+            const uint32_t a01 = (wi & 1) ? w8[1] : w8[0], a23 = (wi & 1) ? w8[3] : w8[2];
+            const uint32_t a45 = (wi & 1) ? w8[5] : w8[4], a67 = (wi & 1) ? w8[7] : w8[6];
+            const uint32_t lo = (wi & 2) ? a23 : a01, hi = (wi & 2) ? a67 : a45;
+            const uint32_t wv = (wi & 4) ? hi : lo;
+            return (int)((ci & 1) ? (wv >> 16) : (wv & 0xFFFFu));
+        };
+        float bd = 0.f;
+        int bk = -1;
+        // rounds are software-pipelined: the codeword of round ci+1 is in flight while round ci is reduced
+        float4 ev[J], en[J];
+        int kc = (need && 0 < cnt) ? entry(0) : 0;
+        float e2c = e2[kc], e2n = 0.f;             // |e|^2 travels with its codeword: requested a round ahead as well
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int d = 4 * sl + 4 * LPF * j;
+            ev[j] = (d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kc * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int ci = 0; ci < cmax; ++ci) {
+            const bool act = need && ci < cnt;
+            const int kn = (need && ci + 1 < cnt) ? entry(ci + 1) : 0;
+            if (ci + 1 < cmax) {
+                e2n = e2[kn];
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int d = 4 * sl + 4 * LPF * j;
+                    en[j] = (d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kn * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                dot = fmaf(xv[j].x, ev[j].x, dot);
+                dot = fmaf(xv[j].y, ev[j].y, dot);
+                dot = fmaf(xv[j].z, ev[j].z, dot);
+                dot = fmaf(xv[j].w, ev[j].w, dot);
+            }
+            dot = group_sum<LPF>(dot);
+            if (act) {
+                const float dist = ref_distance(x2, e2c, dot);
+                if (better(dist, kc, bd, bk)) { bd = dist; bk = kc; }
+            }
+            kc = kn;
+            e2c = e2n;
+#pragma unroll
+            for (int j = 0; j < J; ++j) ev[j] = en[j];
+        }
+        if (need) {
+            k = bk;
+            if (sl == 0) { n_resc += 1; n_short += cnt; }
+        }
+    }
+    if (live && !need && sl == 0) n_short += 1;
+    if (live) {
+        const float* er = E + (size_t)k * D;
+        float4 qv[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int d = 4 * sl + 4 * LPF * j;
+            qv[j] = (d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float fs = 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int d = 4 * sl + 4 * LPF * j;
+            if (d < D) {
+                float4 df, st;
+                df.x = __fsub_rn(qv[j].x, xv[j].x); df.y = __fsub_rn(qv[j].y, xv[j].y);
+                df.z = __fsub_rn(qv[j].z, xv[j].z); df.w = __fsub_rn(qv[j].w, xv[j].w);
+                fs = fmaf(df.x, df.x, fs); fs = fmaf(df.y, df.y, fs); fs = fmaf(df.z, df.z, fs); fs = fmaf(df.w, df.w, fs);
+                st.x = __fadd_rn(xv[j].x, df.x); st.y = __fadd_rn(xv[j].y, df.y);      // straight-through VALUE (:48)
+                st.z = __fadd_rn(xv[j].z, df.z); st.w = __fadd_rn(xv[j].w, df.w);
+                *reinterpret_cast<float4*>(Xs + f * ld + d) = st;
+                if (kResid) {
+                    float* rp = resid + (size_t)k * D + d;
+                    if (resid_v4) red_add_v4(rp, -df.x, -df.y, -df.z, -df.w);
+                    else { atomicAdd(rp, -df.x); atomicAdd(rp + 1, -df.y); atomicAdd(rp + 2, -df.z); atomicAdd(rp + 3, -df.w); }
+                }
+            }
+        }
+        {   // Kahan: sse += fs
+            const float y = fs - sse_c, t = sse + y;
+            sse_c = (t - sse) - y;
+            sse = t;
+        }
+        if (sl == 0) {
+            atomicAdd(counts + k, 1);
+            idx_out[n] = (int64_t)k;
+        }
+    }
+}
+
 constexpr int TAIL_WARPS = 4;   // 128-thread blocks: more independent blocks per SM hide the load / barrier / gather latencies
 
 template <int LPF, int J, bool kResid>
@@ -525,8 +659,7 @@ __global__ void __launch_bounds__(32 * TAIL_WARPS, (J >= 6) ? 4 : 6) tail_kernel
     const int ld = D + 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPF, sl = lane % LPF;
-    float sse = 0.f, sse_c = 0.f;                 // Kahan-compensated per-thread SSE
-    unsigned int n_resc = 0, n_short = 0;
+    TailAcc acc{0.f, 0.f, 0u, 0u};                // Kahan-compensated per-thread SSE, diagnostics
     const bool resid_v4 = kResid && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;   // stats + K is 16B aligned iff K % 4 == 0
 
     auto tile_col = [&](int64_t tile, bool& valid) -> size_t {
@@ -582,127 +715,15 @@ __global__ void __launch_bounds__(32 * TAIL_WARPS, (J >= 6) ? 4 : 6) tail_kernel
         for (int it = 0; it < ITER; ++it) {
             const int f = warp * (TL_F / TAIL_WARPS) + it * FPW + sub;
             const int64_t n = tile * TL_F + f;
-            const bool live = n < N;
-            float4 xv[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int d = 4 * sl + 4 * LPF * j;
-                xv[j] = (d < D) ? *reinterpret_cast<const float4*>(Xs + f * ld + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const int cnt = cnt_r[it];
-            int k = idx32 ? (int)cl_lo[it].x : (int)(cl_lo[it].x & 0xFFFFu);
-            const bool need = live && cnt != kCandFinal && cnt > 1;
-            if (__any_sync(0xffffffffu, need)) {
-                // fp32 rescoring of the shortlisted codes in the reference's op order (whole warp takes part in shuffles)
-                float x2 = 0.f;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    x2 = __fadd_rn(x2, __fmul_rn(xv[j].x, xv[j].x));
-                    x2 = __fadd_rn(x2, __fmul_rn(xv[j].y, xv[j].y));
-                    x2 = __fadd_rn(x2, __fmul_rn(xv[j].z, xv[j].z));
-                    x2 = __fadd_rn(x2, __fmul_rn(xv[j].w, xv[j].w));
-                }
-                x2 = group_sum<LPF>(x2);
-                int cmax = need ? cnt : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-                // shortlist entry ci out of the prefetched row (registers only: no dependent global load per round)
-                const uint32_t w8[8] = {cl_lo[it].x, cl_lo[it].y, cl_lo[it].z, cl_lo[it].w, cl_hi[it].x, cl_hi[it].y, cl_hi[it].z, cl_hi[it].w};
-                auto entry = [&](int ci) -> int {
-                    const int wi = ci >> 1;
-                    const uint32_t a01 = (wi & 1) ? w8[1] : w8[0], a23 = (wi & 1) ? w8[3] : w8[2];
-                    const uint32_t a45 = (wi & 1) ? w8[5] : w8[4], a67 = (wi & 1) ? w8[7] : w8[6];
-                    const uint32_t lo = (wi & 2) ? a23 : a01, hi = (wi & 2) ? a67 : a45;
-                    const uint32_t wv = (wi & 4) ? hi : lo;
-                    return (int)((ci & 1) ? (wv >> 16) : (wv & 0xFFFFu));
-                };
-                float bd = 0.f;
-                int bk = -1;
-                // rounds are software-pipelined: the codeword of round ci+1 is in flight while round ci is reduced
-                float4 ev[J], en[J];
-                int kc = (need && 0 < cnt) ? entry(0) : 0;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const int d = 4 * sl + 4 * LPF * j;
-                    ev[j] = (d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kc * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                for (int ci = 0; ci < cmax; ++ci) {
-                    const bool act = need && ci < cnt;
-                    const int kn = (need && ci + 1 < cnt) ? entry(ci + 1) : 0;
-                    if (ci + 1 < cmax) {
-#pragma unroll
-                        for (int j = 0; j < J; ++j) {
-                            const int d = 4 * sl + 4 * LPF * j;
-                            en[j] = (d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kn * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
-                    float dot = 0.f;
-#pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        dot = fmaf(xv[j].x, ev[j].x, dot);
-                        dot = fmaf(xv[j].y, ev[j].y, dot);
-                        dot = fmaf(xv[j].z, ev[j].z, dot);
-                        dot = fmaf(xv[j].w, ev[j].w, dot);
-                    }
-                    dot = group_sum<LPF>(dot);
-                    if (act) {
-                        const float dist = ref_distance(x2, e2[kc], dot);
-                        if (better(dist, kc, bd, bk)) { bd = dist; bk = kc; }
-                    }
-                    kc = kn;
-#pragma unroll
-                    for (int j = 0; j < J; ++j) ev[j] = en[j];
-                }
-                if (need) {
-                    k = bk;
-                    if (sl == 0) { n_resc += 1; n_short += cnt; }
-                }
-            }
-            if (live && !need && sl == 0) n_short += 1;
-            if (live) {
-                const float* er = E + (size_t)k * D;
-                float4 qv[J];
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const int d = 4 * sl + 4 * LPF * j;
-                    qv[j] = (d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                float fs = 0.f;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const int d = 4 * sl + 4 * LPF * j;
-                    if (d < D) {
-                        float4 df, st;
-                        df.x = __fsub_rn(qv[j].x, xv[j].x); df.y = __fsub_rn(qv[j].y, xv[j].y);
-                        df.z = __fsub_rn(qv[j].z, xv[j].z); df.w = __fsub_rn(qv[j].w, xv[j].w);
-                        fs = fmaf(df.x, df.x, fs); fs = fmaf(df.y, df.y, fs); fs = fmaf(df.z, df.z, fs); fs = fmaf(df.w, df.w, fs);
-                        st.x = __fadd_rn(xv[j].x, df.x); st.y = __fadd_rn(xv[j].y, df.y);      // straight-through VALUE (:48)
-                        st.z = __fadd_rn(xv[j].z, df.z); st.w = __fadd_rn(xv[j].w, df.w);
-                        *reinterpret_cast<float4*>(Xs + f * ld + d) = st;
-                        if (kResid) {
-                            float* rp = resid + (size_t)k * D + d;
-                            if (resid_v4) red_add_v4(rp, -df.x, -df.y, -df.z, -df.w);
-                            else { atomicAdd(rp, -df.x); atomicAdd(rp + 1, -df.y); atomicAdd(rp + 2, -df.z); atomicAdd(rp + 3, -df.w); }
-                        }
-                    }
-                }
-                {   // Kahan: sse += fs
-                    const float y = fs - sse_c, t = sse + y;
-                    sse_c = (t - sse) - y;
-                    sse = t;
-                }
-                if (sl == 0) {
-                    atomicAdd(counts + k, 1);
-                    idx_out[n] = (int64_t)k;
-                }
-            }
+            tail_frame<LPF, J, kResid>(Xs, ld, f, n, n < N, cnt_r[it], cl_lo[it], cl_hi[it], idx32 != nullptr, E, e2, D, idx_out, counts,
+                                       resid, resid_v4, sl, acc);
         }
         if (q_out) {
             __syncthreads();
             tile_store<TAIL_WARPS>(Xs, ld, q_out, col, W, D, valid);
         }
     }
-    double t = (double)sse - (double)sse_c;
+    double t = (double)acc.sse - (double)acc.sse_c;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (lane == 0) red[warp] = t;
@@ -712,9 +733,135 @@ __global__ void __launch_bounds__(32 * TAIL_WARPS, (J >= 6) ? 4 : 6) tail_kernel
         for (int i = 0; i < TAIL_WARPS; ++i) s += red[i];
         sse_partials[blockIdx.x] = s;
     }
-    if (n_resc | n_short) {
-        atomicAdd(&meta->rescored, (unsigned long long)n_resc);
-        atomicAdd(&meta->shortlisted, (unsigned long long)n_short);
+    if (acc.n_resc | acc.n_short) {
+        atomicAdd(&meta->rescored, (unsigned long long)acc.n_resc);
+        atomicAdd(&meta->shortlisted, (unsigned long long)acc.n_short);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused tail, TMA-fed
+// Same per-frame work as tail_kernel, but the latents arrive by TMA: persistent blocks walk tiles of 32 frames of one batch
+// item; a 3-D TMA box [D dims][32 frames] of the NEXT tile is in flight (per block) while the current one is transposed from
+// the box into the frame-major tile, worked on and written back.  No thread ever waits on a global latent load, which is what
+// bounded tail_kernel (latency, 25 % occupancy).  Needs W % 4 == 0 (TMA global strides are multiples of 16 bytes).
+// NW warps per block, NB box buffers (1: the next box is requested right after the transposition freed the buffer).
+template <int LPF, int J, bool kResid, int NW, int NB>
+__global__ void __launch_bounds__(32 * NW, (NW == 4) ? 3 : ((J >= 6) ? 2 : 3))
+tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restrict__ E, const float* __restrict__ e2, int D, int64_t W,
+                int tiles_per_item, int64_t num_tiles, int box_dims, const int* __restrict__ idx32,
+                const uint8_t* __restrict__ cand_cnt, const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
+                float* __restrict__ q_out, int* __restrict__ counts, float* __restrict__ resid,
+                double* __restrict__ sse_partials, WsMeta* meta) {
+    using namespace ptx;
+    constexpr int TT_WARPS = NW;
+    extern __shared__ __align__(128) float tt_smem[];   // NB x [D][32] TMA boxes, then the frame-major tile [32][D + 4]
+    __shared__ double red[TT_WARPS];
+    __shared__ __align__(8) unsigned long long full[2];
+    constexpr int FPW = 32 / LPF;                       // frames a warp works on at once
+    constexpr int ITER = (TL_F / TT_WARPS) / FPW;       // rounds per warp and tile
+    static_assert(ITER >= 1, "a warp must own at least FPW frames of the tile");
+    const int ld = D + 4;
+    float* box = tt_smem;
+    float* Xs = tt_smem + NB * (size_t)D * TL_F;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPF, sl = lane % LPF;
+    TailAcc acc{0.f, 0.f, 0u, 0u};
+    const bool resid_v4 = kResid && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;
+    const uint32_t box_bytes = (uint32_t)D * TL_F * 4;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&full[0]), 1);
+        mbar_init(smem_u32(&full[1]), 1);
+        fence_barrier_init();
+        prefetch_tmap(&tmap_z);
+    }
+    __syncthreads();
+    auto issue = [&](int64_t tile, int buf) {           // one thread: the whole [D][32] box of `tile` (frames past W arrive as zeros)
+        const int b = (int)(tile / tiles_per_item), w0 = (int)(tile - (int64_t)b * tiles_per_item) * TL_F;
+        const uint32_t bar = smem_u32(&full[buf]);
+        mbar_expect_tx(bar, box_bytes);
+        for (int d0 = 0; d0 < D; d0 += box_dims)
+            tma_load_3d(smem_u32(box + ((size_t)buf * D + d0) * TL_F), &tmap_z, bar, w0, d0, b);
+    };
+    int64_t tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < num_tiles) issue(tile, 0);
+    for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = NB == 2 ? (it & 1) : 0;
+        const int b = (int)(tile / tiles_per_item), w0 = (int)(tile - (int64_t)b * tiles_per_item) * TL_F;
+        const int64_t n0 = (int64_t)b * W + w0;           // global frame id of the tile's first frame
+        const int wlim = (int)((W - w0) < TL_F ? (W - w0) : TL_F);   // frames of this tile that exist
+        // shortlist headers of this warp's frames, requested early so their latency hides behind the box wait
+        int cnt_r[ITER];
+        uint4 cl_lo[ITER], cl_hi[ITER];
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int f = warp * (TL_F / TT_WARPS) + i * FPW + sub;
+            cnt_r[i] = 0;
+            cl_lo[i] = make_uint4(0u, 0u, 0u, 0u);
+            cl_hi[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (f < wlim) {
+                const int64_t n = n0 + f;
+                if (idx32) { cnt_r[i] = kCandFinal; cl_lo[i].x = (uint32_t)idx32[n]; }
+                else {
+                    cnt_r[i] = cand_cnt[n];
+                    const uint4* row = reinterpret_cast<const uint4*>(cand_idx + (size_t)n * kCandMax);
+                    cl_lo[i] = row[0];
+                    cl_hi[i] = row[1];
+                }
+            }
+        }
+        // the other box was transposed in the previous iteration (block-wide barriers since): refill it with the next tile
+        const int64_t next = tile + gridDim.x;
+        if (NB == 2 && threadIdx.x == 0 && next < num_tiles) issue(next, buf ^ 1);
+        mbar_wait(smem_u32(&full[buf]), NB == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u));
+        {   // box [d][32 frames] -> frame-major tile: 4 conflict-free LDS.32 + one conflict-free STS.128 per 4 dims
+            const float* bx = box + (size_t)buf * D * TL_F + lane;
+            for (int d0 = warp * 4; d0 < D; d0 += 4 * TT_WARPS) {
+                float4 v;
+                v.x = bx[(d0 + 0) * TL_F];
+                v.y = bx[(d0 + 1) * TL_F];
+                v.z = bx[(d0 + 2) * TL_F];
+                v.w = bx[(d0 + 3) * TL_F];
+                *reinterpret_cast<float4*>(Xs + lane * ld + d0) = v;
+            }
+        }
+        __syncthreads();
+        if (NB == 1 && threadIdx.x == 0 && next < num_tiles) issue(next, 0);   // the box has been consumed: refill it behind the compute
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int f = warp * (TL_F / TT_WARPS) + i * FPW + sub;
+            tail_frame<LPF, J, kResid>(Xs, ld, f, n0 + f, f < wlim, cnt_r[i], cl_lo[i], cl_hi[i], idx32 != nullptr, E, e2, D, idx_out, counts,
+                                       resid, resid_v4, sl, acc);
+        }
+        if (q_out) {
+            __syncthreads();
+            if (lane < wlim) {
+                float* qp = q_out + (size_t)b * D * W + w0 + lane;
+                for (int d0 = warp * 4; d0 < D; d0 += 4 * TT_WARPS) {
+                    const float4 v = *reinterpret_cast<const float4*>(Xs + lane * ld + d0);
+                    float* p = qp + (size_t)d0 * W;
+                    st_stream(p, v.x);
+                    st_stream(p + W, v.y);
+                    st_stream(p + 2 * W, v.z);
+                    st_stream(p + 3 * W, v.w);
+                }
+            }
+        }
+        __syncthreads();                                  // the tile may be overwritten, the box refilled
+    }
+    double t = (double)acc.sse - (double)acc.sse_c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) red[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < TT_WARPS; ++i) s += red[i];
+        sse_partials[blockIdx.x] = s;
+    }
+    if (acc.n_resc | acc.n_short) {
+        atomicAdd(&meta->rescored, (unsigned long long)acc.n_resc);
+        atomicAdd(&meta->shortlisted, (unsigned long long)acc.n_short);
     }
 }
 
@@ -748,16 +895,65 @@ static cudaError_t launch_tail_t(const float* z, const float* codebook, const fl
     return cudaGetLastError();
 }
 
+static int tail_tma_variant() {   // experiments: VQB_TAIL_VARIANT=0: 8 warps, 2 boxes (default); 1: 4 warps, 1 box (3 blocks per SM at D = 256)
+    if (const char* env = getenv("VQB_TAIL_VARIANT")) return atoi(env);
+    return 0;
+}
+static bool tail_tma_enabled() {   // VQB_TAIL_TMA=0 keeps the register-staged tail_kernel (experiments)
+    if (const char* env = getenv("VQB_TAIL_TMA")) return env[0] != '0';
+    return true;
+}
+
+template <int LPF, int J, int NW, int NB>
+static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebook, const float* e2, int D, int64_t W, int tiles_per_item,
+                                     int64_t num_tiles, int box_dims, const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx,
+                                     int64_t* idx_out, float* q_out, int* counts, float* resid, double* part, int n_partials, WsMeta* meta,
+                                     cudaStream_t s) {
+    const size_t smem = (size_t)(NB * D * TL_F + TL_F * (D + 4)) * 4;
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        int per_sm = 1, dev = 0, sms = 148;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW, smem)) != cudaSuccess) return e;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int64_t grid = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+        if (grid > n_partials) grid = n_partials;
+        if (grid > num_tiles) grid = num_tiles;
+        if (grid < 1) grid = 1;
+        kernel<<<(unsigned)grid, 32 * NW, smem, s>>>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx,
+                                                           idx_out, q_out, counts, resid, part, meta);
+        return cudaGetLastError();
+    };
+    return resid ? go(tail_tma_kernel<LPF, J, true, NW, NB>) : go(tail_tma_kernel<LPF, J, false, NW, NB>);
+}
+
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                         int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, cudaStream_t s) {
     const int64_t N = (int64_t)B * W;
-    const int64_t tiles = (N + TL_F - 1) / TL_F;
-    int64_t grid = n_partials < tiles ? n_partials : tiles;
-    if (grid < 1) grid = 1;
     cudaError_t e = cudaMemsetAsync(sse_partials, 0, (size_t)n_partials * sizeof(double), s);
     if (e != cudaSuccess) return e;
     double* part = reinterpret_cast<double*>(sse_partials);
+    if (tail_tma_enabled() && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+        // TMA-fed tail: tiles of 32 frames that never straddle a batch item
+        const int box_dims = D <= 256 ? D : D / 2;
+        CUtensorMap map;
+        if (make_latent_map(&map, z, (uint64_t)B, (uint64_t)D, (uint64_t)W, TL_F, (uint32_t)box_dims) != 0) return cudaErrorInvalidValue;
+        const int tiles_per_item = (int)((W + TL_F - 1) / TL_F);
+        const int64_t num_tiles = (int64_t)B * tiles_per_item;
+#define VQB_TAIL_TMA(LPF, J) e = launch_tail_tma_t<LPF, J, 8, 2>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta, s)
+#define VQB_TAIL_TMA41(LPF, J) e = launch_tail_tma_t<LPF, J, 4, 1>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta, s)
+        if (tail_tma_variant() == 1) VQB_DISPATCH_D8(D, VQB_TAIL_TMA41);
+        else VQB_DISPATCH_D8(D, VQB_TAIL_TMA);
+#undef VQB_TAIL_TMA
+#undef VQB_TAIL_TMA41
+        note_launch();
+        return e;
+    }
+    const int64_t tiles = (N + TL_F - 1) / TL_F;
+    int64_t grid = n_partials < tiles ? n_partials : tiles;
+    if (grid < 1) grid = 1;
     const int g = (int)grid;
 #define VQB_TAIL(LPF, J) e = launch_tail_t<LPF, J>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, g, meta, s)
     VQB_DISPATCH_D8(D, VQB_TAIL);   // measured: 8 lanes per frame beat 16 for the tail at D = 256 (0.91 vs 1.09 ms per 2^20 frames)

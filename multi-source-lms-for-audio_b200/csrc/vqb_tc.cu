@@ -21,6 +21,7 @@
 //               accumulator stages (2 x 256 columns) so the epilogue of tile j overlaps the MMAs of tile j+1
 //   warp 18     TMEM allocator
 #include "vqb_internal.h"
+#include "vqb_ptx.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -73,51 +74,8 @@ struct Barriers {
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a pipeline bug must become a trapped launch, never a hung GPU.  try_wait carries a suspend-time hint, so
-// a waiting warp sleeps in hardware (and is woken by the completing arrive) instead of burning issue slots that the
-// single-thread producer / MMA loops on the same scheduler need.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    long long t0 = 0;
-    for (uint32_t it = 0;; ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity), "r"(0x989680u)
-            : "memory");
-        if (ok) return;
-        if ((it & 63u) == 63u) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000LL) __trap();   // seconds: only a broken pipeline gets here
-        }
-    }
-}
-// One lane of a converged warp; ptxas recognises the elect.sync predicate and issues the following tcgen05 / TMA
-// instructions directly instead of wrapping each one in an elect-and-retry loop.
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// (mbarrier / elect / TMA basics shared with the stand-alone tail kernel: vqb_ptx.cuh)
+using namespace ptx;
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -132,12 +90,6 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 // 2-CTA (cta_group::2) variants.  The pair's leader (cluster rank 0) owns the "full" barriers: both CTAs' TMA loads
@@ -169,9 +121,6 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
                  : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t cols) {
@@ -1100,13 +1049,21 @@ static int make_map_eh(CUtensorMap* map, const void* base, uint64_t rows) {
     return 0;
 }
 
-// fp32 latents in the reference's [B, D, W] layout: box = 128 frames x 16 dims of one batch item, zero fill past W
+// fp32 latents in the reference's [B, D, W] layout: box = 128 frames x box_dims dims of one batch item, zero fill past W
 static int make_map_z(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_dims = SUB_DIMS) {
-    EncodeTiledFn fn = get_encode_fn();
+    return make_latent_map(map, z, B, D, W, (uint32_t)BM, box_dims);
+}
+
+}  // namespace tc
+
+// 3-D TMA view of the [B, D, W] fp32 latents (or of `quantized`): box = box_frames x box_dims x 1, out-of-range frames read as
+// zeros and are clipped on stores.  Needs 16-byte global strides: W % 4 == 0 and a 16-byte aligned base.
+int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims) {
+    tc::EncodeTiledFn fn = tc::get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VQB_E_DEVICE; }
     const cuuint64_t dims[3] = {W, D, B};
     const cuuint64_t strides[2] = {W * 4, D * W * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)BM, box_dims, 1};
+    const cuuint32_t box[3] = {box_frames, box_dims, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(z), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1114,8 +1071,6 @@ static int make_map_z(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, 
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(z) failed with CUresult %d", (int)r); return 1000 + (int)r; }
     return 0;
 }
-
-}  // namespace tc
 
 bool tc_can_fuse(const float* z, int B, int D, int64_t W) {
     (void)B;
@@ -1135,26 +1090,29 @@ bool tc_fused_tail_enabled() {
 
 size_t tc_event_scratch_bytes() { return (size_t)kTcMaxCtas * tc::EPI_THREADS * tc::EV_CAP * tc::EV_WORDS * 4; }
 
-// ---- optional CUDA-event timing of the dominant kernel, on the launching stream (bench.py's roofline leg) -------
-struct TimingSlot { cudaEvent_t start, stop; };
+// ---- optional CUDA-event timing of the stages of vqb_forward, on the launching stream (bench.py's roofline leg) -------
+struct TimingSlot { cudaEvent_t start, stop; int stage; };
 static bool g_timing = false;
-static TimingSlot g_slots[512];
+static TimingSlot g_slots[2048];
 static int g_slots_used = 0, g_slots_made = 0;
 
-static TimingSlot* timing_begin(cudaStream_t s) {
-    if (!g_timing || g_slots_used >= 512) return nullptr;
+void* stage_timing_begin(cudaStream_t s, int stage) {
+    if (!g_timing || g_slots_used >= 2048) return nullptr;
     if (g_slots_used >= g_slots_made) {
         if (cudaEventCreate(&g_slots[g_slots_made].start) != cudaSuccess || cudaEventCreate(&g_slots[g_slots_made].stop) != cudaSuccess)
             return nullptr;
         ++g_slots_made;
     }
     TimingSlot* t = &g_slots[g_slots_used++];
+    t->stage = stage;
     cudaEventRecord(t->start, s);
     return t;
 }
-static void timing_end(TimingSlot* t, cudaStream_t s) {
-    if (t) cudaEventRecord(t->stop, s);
+void stage_timing_end(void* slot, cudaStream_t s) {
+    if (slot) cudaEventRecord(static_cast<TimingSlot*>(slot)->stop, s);
 }
+static TimingSlot* timing_begin(cudaStream_t s) { return static_cast<TimingSlot*>(stage_timing_begin(s, VQB_STAGE_SEARCH)); }
+static void timing_end(TimingSlot* t, cudaStream_t s) { stage_timing_end(t, s); }
 
 int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh,
                      const float* band, int64_t N, int64_t N_pad, int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx,
@@ -1258,26 +1216,31 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
 }  // namespace vqb
 
 extern "C" {
-// enable != 0: record a CUDA-event pair around every tc_search_kernel launch from now on (and forget earlier ones)
+// enable != 0: record a CUDA-event pair around every stage of vqb_forward from now on (and forget earlier ones)
 int vqb_debug_kernel_timing(int enable) {
     vqb::g_timing = enable != 0;
     vqb::g_slots_used = 0;
     return 0;
 }
-// total milliseconds and number of timed tc_search_kernel launches since timing was enabled (synchronises the events)
-int vqb_debug_kernel_time_ms(double* total_ms, int* launches) {
-    if (!total_ms || !launches) { vqb::set_error("vqb_debug_kernel_time_ms: NULL output"); return VQB_E_NULL; }
+// total milliseconds and number of timed launches of one stage (VQB_STAGE_*) since timing was enabled (synchronises the events)
+int vqb_debug_stage_time_ms(int stage, double* total_ms, int* launches) {
+    if (!total_ms || !launches) { vqb::set_error("vqb_debug_stage_time_ms: NULL output"); return VQB_E_NULL; }
     double t = 0.0;
+    int n = 0;
     for (int i = 0; i < vqb::g_slots_used; ++i) {
+        if (vqb::g_slots[i].stage != stage) continue;
         cudaError_t e = cudaEventSynchronize(vqb::g_slots[i].stop);
         if (e != cudaSuccess) return vqb::cuda_fail(e, "cudaEventSynchronize");
         float ms = 0.f;
         e = cudaEventElapsedTime(&ms, vqb::g_slots[i].start, vqb::g_slots[i].stop);
         if (e != cudaSuccess) return vqb::cuda_fail(e, "cudaEventElapsedTime");
         t += ms;
+        ++n;
     }
     *total_ms = t;
-    *launches = vqb::g_slots_used;
+    *launches = n;
     return 0;
 }
+// the dominant kernel (tc_search_kernel): VQB_STAGE_SEARCH
+int vqb_debug_kernel_time_ms(double* total_ms, int* launches) { return vqb_debug_stage_time_ms(VQB_STAGE_SEARCH, total_ms, launches); }
 }
