@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-resid", action="store_true", help="diagnostic: skip the per-code residual statistics")
     ap.add_argument("--no-q", action="store_true", help="diagnostic: index export only (no quantized output)")
+    ap.add_argument("--no-sampler", action="store_true", help="diagnostic: do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -210,7 +211,7 @@ def main():
     del out
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_sampler:
         sampler.start()
     lib.vqb_debug_kernel_timing(1)
     lib.vqb_debug_launch_count(1)

@@ -38,6 +38,7 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags) {
     L.e2 = take((size_t)L.k_pad * 4);
     L.counts = take((size_t)K * 4);
     L.sse_partials = take((size_t)L.n_partials * 8);
+    L.resid_rep = (flags & VQB_WANT_RESID) ? take((size_t)(kResidReplicasMax - 1) * K * D * 4) : 0;
     if (prec == VQB_PREC_FP32) {
         L.idx32 = take((size_t)N * 4);
         L.cand_cnt = L.cand_idx = L.fallback_rows = L.best64 = L.x2 = L.eb = L.eh = L.xb = L.ev = 0;
@@ -128,6 +129,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
     int* counts = reinterpret_cast<int*>(ws + L.counts);
     float* part = reinterpret_cast<float*>(ws + L.sse_partials);
     float* resid = (flags & VQB_WANT_RESID) ? stats_out + K : nullptr;
+    float* resid_rep = resid ? reinterpret_cast<float*>(ws + L.resid_rep) : nullptr;
 
     void* tprep = stage_timing_begin(s, VQB_STAGE_PREP);
     if (!accumulate) {
@@ -147,7 +149,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         stage_timing_end(t0, s);
         void* t1 = stage_timing_begin(s, VQB_STAGE_TAIL);
         VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, idx32, nullptr, nullptr, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
-                             counts, resid, part, L.n_partials, meta, s), "tail");
+                             counts, resid, part, L.n_partials, meta, resid_rep, s), "tail");
         stage_timing_end(t1, s);
     } else {
         uint8_t* cand_cnt = reinterpret_cast<uint8_t*>(ws + L.cand_cnt);
@@ -183,7 +185,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
             stage_timing_end(tfb, s);
             void* tt = stage_timing_begin(s, VQB_STAGE_TAIL);
             VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, nullptr, cand_cnt, cand_idx, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
-                                 counts, resid, part, L.n_partials, meta, s), "tail");
+                                 counts, resid, part, L.n_partials, meta, resid_rep, s), "tail");
             stage_timing_end(tt, s);
         }
     }

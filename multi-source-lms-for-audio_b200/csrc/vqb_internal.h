@@ -29,7 +29,7 @@ struct WsMeta {
 };
 
 struct WsLayout {
-    size_t meta, e2, counts, sse_partials, idx32, cand_cnt, cand_idx, fallback_rows, best64, x2, eb, eh, xb, ev, total;
+    size_t meta, e2, counts, sse_partials, resid_rep, idx32, cand_cnt, cand_idx, fallback_rows, best64, x2, eb, eh, xb, ev, total;
     int    k_pad;
     int64_t n_pad;
     int    n_partials;
@@ -39,6 +39,7 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags);
 constexpr int kTcMaxCtas = 160;         // persistent grid bound of the tensor-core search (event scratch is sized for it)
 size_t tc_event_scratch_bytes();
 constexpr int kTailGridMax = 148 * 8;   // persistent grid of the fused tail kernel (sse partial slots)
+constexpr int kResidReplicasMax = 8;     // residual-sum replicas against same-address atomic serialisation (see pick_resid_replica)
 constexpr int kFallbackTailGrid = 148;  // fused-tail mode: sse slots [kTcMaxCtas, kTcMaxCtas + kFallbackTailGrid) belong to fallback_tail_kernel
 
 // CUDA-event pair around one stage of vqb_forward when vqb_debug_kernel_timing(1) is on (else begin returns null, end is a no-op)
@@ -92,7 +93,8 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
                                 unsigned long long* best64, cudaStream_t s);
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
-                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, cudaStream_t s);
+                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s);
+int resid_replicas();   // copies of the residual sums the tail kernels spread their atomics over (workspace holds kResidReplicasMax - 1)
 // fused-tail mode: finishes the (rare) frames the exact fallback search decided - one warp per frame of the list
 cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, int D, int64_t W, int K, const int* rows,
                                  const int* row_count, const unsigned long long* best64, int64_t* idx_out, float* q_out, int* counts,
@@ -110,8 +112,10 @@ cudaError_t launch_gather(const float* codebook, const int64_t* idx, int B, int 
 cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int64_t pad_id, int64_t* tokens, float* mask,
                           cudaStream_t s);
 
-// 3-D TMA view of a [B, D, W] fp32 tensor (vqb_tc.cu): box = box_frames x box_dims of one batch item
-int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims);
+// 3-D TMA view of a [B, D, W] fp32 tensor (vqb_tc.cu): box = box_frames x box_dims of one batch item; swizzle128 needs
+// box_frames == 32 (128-byte rows) and a 1024-byte aligned destination
+int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims,
+                    bool swizzle128 = false);
 
 // ---- tensor-core search (vqb_tc.cu) ---------------------------------------------------------------------------
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.

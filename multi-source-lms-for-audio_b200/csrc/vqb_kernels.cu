@@ -508,6 +508,27 @@ cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, i
 // move one float4 (4 consecutive dims of one frame) per thread, the per-frame phase reads float4 rows - both are
 // bank-conflict free - and the codebook rows, residual atomics (red.v4) and shared accesses are all 16 bytes wide.
 // LPF lanes cooperate on one frame (32 / LPF frames per warp at a time), each lane owning 4*J dims.
+// Residual-sum replicas.  Every frame adds its D residuals to the row of its code with atomics; the L2 serialises atomics
+// per address, so the most popular code bounds the whole pass (measured: 8 of 20 ms at BASELINE config 3 with a code that
+// takes ~1.5 % of the frames).  The blocks of different SMs therefore add into one of n_rep copies (copy 0 is the caller's
+// buffer, the others live in the workspace) and fold_resid_kernel sums the copies afterwards.
+__device__ __forceinline__ float* pick_resid_replica(float* resid, float* resid_rep, int n_rep, size_t rep_stride) {
+    if (!resid || n_rep <= 1) return resid;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned int r = smid % (unsigned int)n_rep;
+    return r ? resid_rep + (size_t)(r - 1) * rep_stride : resid;
+}
+__global__ void __launch_bounds__(256) fold_resid_kernel(float* __restrict__ resid, const float* __restrict__ resid_rep, int n_rep,
+                                                         size_t rep_stride) {
+    // the caller's buffer (stats + K) is only 4-byte aligned when K % 4 != 0: plain scalar accesses, the arrays are small
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < rep_stride; i += (size_t)gridDim.x * 256) {
+        float a = resid[i];
+        for (int r = 0; r + 1 < n_rep; ++r) a += resid_rep[(size_t)r * rep_stride + i];
+        resid[i] = a;
+    }
+}
+
 // One frame of a frame-major shared tile (LPF lanes cooperate, lane `sl` of the group owns dims 4*sl + 4*LPF*j): settle the
 // index (rescoring in fp32 in the reference's op order when more than one code is shortlisted), gather the codeword, write the
 // straight-through value back into the tile, accumulate SSE / histogram / residual sums, publish the index.
@@ -650,7 +671,8 @@ __global__ void __launch_bounds__(32 * TAIL_WARPS, (J >= 6) ? 4 : 6) tail_kernel
                                                       const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
                                                       float* __restrict__ q_out, int* __restrict__ counts,
                                                       float* __restrict__ resid, double* __restrict__ sse_partials,
-                                                      WsMeta* meta, int ldg) {
+                                                      WsMeta* meta, float* resid_rep, int n_rep, size_t rep_stride, int ldg) {
+    resid = pick_resid_replica(resid, resid_rep, n_rep, rep_stride);
     extern __shared__ __align__(16) float Xbuf[];   // 2 x [32][D + 4]: the next tile streams in while this one is worked on
     __shared__ double red[TAIL_WARPS];
     constexpr int FPW = 32 / LPF;                 // frames a warp works on at once
@@ -751,7 +773,8 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restr
                 int tiles_per_item, int64_t num_tiles, int box_dims, const int* __restrict__ idx32,
                 const uint8_t* __restrict__ cand_cnt, const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
                 float* __restrict__ q_out, int* __restrict__ counts, float* __restrict__ resid,
-                double* __restrict__ sse_partials, WsMeta* meta) {
+                double* __restrict__ sse_partials, WsMeta* meta, float* resid_rep, int n_rep, size_t rep_stride) {
+    resid = pick_resid_replica(resid, resid_rep, n_rep, rep_stride);
     using namespace ptx;
     constexpr int TT_WARPS = NW;
     extern __shared__ __align__(128) float tt_smem[];   // NB x [D][32] TMA boxes, then the frame-major tile [32][D + 4]
@@ -880,24 +903,33 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restr
 template <int LPF, int J>
 static cudaError_t launch_tail_t(const float* z, const float* codebook, const float* e2, int D, int64_t W, int64_t N, int K,
                                  const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
-                                 int* counts, float* resid, double* part, int grid, WsMeta* meta, cudaStream_t s) {
+                                 int* counts, float* resid, double* part, int grid, WsMeta* meta, float* resid_rep, int n_rep,
+                                 size_t rep_stride, cudaStream_t s) {
     const size_t smem = (size_t)(tile_ldg_mode() ? 1 : 2) * TL_F * (D + 4) * 4;   // the second buffer only serves the cp.async pipeline
     cudaError_t e;
     if (resid) {
         if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
         tail_kernel<LPF, J, true><<<grid, 32 * TAIL_WARPS, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
-                                                          resid, part, meta, tile_ldg_mode());
+                                                          resid, part, meta, resid_rep, n_rep, rep_stride, tile_ldg_mode());
     } else {
         if ((e = cudaFuncSetAttribute(tail_kernel<LPF, J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
         tail_kernel<LPF, J, false><<<grid, 32 * TAIL_WARPS, smem, s>>>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts,
-                                                           nullptr, part, meta, tile_ldg_mode());
+                                                           nullptr, part, meta, nullptr, 1, 0, tile_ldg_mode());
     }
     return cudaGetLastError();
 }
 
-static int tail_tma_variant() {   // experiments: VQB_TAIL_VARIANT=0: 8 warps, 2 boxes (default); 1: 4 warps, 1 box (3 blocks per SM at D = 256)
+int resid_replicas() {   // 1..kResidReplicasMax copies of the residual sums (VQB_RESID_REPLICAS, experiments)
+    if (const char* env = getenv("VQB_RESID_REPLICAS")) { const int v = atoi(env); if (v >= 1 && v <= kResidReplicasMax) return v; }
+    return 2;   // measured at BASELINE config 3: 21.0 ms with one copy, 13.7 ms with two, no further gain from four or eight
+}
+// VQB_TAIL_VARIANT (experiments): 1 (default) = 4 warps and one box per block (3 blocks per SM at D = 256: 13.7 ms in the
+// BASELINE config 3 step), 0 = 8 warps and two boxes (2 blocks per SM: 14.6 ms).  A third form without block barriers (every
+// warp transposing its own 8 frames out of a 128-byte-swizzled box, rescoring pairs dealt out over the lane groups) measured
+// 14.7 ms and was dropped: after the residual replicas the pass is bound by its L2 / DRAM traffic, not by the barriers.
+static int tail_tma_variant() {
     if (const char* env = getenv("VQB_TAIL_VARIANT")) return atoi(env);
-    return 0;
+    return 1;
 }
 static bool tail_tma_enabled() {   // VQB_TAIL_TMA=0 keeps the register-staged tail_kernel (experiments)
     if (const char* env = getenv("VQB_TAIL_TMA")) return env[0] != '0';
@@ -908,7 +940,7 @@ template <int LPF, int J, int NW, int NB>
 static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebook, const float* e2, int D, int64_t W, int tiles_per_item,
                                      int64_t num_tiles, int box_dims, const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx,
                                      int64_t* idx_out, float* q_out, int* counts, float* resid, double* part, int n_partials, WsMeta* meta,
-                                     cudaStream_t s) {
+                                     float* resid_rep, int n_rep, size_t rep_stride, cudaStream_t s) {
     const size_t smem = (size_t)(NB * D * TL_F + TL_F * (D + 4)) * 4;
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -922,7 +954,7 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
         if (grid > num_tiles) grid = num_tiles;
         if (grid < 1) grid = 1;
         kernel<<<(unsigned)grid, 32 * NW, smem, s>>>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx,
-                                                           idx_out, q_out, counts, resid, part, meta);
+                                                           idx_out, q_out, counts, resid, part, meta, resid_rep, n_rep, rep_stride);
         return cudaGetLastError();
     };
     return resid ? go(tail_tma_kernel<LPF, J, true, NW, NB>) : go(tail_tma_kernel<LPF, J, false, NW, NB>);
@@ -930,11 +962,21 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
 
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
-                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, cudaStream_t s) {
+                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s) {
     const int64_t N = (int64_t)B * W;
     cudaError_t e = cudaMemsetAsync(sse_partials, 0, (size_t)n_partials * sizeof(double), s);
     if (e != cudaSuccess) return e;
     double* part = reinterpret_cast<double*>(sse_partials);
+    const size_t rep_stride = (size_t)K * D;
+    int n_rep = (resid && resid_rep) ? resid_replicas() : 1;
+    if (n_rep > 1 && (e = cudaMemsetAsync(resid_rep, 0, (size_t)(n_rep - 1) * rep_stride * 4, s)) != cudaSuccess) return e;
+    auto fold = [&]() -> cudaError_t {            // sum the residual replicas into the caller's buffer
+        if (n_rep <= 1) return cudaSuccess;
+        const size_t blocks = (rep_stride + 255) / 256;
+        fold_resid_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, s>>>(resid, resid_rep, n_rep, rep_stride);
+        note_launch();
+        return cudaGetLastError();
+    };
     if (tail_tma_enabled() && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
         // TMA-fed tail: tiles of 32 frames that never straddle a batch item
         const int box_dims = D <= 256 ? D : D / 2;
@@ -942,24 +984,24 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
         if (make_latent_map(&map, z, (uint64_t)B, (uint64_t)D, (uint64_t)W, TL_F, (uint32_t)box_dims) != 0) return cudaErrorInvalidValue;
         const int tiles_per_item = (int)((W + TL_F - 1) / TL_F);
         const int64_t num_tiles = (int64_t)B * tiles_per_item;
-#define VQB_TAIL_TMA(LPF, J) e = launch_tail_tma_t<LPF, J, 8, 2>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta, s)
-#define VQB_TAIL_TMA41(LPF, J) e = launch_tail_tma_t<LPF, J, 4, 1>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta, s)
+#define VQB_TAIL_TMA(LPF, J) e = launch_tail_tma_t<LPF, J, 8, 2>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta, resid_rep, n_rep, rep_stride, s)
+#define VQB_TAIL_TMA41(LPF, J) e = launch_tail_tma_t<LPF, J, 4, 1>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta, resid_rep, n_rep, rep_stride, s)
         if (tail_tma_variant() == 1) VQB_DISPATCH_D8(D, VQB_TAIL_TMA41);
         else VQB_DISPATCH_D8(D, VQB_TAIL_TMA);
 #undef VQB_TAIL_TMA
 #undef VQB_TAIL_TMA41
         note_launch();
-        return e;
+        return e != cudaSuccess ? e : fold();
     }
     const int64_t tiles = (N + TL_F - 1) / TL_F;
     int64_t grid = n_partials < tiles ? n_partials : tiles;
     if (grid < 1) grid = 1;
     const int g = (int)grid;
-#define VQB_TAIL(LPF, J) e = launch_tail_t<LPF, J>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, g, meta, s)
+#define VQB_TAIL(LPF, J) e = launch_tail_t<LPF, J>(z, codebook, e2, D, W, N, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, g, meta, resid_rep, n_rep, rep_stride, s)
     VQB_DISPATCH_D8(D, VQB_TAIL);   // measured: 8 lanes per frame beat 16 for the tail at D = 256 (0.91 vs 1.09 ms per 2^20 frames)
 #undef VQB_TAIL
     note_launch();
-    return e;
+    return e != cudaSuccess ? e : fold();
 }
 
 // counts (int) and SSE partials (double) -> the fp32 statistics buffer [counts | resid | SSE | N]

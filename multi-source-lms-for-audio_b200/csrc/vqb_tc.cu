@@ -1058,7 +1058,8 @@ static int make_map_z(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, 
 
 // 3-D TMA view of the [B, D, W] fp32 latents (or of `quantized`): box = box_frames x box_dims x 1, out-of-range frames read as
 // zeros and are clipped on stores.  Needs 16-byte global strides: W % 4 == 0 and a 16-byte aligned base.
-int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims) {
+int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims,
+                    bool swizzle128) {
     tc::EncodeTiledFn fn = tc::get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VQB_E_DEVICE; }
     const cuuint64_t dims[3] = {W, D, B};
@@ -1066,8 +1067,8 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
     const cuuint32_t box[3] = {box_frames, box_dims, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(z), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(z) failed with CUresult %d", (int)r); return 1000 + (int)r; }
     return 0;
 }
