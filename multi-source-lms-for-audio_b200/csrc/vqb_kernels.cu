@@ -1130,15 +1130,107 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(cons
     }
 }
 
+// Second form of dX: only the codeword term needs a gather, so only the codewords are transposed.  Per tile of 32 frames of one
+// batch item: the 32 selected codebook rows are fetched with coalesced 16-byte loads (8 lanes per row) and written transposed
+// into Es[d][33] (conflict-free), then every warp streams whole latent rows in the tensors' own [B, D, W] layout -
+// dX[b, d, w0 + lane] = Gq + coef * (x - Es[d][lane]) - with 2 x DX_UNROLL independent coalesced loads in flight per thread and
+// no shared-memory round trip for the latents or the upstream gradient.
+constexpr int DX_UNROLL = 8;
+
+template <int J>
+__global__ void __launch_bounds__(256) backward_dx_rows_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                               const int64_t* __restrict__ idx, const float* __restrict__ Gq,
+                                                               const float* __restrict__ g_c, float beta, int D, int64_t W, int64_t N,
+                                                               int tiles_per_item, int64_t num_tiles, float* __restrict__ dX) {
+    extern __shared__ __align__(16) float Es[];   // [D][33] codeword components of the tile's frames, dim-major
+    constexpr int LPF = 8, EP = TL_F + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPF, sl = lane % LPF;
+    const float gc = g_c ? *g_c : 0.f;
+    const float coef = gc * beta * (2.0f / ((float)N * (float)D));
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / tiles_per_item), w0 = (int)(tile - (int64_t)b * tiles_per_item) * TL_F;
+        {   // this warp's four frames: one codebook row each, 8 lanes x 16 bytes per request
+            const int f = warp * 4 + sub;
+            const bool live = w0 + f < W;
+            const int64_t k = live ? idx[(int64_t)b * W + w0 + f] : 0;
+            const float* er = E + (size_t)k * D;
+            float4 ev[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int d = 4 * sl + 4 * LPF * j;
+                ev[j] = (live && d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int d = 4 * sl + 4 * LPF * j;
+                if (d < D) {
+                    Es[(d + 0) * EP + f] = ev[j].x;
+                    Es[(d + 1) * EP + f] = ev[j].y;
+                    Es[(d + 2) * EP + f] = ev[j].z;
+                    Es[(d + 3) * EP + f] = ev[j].w;
+                }
+            }
+        }
+        __syncthreads();
+        if (w0 + lane < W) {
+            const size_t at = (size_t)b * D * W + w0 + lane;
+            for (int d0 = warp * DX_UNROLL; d0 < D; d0 += 8 * DX_UNROLL) {
+                float x[DX_UNROLL], g[DX_UNROLL];
+#pragma unroll
+                for (int u = 0; u < DX_UNROLL; ++u) {
+                    const int d = d0 + u;
+                    x[u] = (d < D) ? ld_stream(z + at + (size_t)d * W) : 0.f;
+                    g[u] = (d < D && Gq) ? ld_stream(Gq + at + (size_t)d * W) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < DX_UNROLL; ++u) {
+                    const int d = d0 + u;
+                    if (d < D) st_stream(dX + at + (size_t)d * W, g[u] + coef * __fsub_rn(x[u], Es[d * EP + lane]));
+                }
+            }
+        }
+        __syncthreads();                           // Es is rewritten for the next tile
+    }
+}
+
 cudaError_t launch_backward_dx(const float* z, const float* codebook, const int64_t* idx, const float* Gq, const float* g_c,
                                float beta, int B, int D, int64_t W, int K, float* dX, cudaStream_t s) {
     (void)K;
     const int64_t N = (int64_t)B * W;
+    cudaError_t e = cudaSuccess;
+    const char* old_env = getenv("VQB_DX_TILES");
+    if (D <= 256 && !(old_env && old_env[0] == '1')) {
+        const int tiles_per_item = (int)((W + TL_F - 1) / TL_F);
+        const int64_t num_tiles = (int64_t)B * tiles_per_item;
+        const size_t smem = (size_t)D * (TL_F + 1) * 4;
+        auto go = [&](auto kernel) -> cudaError_t {
+            cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e2 != cudaSuccess) return e2;
+            int per_sm = 1, dev = 0, sms = 148;
+            if ((e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem)) != cudaSuccess) return e2;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            int64_t grid = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+            if (grid > num_tiles) grid = num_tiles;
+            if (grid < 1) grid = 1;
+            kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, tiles_per_item, num_tiles, dX);
+            return cudaGetLastError();
+        };
+        if (D <= 32) e = go(backward_dx_rows_kernel<1>);
+        else if (D <= 64) e = go(backward_dx_rows_kernel<2>);
+        else if (D <= 96) e = go(backward_dx_rows_kernel<3>);
+        else if (D <= 128) e = go(backward_dx_rows_kernel<4>);
+        else if (D <= 192) e = go(backward_dx_rows_kernel<6>);
+        else e = go(backward_dx_rows_kernel<8>);
+        if (e != cudaSuccess) return e;
+        note_launch();
+        return cudaSuccess;
+    }
     const size_t smem = (size_t)2 * TL_F * (D + 4) * 4;
     const int64_t tiles = (N + TL_F - 1) / TL_F;
     int64_t grid = tiles < kTailGridMax ? tiles : kTailGridMax;
     if (grid < 1) grid = 1;
-    cudaError_t e = cudaSuccess;
 #define VQB_DX(LPF, J)                                                                                                          \
     do {                                                                                                                        \
         e = cudaFuncSetAttribute(backward_dx_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);          \
