@@ -94,7 +94,7 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                         int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s);
-int resid_replicas();   // copies of the residual sums the tail kernels spread their atomics over (workspace holds kResidReplicasMax - 1)
+int resid_replicas(int K, int D);   // copies of the residual sums the tail kernels spread their atomics over (workspace holds kResidReplicasMax - 1)
 // fused-tail mode: finishes the (rare) frames the exact fallback search decided - one warp per frame of the list
 cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, int D, int64_t W, int K, const int* rows,
                                  const int* row_count, const unsigned long long* best64, int64_t* idx_out, float* q_out, int* counts,

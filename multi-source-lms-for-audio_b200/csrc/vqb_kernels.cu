@@ -919,9 +919,16 @@ static cudaError_t launch_tail_t(const float* z, const float* codebook, const fl
     return cudaGetLastError();
 }
 
-int resid_replicas() {   // 1..kResidReplicasMax copies of the residual sums (VQB_RESID_REPLICAS, experiments)
+// Copies of the residual sums: as many as keep the copies within 16 MiB (they should stay L2-resident next to the codebook),
+// between 2 and kResidReplicasMax.  Measured at BASELINE config 3 (8 MiB per copy): 21.0 ms with one copy, 13.7 ms with two, no
+// further gain from four or eight; small codebooks (the reference's K = 512) have hotter codes and get all eight.
+int resid_replicas(int K, int D) {
     if (const char* env = getenv("VQB_RESID_REPLICAS")) { const int v = atoi(env); if (v >= 1 && v <= kResidReplicasMax) return v; }
-    return 2;   // measured at BASELINE config 3: 21.0 ms with one copy, 13.7 ms with two, no further gain from four or eight
+    const size_t per_copy = (size_t)K * D * 4;
+    size_t n = (16u << 20) / (per_copy ? per_copy : 1);
+    if (n < 2) n = 2;
+    if (n > (size_t)kResidReplicasMax) n = kResidReplicasMax;
+    return (int)n;
 }
 // VQB_TAIL_VARIANT (experiments): 1 (default) = 4 warps and one box per block (3 blocks per SM at D = 256: 13.7 ms in the
 // BASELINE config 3 step), 0 = 8 warps and two boxes (2 blocks per SM: 14.6 ms).  A third form without block barriers (every
@@ -968,7 +975,7 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
     if (e != cudaSuccess) return e;
     double* part = reinterpret_cast<double*>(sse_partials);
     const size_t rep_stride = (size_t)K * D;
-    int n_rep = (resid && resid_rep) ? resid_replicas() : 1;
+    int n_rep = (resid && resid_rep) ? resid_replicas(K, D) : 1;
     if (n_rep > 1 && (e = cudaMemsetAsync(resid_rep, 0, (size_t)(n_rep - 1) * rep_stride * 4, s)) != cudaSuccess) return e;
     auto fold = [&]() -> cudaError_t {            // sum the residual replicas into the caller's buffer
         if (n_rep <= 1) return cudaSuccess;

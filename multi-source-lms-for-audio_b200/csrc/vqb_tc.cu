@@ -67,10 +67,13 @@ struct Barriers {
     unsigned long long a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
     unsigned long long eh_full[EH_SLOTS], eh_empty[EH_SLOTS], tmem_full[2], tmem_empty[2];
     unsigned long long stg_full[STG_SLOTS], stg_empty[STG_SLOTS];
-    unsigned long long tail_full[2], tail_empty[2];
-    unsigned long long tx_full[TX_SLOTS], tx_empty[TX_SLOTS];
     unsigned int tmem_base;
     unsigned int pad;
+};
+
+struct TailBarriers {   // fused tail only (kept out of Barriers: the default kernel has 120 bytes of shared memory to spare)
+    unsigned long long tail_full[2], tail_empty[2];
+    unsigned long long tx_full[TX_SLOTS], tx_empty[TX_SLOTS];
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -446,7 +449,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint8_t* sCandCnt = reinterpret_cast<uint8_t*>(sCand + (kTail ? 2 * BM * kCandFill : 0));   // [2][128] 0 = not for the tail
     float2* sPair = reinterpret_cast<float2*>(sCandCnt + (kTail ? 2 * BM : 0));                  // [4][32] (distance, code) hand-back
     unsigned char* sTx = reinterpret_cast<unsigned char*>(sPair + (kTail ? TAIL_WARPS * 32 + 16 : 0));   // (+128 B of per-warp totals) TX_SLOTS x 4 KiB latent boxes
-    Barriers* bars = reinterpret_cast<Barriers*>(sTx + (kTail ? TX_SLOTS * TX_BYTES : 0));          // sCnt: [128] pooled running maximum per frame (ordered int)
+    TailBarriers* tbars = reinterpret_cast<TailBarriers*>(sTx + (kTail ? TX_SLOTS * TX_BYTES : 0));
+    Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<unsigned char*>(tbars) + (kTail ? sizeof(TailBarriers) : 0));   // sCnt: [128] pooled running maximum per frame (ordered int)
 
     // Logical warp id = role.  With the fused tail the roles are rotated so that the tail warps are the four LOWEST hardware
     // warps: the scheduler favours high warp ids, and the tail must never win an issue slot against the MMA / TMA / epilogue warps.
@@ -481,13 +485,15 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_init(smem_u32(&bars->eh_full[i]), 1);
             mbar_init(smem_u32(&bars->eh_empty[i]), 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&bars->tail_full[i]), 4);                 // the four epilogue warps that publish the counts
-            mbar_init(smem_u32(&bars->tail_empty[i]), TAIL_WARPS);
-        }
-        for (int i = 0; i < TX_SLOTS; ++i) {
-            mbar_init(smem_u32(&bars->tx_full[i]), 1);
-            mbar_init(smem_u32(&bars->tx_empty[i]), TAIL_WARPS);
+        if (kTail) {
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(smem_u32(&tbars->tail_full[i]), 4);                // the four epilogue warps that publish the counts
+                mbar_init(smem_u32(&tbars->tail_empty[i]), TAIL_WARPS);
+            }
+            for (int i = 0; i < TX_SLOTS; ++i) {
+                mbar_init(smem_u32(&tbars->tx_full[i]), 1);
+                mbar_init(smem_u32(&tbars->tx_empty[i]), TAIL_WARPS);
+            }
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->tmem_full[i]), 1);
@@ -763,7 +769,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         unsigned int* acc_cnt = reinterpret_cast<unsigned int*>(sPair + TAIL_WARPS * 32 + 4) + 2 * tw;   // rescored / shortlisted
         if (lane == 0) { *acc_sse = 0.0; acc_cnt[0] = 0u; acc_cnt[1] = 0u; }
         const uint64_t pol_once = 0;
-        const uint32_t bar_full = smem_u32(&bars->tx_full[0]), bar_empty = smem_u32(&bars->tx_empty[0]);
+        const uint32_t bar_full = smem_u32(&tbars->tx_full[0]), bar_empty = smem_u32(&tbars->tx_empty[0]);
         const bool loader = tw == 0;
         RingPos pos{0u, 0u};
         if (loader && lane == 0) prefetch_tmap(&tmap_xt);
@@ -771,7 +777,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         int mt = cluster_id * cs + (int)crank;
         for (int rd = 0; rd < rounds; ++rd, mt += mt_step) {
             const int tbuf = rd & 1;
-            mbar_wait(smem_u32(&bars->tail_full[tbuf]), (rd >> 1) & 1);
+            mbar_wait(smem_u32(&tbars->tail_full[tbuf]), (rd >> 1) & 1);
             if (mt < num_m_tiles) {
                 const int b = mt / tiles_per_item, w0 = (mt - b * tiles_per_item) * BM;
                 const int cnt = sCandCnt[tbuf * BM + f];
@@ -846,7 +852,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (lane == 0) { *acc_sse += (double)fs; acc_cnt[0] += n_resc; acc_cnt[1] += n_short; }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->tail_empty[tbuf]));
+            if (lane == 0) mbar_arrive(smem_u32(&tbars->tail_empty[tbuf]));
         }
         asm volatile("bar.sync 3, 128;" ::: "memory");
         if (tw == 0 && lane == 0) {
@@ -930,7 +936,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // ---- resolve this thread's chunks against the frame's final maximum and publish the shortlist
             sMin[colq * BM + row_in_tile] = thr + hband;                     // running maximum of this column quarter
             const int tbuf = rd & 1;
-            if (kTail) mbar_wait(smem_u32(&bars->tail_empty[tbuf]), ((rd >> 1) & 1) ^ 1);   // the tail is done with the tile before last
+            if (kTail) mbar_wait(smem_u32(&tbars->tail_empty[tbuf]), ((rd >> 1) & 1) ^ 1);   // the tail is done with the tile before last
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (row < N && !scores_dbg) {
                 const float gmax = fmaxf(fmaxf(sMin[row_in_tile], sMin[BM + row_in_tile]),
@@ -987,7 +993,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (kTail) {
                     sCandCnt[tbuf * BM + row_in_tile] = (uint8_t)tcnt;
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars->tail_full[tbuf]));   // release: the shortlists were written before bar 2
+                    if (lane == 0) mbar_arrive(smem_u32(&tbars->tail_full[tbuf]));   // release: the shortlists were written before bar 2
                 }
             }
         }
@@ -1134,9 +1140,16 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     if (rc != 0) return rc;
     const int tiles_per_item = (int)((W + BM - 1) / BM);
     const int num_kb = (D + BK - 1) / BK;
-    // A ring: double-buffered for small D; fused mode keeps two spare chunks so that half of the next tile is converted ahead
+    // A ring.  Unfused: double-buffered for small D, else one tile.  Fused operand preparation: a full second tile when it fits
+    // (the converter then works a whole frame tile ahead of the tensor core: no bubble at the tile boundary, where otherwise
+    // the last chunks of the next tile can only be converted inside the last codebook tile), else two spare chunks.
     int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
     if (z_fused != nullptr && num_kb > 2 && num_kb + 2 <= 6) a_slots = num_kb + 2;
+    if (z_fused != nullptr && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
+        bool full_second_tile = true;
+        if (const char* env = getenv("VQB_TC_ASLOTS")) full_second_tile = atoi(env) >= 2 * num_kb;   // experiments
+        if (full_second_tile) a_slots = 2 * num_kb;   // pays with one codebook stage (3 instead of 4: measured equal)
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1154,7 +1167,8 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     const size_t stage_bytes = two ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
     const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
                          (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
-                         (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES : 0) + sizeof(Barriers) + 256;
+                         (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
+                         sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
     int b_stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (b_stages > (two ? 8 : 4)) b_stages = two ? 8 : 4;
     if (const char* env = getenv("VQB_TC_STAGES")) { const int v = atoi(env); if (v >= 2 && v < b_stages) b_stages = v; }   // experiments
