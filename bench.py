@@ -315,6 +315,16 @@ def main():
                     "algorithmic_flops_per_launch": flops_per_launch,
                     # fused operand preparation reads the fp32 latents once (4 D bytes per frame); the unfused path reads a bf16 copy
                     "algorithmic_dram_bytes_per_launch": (4.0 if fused_operands(W) else 2.0) * D * N}
+    # second roofline: the tail kernel (rescoring, gather, straight-through value, statistics) against the HBM copy bandwidth.
+    # Algorithmic bytes per frame: read the latent (4 D) + write `quantized` (4 D) + write the int64 index (8).
+    roofline_tail = None
+    if stages.get("tail", 0.0) > 0.0:
+        tail_bytes = ((8.0 if not args.no_q else 4.0) * D + 8.0) * N
+        gbs = tail_bytes / (stages["tail"] * 1e-3) / 1e9
+        roofline_tail = {"bound": "hbm", "kernel": "tail_tma_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "kernel_ms": stages["tail"], "kernel_share_of_step": stages["tail"] / ms_per_step,
+                         "algorithmic_bytes_per_launch": tail_bytes, "traffic": load_traffic(args.workload + "_tail"),
+                         "peak_source": peaks["source"] + " copy bandwidth"}
     cpu = None
     if not args.no_cpu:
         n_cpu = cpu_sample_size(K, D)
@@ -328,7 +338,7 @@ def main():
             "config": {"workload": desc, "frames_per_gpu": N, "K": K, "D": D, "precision": args.precision, "parallelism": f"dp{world}",
                        "l2": "inputs (>=268 MB per step) larger than the 126 MB L2; no explicit flush",
                        "step": "training-mode forward (indices + quantized + stats + losses)"},
-            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "train_step": train,
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "roofline_tail": roofline_tail, "cpu_baseline": cpu, "train_step": train,
             "stage_ms_per_step": stages,
             "shortlist": {"rescored_frames_per_step": counters["rescored"], "fallback_frames_per_step": counters["fallback"],
                           "mean_candidates": counters["shortlisted"] / max(1, N)},
