@@ -165,6 +165,53 @@ def test_fused_tail_variant_matches_oracle(B, D, W, K, cb_scale, monkeypatch):
     np.testing.assert_allclose(vq.codebook.weight.grad.cpu().numpy(), dE, rtol=1e-4, atol=1e-6 * np.abs(dE).max())
 
 
+@pytest.mark.parametrize("env", [{"VQB_TAIL_TMA": "0"}, {"VQB_TAIL_VARIANT": "0"}, {"VQB_RESID_REPLICAS": "1"},
+                                 {"VQB_RESID_REPLICAS": "8"}, {"VQB_DX_TILES": "1"}, {"VQB_TC_ASLOTS": "6"}])
+def test_kernel_variants_agree_with_the_default_path(env, monkeypatch):
+    """The experiment switches select other forms of the same kernels (register-staged tail, 8-warp TMA tail, one / eight
+    residual-sum replicas, tile-staged backward, two spare A chunks): indices and `quantized` must be identical, statistics and
+    gradients equal up to the summation order of the atomics.  A hot code (a quarter of the frames) stresses the replicas."""
+    B, D, W, K, beta = 3, 256, 1536, 700, 0.25
+    cb = seeded(11, (K, D))
+    z = seeded(12, (B, D, W))
+    hot = np.random.default_rng(13).random((B, W)) < 0.25
+    z[np.nonzero(hot)[0], :, np.nonzero(hot)[1]] = cb[5] + seeded(14, (int(hot.sum()), D), 0.05)
+    Gq = seeded(7, z.shape, 1e-3)
+
+    def run():
+        vq, zt, (emb, com, q, ppl, enc, idx) = run_module(z, cb, beta, "bf16", Gq=Gq)
+        return (idx.reshape(-1).cpu().numpy(), q.detach().cpu().numpy(), emb.item(), ppl.item(), zt.grad.cpu().numpy(),
+                vq.codebook.weight.grad.cpu().numpy())
+    ref = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    assert (got[0] == 5).mean() > 0.2
+    np.testing.assert_allclose(got[2], ref[2], rtol=1e-6)
+    np.testing.assert_allclose(got[3], ref[3], rtol=1e-6)
+    np.testing.assert_allclose(got[4], ref[4], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got[5], ref[5], rtol=1e-4, atol=1e-6 * np.abs(ref[5]).max())
+
+
+def test_stage_timing_reports_every_stage_of_the_forward():
+    """vqb_debug_stage_time_ms (bench.py's roofline legs): one timed launch per stage and forward, durations positive."""
+    import ctypes as C
+    lib = _lib.lib()
+    z = torch.from_numpy(seeded(21, (2, 64, 2048))).to(DEV)
+    cb = torch.from_numpy(seeded(22, (512, 64))).to(DEV)
+    F.vq_forward(z, cb, precision="bf16")
+    torch.cuda.synchronize()
+    lib.vqb_debug_kernel_timing(1)
+    for _ in range(3):
+        F.vq_forward(z, cb, precision="bf16")
+    for stage in range(5):
+        ms, n = C.c_double(0), C.c_int(0)
+        _lib.check("vqb_debug_stage_time_ms", lib.vqb_debug_stage_time_ms(stage, C.byref(ms), C.byref(n)))
+        assert n.value == 3 and ms.value > 0.0, (stage, n.value, ms.value)
+    lib.vqb_debug_kernel_timing(0)
+
+
 def test_trained_like_latents_use_single_candidate_shortlists():
     """Clustered latents (codeword + noise): the shortlist is a single code for almost every frame and nothing falls back."""
     K, D = 2048, 128
