@@ -221,17 +221,21 @@ constexpr int EV_CAP = 32;
 constexpr int EV_WORDS = 12;   // 8 accumulators, chunk minimum, chunk id, 2 pad
 
 struct EventStack {
-    uint32_t* base;   // this thread's EV_CAP x EV_WORDS words; an entry = 8 accumulators, chunk maximum, chunk id
+    uint32_t* base;   // this thread's EV_CAP x EV_WORDS words in global scratch; an entry = 8 accumulators, chunk maximum, chunk id
+    uint32_t* sbase;  // the first `sm` entries live in shared memory instead (when the tile pipeline leaves room: small D).  With a
+    int       sm;     // small codebook there are few codebook tiles per frame tile, and two dependent L2 round trips to the stack
+                      // at the end of EVERY frame tile were ~45 % of the kernel at K = 1024, D = 64
     int       n;      // chunks appended for the current frame tile (may exceed EV_CAP: overflow)
+    __device__ __forceinline__ uint32_t* slot(int i) const { return (i < sm ? sbase : base) + i * EV_WORDS; }
     __device__ __forceinline__ void push_if(bool p, float tmin, int chunk, const uint32_t* a) {
         const bool q = p && n < EV_CAP;
-        uint32_t* dst = base + n * EV_WORDS;
+        uint32_t* dst = slot(n);
         asm volatile(
             "{\n\t.reg .pred q;\n\t"
             "setp.ne.u32 q, %0, 0;\n\t"
-            "@q st.global.v4.u32 [%1], {%2, %3, %4, %5};\n\t"
-            "@q st.global.v4.u32 [%1+16], {%6, %7, %8, %9};\n\t"
-            "@q st.global.v2.u32 [%1+32], {%10, %11};\n\t}" ::"r"((uint32_t)q),
+            "@q st.v4.u32 [%1], {%2, %3, %4, %5};\n\t"
+            "@q st.v4.u32 [%1+16], {%6, %7, %8, %9};\n\t"
+            "@q st.v2.u32 [%1+32], {%10, %11};\n\t}" ::"r"((uint32_t)q),
             "l"(dst), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(__float_as_uint(tmin)),
             "r"((uint32_t)chunk)
             : "memory");
@@ -432,7 +436,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
-                 const TailArgs tail, const int tail_dbg) {
+                 const TailArgs tail, const int tail_dbg, const int ev_sm) {
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
@@ -444,8 +448,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     float* sBand = reinterpret_cast<float*>(sStg + (kFuse ? STG_SLOTS * STG_BYTES : 0));   // fused mode: [2][128] guard bands
     float* sMin = sBand + (kFuse ? 2 * BM : 0);                          // [4][128] running maxima of the four column quarters
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
+    uint32_t* sEv = reinterpret_cast<uint32_t*>(sCnt + 3 * BM);          // [512][ev_sm] shared-memory part of the event stacks
     // fused tail: the shortlists of two frame tiles (the epilogue fills one while the tail warps consume the other)
-    uint16_t* sCand = reinterpret_cast<uint16_t*>(sCnt + 3 * BM);        // [2][128][kCandFill] codes
+    uint16_t* sCand = reinterpret_cast<uint16_t*>(sEv + (size_t)EPI_THREADS * ev_sm * EV_WORDS);   // [2][128][kCandFill] codes
     uint8_t* sCandCnt = reinterpret_cast<uint8_t*>(sCand + (kTail ? 2 * BM * kCandFill : 0));   // [2][128] 0 = not for the tail
     float2* sPair = reinterpret_cast<float2*>(sCandCnt + (kTail ? 2 * BM : 0));                  // [4][32] (distance, code) hand-back
     unsigned char* sTx = reinterpret_cast<unsigned char*>(sPair + (kTail ? TAIL_WARPS * 32 + 16 : 0));   // (+128 B of per-warp totals) TX_SLOTS x 4 KiB latent boxes
@@ -873,6 +878,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int et = (warp - EPI_WARP0) * 32 + lane;           // 0..511
         EventStack ev;
         ev.base = ev_scratch + ((size_t)blockIdx.x * EPI_THREADS + et) * (EV_CAP * EV_WORDS);
+        ev.sbase = sEv + (size_t)et * ev_sm * EV_WORDS;
+        ev.sm = ev_sm;
         ev.n = 0;
         if (colq == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; sCnt[2 * BM + row_in_tile] = f2ord(-INFINITY); }
         int* smax = sCnt + 2 * BM + row_in_tile;
@@ -949,12 +956,12 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     uint2 hd[8];     // headers (chunk maximum, chunk id) of 8 events fetched together: one L2 latency, not eight
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        hd[u] = (e0 + u < n_ev) ? *reinterpret_cast<const uint2*>(ev.base + (e0 + u) * EV_WORDS + 8)
+                        hd[u] = (e0 + u < n_ev) ? *reinterpret_cast<const uint2*>(ev.slot(e0 + u) + 8)
                                                 : make_uint2(0xff800000u, 0u);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         if (__uint_as_float(hd[u].x) >= cutoff) {
-                            const uint32_t* en = ev.base + (e0 + u) * EV_WORDS;
+                            const uint32_t* en = ev.slot(e0 + u);
                             const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 4);
                             const int k0 = (int)hd[u].y * 8;
                             const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -1169,11 +1176,20 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
                          (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
                          (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
                          sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
-    int b_stages = (int)((227 * 1024 - fixed) / stage_bytes);
+    // shared-memory part of the event stacks: whatever four codebook stages leave, at most 3 entries per epilogue thread
+    const size_t ev_entry_bytes = (size_t)EPI_THREADS * EV_WORDS * 4;   // one entry for every epilogue thread: 24 KiB
+    int ev_sm = 0;
+    if (!with_tail && !scores_dbg && 227 * 1024 > fixed + 4 * stage_bytes) {
+        ev_sm = (int)((227 * 1024 - fixed - 4 * stage_bytes) / ev_entry_bytes);
+        if (ev_sm > 3) ev_sm = 3;
+    }
+    if (const char* env = getenv("VQB_TC_EVSM")) { const int v = atoi(env); if (v >= 0 && v < ev_sm) ev_sm = v; }   // experiments
+    const size_t fixed_ev = fixed + (size_t)ev_sm * ev_entry_bytes;
+    int b_stages = (int)((227 * 1024 - fixed_ev) / stage_bytes);
     if (b_stages > (two ? 8 : 4)) b_stages = two ? 8 : 4;
     if (const char* env = getenv("VQB_TC_STAGES")) { const int v = atoi(env); if (v >= 2 && v < b_stages) b_stages = v; }   // experiments
     if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
-    const size_t smem = fixed + (size_t)b_stages * stage_bytes;
+    const size_t smem = fixed_ev + (size_t)b_stages * stage_bytes;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_search_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1212,7 +1228,7 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
 #define VQB_TC_LAUNCH(TWO, FUSE, TAIL)                                                                                                       \
     le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
                             num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \
-                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, tail_dbg)
+                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, tail_dbg, ev_sm)
     if (two && with_tail) VQB_TC_LAUNCH(true, true, true);
     else if (with_tail) VQB_TC_LAUNCH(false, true, true);
     else if (two && fuse) VQB_TC_LAUNCH(true, true, false);
