@@ -950,13 +950,20 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
                                      float* resid_rep, int n_rep, size_t rep_stride, cudaStream_t s) {
     const size_t smem = (size_t)(NB * D * TL_F + TL_F * (D + 4)) * 4;
     auto go = [&](auto kernel) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        int per_sm = 1, dev = 0, sms = 148;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW, smem)) != cudaSuccess) return e;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int64_t grid = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+        // attribute + occupancy are looked up once per kernel instance and shared-memory size (this path is launch-bound for small batches)
+        static thread_local size_t cached_smem = ~(size_t)0;
+        static thread_local int cached_blocks = 0;
+        cudaError_t e = cudaSuccess;
+        if (cached_smem != smem) {
+            if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+            int per_sm = 1, dev = 0, sms = 148;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW, smem)) != cudaSuccess) return e;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cached_blocks = sms * (per_sm < 1 ? 1 : per_sm);
+            cached_smem = smem;
+        }
+        int64_t grid = cached_blocks;
         if (grid > n_partials) grid = n_partials;
         if (grid > num_tiles) grid = num_tiles;
         if (grid < 1) grid = 1;
@@ -1212,13 +1219,19 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
         const int64_t num_tiles = (int64_t)B * tiles_per_item;
         const size_t smem = (size_t)D * (TL_F + 1) * 4;
         auto go = [&](auto kernel) -> cudaError_t {
-            cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            if (e2 != cudaSuccess) return e2;
-            int per_sm = 1, dev = 0, sms = 148;
-            if ((e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem)) != cudaSuccess) return e2;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            int64_t grid = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+            static thread_local size_t cached_smem = ~(size_t)0;   // see launch_tail_tma_t
+            static thread_local int cached_blocks = 0;
+            cudaError_t e2 = cudaSuccess;
+            if (cached_smem != smem) {
+                if ((e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e2;
+                int per_sm = 1, dev = 0, sms = 148;
+                if ((e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem)) != cudaSuccess) return e2;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cached_blocks = sms * (per_sm < 1 ? 1 : per_sm);
+                cached_smem = smem;
+            }
+            int64_t grid = cached_blocks;
             if (grid > num_tiles) grid = num_tiles;
             if (grid < 1) grid = 1;
             kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, tiles_per_item, num_tiles, dX);
