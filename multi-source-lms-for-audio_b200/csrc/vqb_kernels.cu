@@ -950,11 +950,13 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
                                      float* resid_rep, int n_rep, size_t rep_stride, cudaStream_t s) {
     const size_t smem = (size_t)(NB * D * TL_F + TL_F * (D + 4)) * 4;
     auto go = [&](auto kernel) -> cudaError_t {
-        // attribute + occupancy are looked up once per kernel instance and shared-memory size (this path is launch-bound for small batches)
+        // attribute + occupancy are looked up once per kernel instance and shared-memory size (this path is launch-bound for small
+        // batches).  All instances share one signature, hence ONE instantiation of this lambda: the kernel pointer is part of the key.
         static thread_local size_t cached_smem = ~(size_t)0;
+        static thread_local const void* cached_kernel = nullptr;
         static thread_local int cached_blocks = 0;
         cudaError_t e = cudaSuccess;
-        if (cached_smem != smem) {
+        if (cached_smem != smem || cached_kernel != reinterpret_cast<const void*>(kernel)) {
             if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
             int per_sm = 1, dev = 0, sms = 148;
             if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW, smem)) != cudaSuccess) return e;
@@ -962,6 +964,7 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cached_blocks = sms * (per_sm < 1 ? 1 : per_sm);
             cached_smem = smem;
+            cached_kernel = reinterpret_cast<const void*>(kernel);
         }
         int64_t grid = cached_blocks;
         if (grid > n_partials) grid = n_partials;
@@ -1220,9 +1223,10 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
         const size_t smem = (size_t)D * (TL_F + 1) * 4;
         auto go = [&](auto kernel) -> cudaError_t {
             static thread_local size_t cached_smem = ~(size_t)0;   // see launch_tail_tma_t
+            static thread_local const void* cached_kernel = nullptr;
             static thread_local int cached_blocks = 0;
             cudaError_t e2 = cudaSuccess;
-            if (cached_smem != smem) {
+            if (cached_smem != smem || cached_kernel != reinterpret_cast<const void*>(kernel)) {
                 if ((e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e2;
                 int per_sm = 1, dev = 0, sms = 148;
                 if ((e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem)) != cudaSuccess) return e2;
@@ -1230,6 +1234,7 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
                 cached_blocks = sms * (per_sm < 1 ? 1 : per_sm);
                 cached_smem = smem;
+                cached_kernel = reinterpret_cast<const void*>(kernel);
             }
             int64_t grid = cached_blocks;
             if (grid > num_tiles) grid = num_tiles;
