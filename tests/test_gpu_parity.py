@@ -114,6 +114,9 @@ CASES = [
     (3, 512, 200, 1000, 1.0, 0.5),      # largest D
     (1, 64, 1, 512, 1.0, 1.0),          # a single frame
     (2, 48, 500, 1, 1.0, 1.0),          # a single code
+    (3, 16, 4, 5, 1.0, 1.0),            # W % 4 == 0 but shorter than one TMA box of the tail (32 frames)
+    (2, 32, 36, 64, 1.0, 1.0),          # one full box + a 4-frame remainder per batch item
+    (1, 192, 2052, 600, 1.0, 1.0),      # fused operand preparation with a ragged last frame tile, D = 192 (J = 6)
 ]
 
 
