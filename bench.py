@@ -35,6 +35,8 @@ WORKLOADS = {
     "cfg3": (1024, 256, 16384, 8192, "quantizer-only N=2^24/GPU K=8192 D=256 (BASELINE.json configs[2])"),
     "cfg2": (64, 64, 16384, 1024, "quantizer-only N=2^20 K=1024 D=64 (BASELINE.json configs[1])"),
     "cfg1": (2, 64, 11000, 512, "VQ bottleneck at debug-batch shape N=22000 K=512 D=64 (BASELINE.json configs[0])"),
+    # index export for the BERT stage: indices only (no quantized output, no statistics) + 512-token windows with masks
+    "cfg5": (64, 64, 11000, 512, "index export B=64 clips/GPU x 11000 frames, K=512 D=64, 22 windows of 512 (BASELINE.json configs[4])"),
 }
 BETA = 0.25
 
@@ -115,8 +117,9 @@ def cpu_port_rate(K: int, D: int, rows_total: int, chunk: int, repeats: int = 1)
 
 
 def cpu_sample_size(K: int, D: int) -> int:
-    # ~10-30 s of CPU work on a handful of cores: 2 K D flops per vector at ~100 GFLOP/s effective
-    target_flops = 2.0e12
+    # ~10-30 s of CPU work on the box's 16 cores (the port spends three sgemm-sized passes per chunk): 2^20 frames at
+    # BASELINE config 3 take ~14 s; small workloads are run whole
+    target_flops = 8.0e12
     n = int(target_flops / (2.0 * K * D))
     return max(4096, min(1 << 20, 1 << (n.bit_length() - 1)))
 
@@ -127,7 +130,7 @@ def run_reference(args):
     if rank != 0:
         return
     B, D, W, K, desc = WORKLOADS[args.workload]
-    n = cpu_sample_size(K, D) // 4
+    n = min(cpu_sample_size(K, D) // 4, B * W)
     chunk = min(n, 32768)
     times = []
     for i in range(args.warmup + args.steps):
@@ -194,7 +197,13 @@ def main():
     stats = torch.empty(_lib.stats_len(K, D), device=dev)
     lib = _lib.lib()
 
+    export_only = args.workload == "cfg5"
+
     def step():
+        if export_only:     # Quantize.get_encodings_idx + the window preparation of AudioBert.forward (transform.py:15-16, bert.py:50-69)
+            idx, _, st = F.vq_forward(z, codebook, precision=args.precision, want_q=False, want_resid=False, stats=stats)
+            tokens, mask = F.window_indices(idx, B, window=512, pad_id=0)
+            return idx, tokens, F.vq_finalize(st, K, D, BETA)
         idx, q, st = F.vq_forward(z, codebook, precision=args.precision, want_q=not args.no_q, want_resid=not args.no_resid, stats=stats)
         if comm is not None:
             comm.allreduce(st)
@@ -244,7 +253,7 @@ def main():
 
     # ---- training step (forward + backward) as a second, explanatory number
     train = None
-    if not args.no_train:
+    if not args.no_train and not export_only:
         Gq = torch.randn(B, D, W, device=dev, generator=g) * 1e-3
         one = torch.ones((), device=dev)
 
@@ -319,7 +328,7 @@ def main():
     # Algorithmic bytes per frame: read the latent (4 D) + write `quantized` (4 D) + write the int64 index (8).
     roofline_tail = None
     if stages.get("tail", 0.0) > 0.0:
-        tail_bytes = ((8.0 if not args.no_q else 4.0) * D + 8.0) * N
+        tail_bytes = ((8.0 if not (args.no_q or export_only) else 4.0) * D + 8.0) * N
         gbs = tail_bytes / (stages["tail"] * 1e-3) / 1e9
         roofline_tail = {"bound": "hbm", "kernel": "tail_tma_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / peaks["hbm_gbs"], "kernel_ms": stages["tail"], "kernel_share_of_step": stages["tail"] / ms_per_step,
@@ -327,7 +336,7 @@ def main():
                          "peak_source": peaks["source"] + " copy bandwidth"}
     cpu = None
     if not args.no_cpu:
-        n_cpu = cpu_sample_size(K, D)
+        n_cpu = min(cpu_sample_size(K, D), N)
         chunk = min(n_cpu, 32768)
         rate, secs = cpu_port_rate(K, D, n_cpu, chunk)
         cpu = {"value": rate, "unit": "vectors/s", "cores": os.cpu_count(), "kind": "port", "seconds": secs,
@@ -337,7 +346,8 @@ def main():
             "dtype": "bf16 shortlist + fp32 rescoring" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": desc, "frames_per_gpu": N, "K": K, "D": D, "precision": args.precision, "parallelism": f"dp{world}",
                        "l2": "inputs (>=268 MB per step) larger than the 126 MB L2; no explicit flush",
-                       "step": "training-mode forward (indices + quantized + stats + losses)"},
+                       "step": ("index export (indices + BERT windows + masks)" if export_only else
+                                "training-mode forward (indices + quantized + stats + losses)")},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "roofline_tail": roofline_tail, "cpu_baseline": cpu, "train_step": train,
             "stage_ms_per_step": stages,
             "shortlist": {"rescored_frames_per_step": counters["rescored"], "fallback_frames_per_step": counters["fallback"],
