@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(32 * TAIL_WARPS, (J >= 6) ? 4 : 6) tail_kernel
 // bounded tail_kernel (latency, 25 % occupancy).  Needs W % 4 == 0 (TMA global strides are multiples of 16 bytes).
 // NW warps per block, NB box buffers (1: the next box is requested right after the transposition freed the buffer).
 template <int LPF, int J, bool kResid, int NW, int NB>
-__global__ void __launch_bounds__(32 * NW, (NW == 4) ? 3 : ((J >= 6) ? 2 : 3))
+__global__ void __launch_bounds__(32 * NW, (NW == 4) ? ((J <= 2) ? 6 : ((J <= 4) ? 4 : 3)) : ((J >= 6) ? 2 : 3))
 tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restrict__ E, const float* __restrict__ e2, int D, int64_t W,
                 int tiles_per_item, int64_t num_tiles, int box_dims, const int* __restrict__ idx32,
                 const uint8_t* __restrict__ cand_cnt, const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
