@@ -1,10 +1,12 @@
 // CUDA-core kernels of the VQ bottleneck for sm_100a: codebook / latent preparation, the exact fp32 search
-// (parity anchor + fallback of the tensor-core shortlist), the fused tail (fp32 rescoring in the reference's op
-// order, codeword gather, SSE, straight-through value, per-code statistics) and the backward kernels.
+// (parity anchor + fallback of the tensor-core shortlist), the tail (fp32 rescoring in the reference's op order,
+// codeword gather, SSE, straight-through value, per-code statistics; TMA-fed and register-staged forms) and the
+// backward kernels.
 //
 // Reference semantics restated here (never copied): src/model/components/vector_quantizer.py:25-52.
-// All of these are HBM-bound: they read latents straight from the reference's [B, D, W] layout with frame-contiguous
-// (coalesced) accesses, transpose through padded shared memory, and touch every latent byte once per kernel.
+// All of these are HBM-bound: they read latents straight from the reference's [B, D, W] layout (TMA boxes or
+// frame-contiguous coalesced accesses), transpose through padded shared memory where a gather needs frame-major rows,
+// and touch every latent byte once per kernel.
 #include "vqb_internal.h"
 #include "vqb_ptx.cuh"
 

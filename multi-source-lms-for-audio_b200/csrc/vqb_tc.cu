@@ -10,16 +10,18 @@
 // replaces `distances` + `argmin` of src/model/components/vector_quantizer.py:32-37.  The N x K score matrix never
 // leaves the SM: tcgen05.mma accumulates a 128-frame x 256-code tile in TMEM, epilogue warps pull it back with
 // tcgen05.ld, add |e_k|^2 and keep, per frame, the codes whose score is within a rigorous guard band of the running
-// minimum (at most 12 per frame).  The fused tail kernel then rescores those few codes in fp32 in the reference's
+// minimum (at most 12 per frame).  The tail kernel (vqb_kernels.cu) then rescores those few codes in fp32 in the reference's
 // operation order, which decides the index; frames whose shortlist overflowed go to the exact fp32 search.
 //
-// Structure (one persistent CTA per SM, 640 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 640 threads, warp-specialised; CTA pairs with cta_group::2 MMAs by default):
 //   warps 0-15  epilogue: warp w owns TMEM lanes 32*(w%4).., column quarter w/4 (64 of the 256 columns)
-//   warp 16     TMA producer (one thread): latent tile A (128 frames x D, resident per M tile) and codebook tiles B
-//               (256 codes x 64 dims per stage) as 128B-swizzled K-major boxes, bias-operand slices by bulk copy
-//   warp 17     MMA issuer (one thread): tcgen05.mma cta_group::1 kind::f16 M128 N256 K16, fp32 accumulate, two TMEM
-//               accumulator stages (2 x 256 columns) so the epilogue of tile j overlaps the MMAs of tile j+1
-//   warp 18     TMEM allocator
+//   warp 16     TMA producer (one thread): codebook tiles B (256 codes x 64 dims per stage; half tiles per CTA of a pair)
+//               as 128B-swizzled K-major boxes, bias-operand slices; in the unfused mode also the bf16 latent tile A
+//   warp 17     MMA issuer (one thread): tcgen05.mma kind::f16, M128 (M256 over a pair) N256 K16, fp32 accumulate, two
+//               TMEM accumulator stages (2 x 256 columns) so the epilogue of tile j overlaps the MMAs of tile j+1
+//   warps 18-19 fused operand preparation: fp32 [B, D, W] latents -> bf16 swizzled A chunks (warp 19 also issues the 3-D
+//               TMA loads of the staging ring; warp 18 also allocates TMEM)
+//   warps 20-23 only in the opt-in fused-tail variant (kTail): finish the frames one tile behind the epilogue
 #include "vqb_internal.h"
 #include "vqb_ptx.cuh"
 
