@@ -51,8 +51,10 @@ def load_traffic(workload: str):
     return None
 
 
-def fused_operands(W: int) -> bool:
+def fused_operands(W: int, B: int = 1 << 20, D: int = 256) -> bool:
     """Mirror of tc_can_fuse() in csrc/vqb_tc.cu: does the tensor-core kernel read the fp32 [B, D, W] latents itself?"""
+    if D > 448 and B * ((W + 127) // 128) < 4:
+        return False
     return os.environ.get("VQB_TC_FUSE", "1") != "0" and W % 4 == 0 and (W % 128 == 0 or W >= 1024)
 
 
@@ -323,7 +325,7 @@ def main():
                     "launches_timed": kn.value, "traffic": load_traffic(args.workload),
                     "algorithmic_flops_per_launch": flops_per_launch,
                     # fused operand preparation reads the fp32 latents once (4 D bytes per frame); the unfused path reads a bf16 copy
-                    "algorithmic_dram_bytes_per_launch": (4.0 if fused_operands(W) else 2.0) * D * N}
+                    "algorithmic_dram_bytes_per_launch": (4.0 if fused_operands(W, B, D) else 2.0) * D * N}
     # second roofline: the tail kernel (rescoring, gather, straight-through value, statistics) against the HBM copy bandwidth.
     # Algorithmic bytes per frame: read the latent (4 D) + write `quantized` (4 D) + write the int64 index (8).
     roofline_tail = None

@@ -1089,8 +1089,10 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 }
 
 bool tc_can_fuse(const float* z, int B, int D, int64_t W) {
-    (void)B;
     if (const char* env = getenv("VQB_TC_FUSE")) if (env[0] == '0') return false;
+    // fewer than four frame tiles run without CTA pairs (whole-tile codebook stages of 32 KiB): with an eight-chunk A tile
+    // (D > 448) the staging ring of the fused preparation then leaves room for one stage only
+    if (D > 448 && (int64_t)B * ((W + tc::BM - 1) / tc::BM) < 4) return false;
     // 3-D TMA needs 16-byte global strides; short clips would waste most of every 128-frame tile on padding
     return (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (D % tc::SUB_DIMS) == 0 && (W % 128 == 0 || W >= 1024);
 }
@@ -1154,11 +1156,6 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     // the last chunks of the next tile can only be converted inside the last codebook tile), else two spare chunks.
     int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
     if (z_fused != nullptr && num_kb > 2 && num_kb + 2 <= 6) a_slots = num_kb + 2;
-    if (z_fused != nullptr && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
-        bool full_second_tile = true;
-        if (const char* env = getenv("VQB_TC_ASLOTS")) full_second_tile = atoi(env) >= 2 * num_kb;   // experiments
-        if (full_second_tile) a_slots = 2 * num_kb;   // pays with one codebook stage (3 instead of 4: measured equal)
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1174,10 +1171,17 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     if (two) cs = 2;
     if (num_m_tiles < 2 * cs) { cs = 1; two = false; }
     const size_t stage_bytes = two ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
-                         (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
-                         (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
-                         sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
+    const size_t fixed_no_a = EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
+                              (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
+                              (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
+                              sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
+    if (z_fused != nullptr && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
+        // the full second tile must leave three codebook stages (it does for CTA pairs at D = 256: 3 x 16 KiB half-tile stages)
+        bool full_second_tile = fixed_no_a + (size_t)2 * num_kb * A_CHUNK_BYTES + 3 * stage_bytes <= 227 * 1024;
+        if (const char* env = getenv("VQB_TC_ASLOTS")) full_second_tile = full_second_tile && atoi(env) >= 2 * num_kb;   // experiments
+        if (full_second_tile) a_slots = 2 * num_kb;   // pays with one codebook stage (3 instead of 4: measured equal)
+    }
+    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + fixed_no_a;
     // shared-memory part of the event stacks: whatever four codebook stages leave, at most 3 entries per epilogue thread
     const size_t ev_entry_bytes = (size_t)EPI_THREADS * EV_WORDS * 4;   // one entry for every epilogue thread: 24 KiB
     int ev_sm = 0;

@@ -117,6 +117,10 @@ CASES = [
     (3, 16, 4, 5, 1.0, 1.0),            # W % 4 == 0 but shorter than one TMA box of the tail (32 frames)
     (2, 32, 36, 64, 1.0, 1.0),          # one full box + a 4-frame remainder per batch item
     (1, 192, 2052, 600, 1.0, 1.0),      # fused operand preparation with a ragged last frame tile, D = 192 (J = 6)
+    (1, 256, 256, 512, 1.0, 1.0),       # D = 256 with two frame tiles only: no CTA pairs, whole-tile codebook stages (found by stress_shapes.py)
+    (2, 256, 128, 300, 1.0, 1.0),       # same, one tile per batch item
+    (1, 512, 256, 40, 1.0, 1.0),        # D = 512 with two frame tiles: unfused operand preparation (found by stress_shapes.py)
+    (3, 448, 128, 257, 1.0, 1.0),       # D = 448, three tiles: fused preparation without CTA pairs, two codebook stages
 ]
 
 
