@@ -53,7 +53,7 @@ def load_traffic(workload: str):
 
 def fused_operands(W: int, B: int = 1 << 20, D: int = 256) -> bool:
     """Mirror of tc_can_fuse() in csrc/vqb_tc.cu: does the tensor-core kernel read the fp32 [B, D, W] latents itself?"""
-    if D > 448 and B * ((W + 127) // 128) < 4:
+    if D > 448 and (B * ((W + 127) // 128) < 4 or os.environ.get("VQB_TC_MODE") == "1"):
         return False
     return os.environ.get("VQB_TC_FUSE", "1") != "0" and W % 4 == 0 and (W % 128 == 0 or W >= 1024)
 

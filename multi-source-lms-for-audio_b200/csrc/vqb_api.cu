@@ -164,7 +164,8 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         const bool fuse = tc_can_fuse(z, B, D, W);
         // fused tail: the search kernel finishes the frames itself (index, quantized, statistics); only the frames it
         // sends to the exact search are finished by a small list kernel.  Otherwise the stand-alone tail kernel runs.
-        const bool fused_tail = fuse && !scores_dbg && tc_fused_tail_enabled() && (reinterpret_cast<uintptr_t>(codebook) & 31) == 0;
+        const bool fused_tail = fuse && !scores_dbg && tc_fused_tail_enabled() && (reinterpret_cast<uintptr_t>(codebook) & 31) == 0 &&
+                                tc_fused_tail_fits(B, D, W);
         double* part_d = reinterpret_cast<double*>(part);
         TailArgs targs{z, codebook, e2, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr, counts, resid, part_d};
         if (!fuse) VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");

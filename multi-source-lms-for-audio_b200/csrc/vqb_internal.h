@@ -120,6 +120,7 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 // ---- tensor-core search (vqb_tc.cu) ---------------------------------------------------------------------------
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.
 bool tc_can_fuse(const float* z, int B, int D, int64_t W);   // can the tensor-core kernel read the fp32 [B, D, W] latents itself?
+bool tc_fused_tail_fits(int B, int D, int64_t W);            // ... and its shared memory leaves room for the tile pipeline
 bool tc_fused_tail_enabled();                               // VQB_TC_TAIL=0 keeps the stand-alone tail kernel (experiments)
 // z_fused != nullptr: fused operand preparation (xb / band unused); else xb / band from latent_prep_bf16_kernel
 int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh,

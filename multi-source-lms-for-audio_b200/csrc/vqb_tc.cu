@@ -1088,11 +1088,67 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
     return 0;
 }
 
+// Shared-memory plan of one launch: cluster mode, A ring, codebook stages, shared-memory event-stack entries.
+// One function decides for the launcher AND for the callers that must know beforehand whether a variant fits
+// (tc_can_fuse, tc_fused_tail_fits).
+struct TcPlan {
+    bool ok, two;
+    int cs, a_slots, b_stages, ev_sm;
+    size_t smem;
+};
+
+static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int D) {
+    using namespace tc;
+    TcPlan p{};
+    const int num_kb = (D + BK - 1) / BK;
+    // default: CTA pairs with cta_group::2 MMAs; VQB_TC_MODE=1: cta_group::1 with VQB_TC_CLUSTER-way codebook multicast
+    p.two = true;
+    if (const char* env = getenv("VQB_TC_MODE")) p.two = env[0] != '1';
+    p.cs = 2;
+    if (const char* env = getenv("VQB_TC_CLUSTER")) p.cs = atoi(env);
+    if (p.cs != 1 && p.cs != 2 && p.cs != 4) p.cs = 2;
+    if (p.two) p.cs = 2;
+    if (num_m_tiles < 2 * p.cs) { p.cs = 1; p.two = false; }
+    const size_t stage_bytes = p.two ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+    // A ring.  Unfused: double-buffered for small D, else one tile.  Fused operand preparation: a full second tile when it fits
+    // (the converter then works a whole frame tile ahead of the tensor core: no bubble at the tile boundary, where otherwise
+    // the last chunks of the next tile can only be converted inside the last codebook tile), else two spare chunks.
+    p.a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
+    if (fuse && num_kb > 2 && num_kb + 2 <= 6) p.a_slots = num_kb + 2;
+    const size_t fixed_no_a = EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
+                              (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
+                              (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
+                              sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
+    if (fuse && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
+        // the full second tile must leave three codebook stages (it does for CTA pairs at D = 256: 3 x 16 KiB half-tile stages)
+        bool full_second_tile = fixed_no_a + (size_t)2 * num_kb * A_CHUNK_BYTES + 3 * stage_bytes <= 227 * 1024;
+        if (const char* env = getenv("VQB_TC_ASLOTS")) full_second_tile = full_second_tile && atoi(env) >= 2 * num_kb;   // experiments
+        if (full_second_tile) p.a_slots = 2 * num_kb;   // pays with one codebook stage (3 instead of 4: measured equal)
+    }
+    const size_t fixed = (size_t)p.a_slots * A_CHUNK_BYTES + fixed_no_a;
+    // shared-memory part of the event stacks: whatever four codebook stages leave, at most 3 entries per epilogue thread
+    const size_t ev_entry_bytes = (size_t)EPI_THREADS * EV_WORDS * 4;   // one entry for every epilogue thread: 24 KiB
+    p.ev_sm = 0;
+    if (!with_tail && !dbg && 227 * 1024 > fixed + 4 * stage_bytes) {
+        p.ev_sm = (int)((227 * 1024 - fixed - 4 * stage_bytes) / ev_entry_bytes);
+        if (p.ev_sm > 3) p.ev_sm = 3;
+    }
+    if (const char* env = getenv("VQB_TC_EVSM")) { const int v = atoi(env); if (v >= 0 && v < p.ev_sm) p.ev_sm = v; }   // experiments
+    const size_t fixed_ev = fixed + (size_t)p.ev_sm * ev_entry_bytes;
+    p.b_stages = fixed_ev < 227 * 1024 ? (int)((227 * 1024 - fixed_ev) / stage_bytes) : 0;
+    if (p.b_stages > (p.two ? 8 : 4)) p.b_stages = p.two ? 8 : 4;
+    if (const char* env = getenv("VQB_TC_STAGES")) { const int v = atoi(env); if (v >= 2 && v < p.b_stages) p.b_stages = v; }   // experiments
+    p.ok = p.b_stages >= 2 && p.a_slots <= MAX_A_SLOTS;
+    p.smem = fixed_ev + (size_t)p.b_stages * stage_bytes;
+    return p;
+}
+
 bool tc_can_fuse(const float* z, int B, int D, int64_t W) {
     if (const char* env = getenv("VQB_TC_FUSE")) if (env[0] == '0') return false;
-    // fewer than four frame tiles run without CTA pairs (whole-tile codebook stages of 32 KiB): with an eight-chunk A tile
-    // (D > 448) the staging ring of the fused preparation then leaves room for one stage only
-    if (D > 448 && (int64_t)B * ((W + tc::BM - 1) / tc::BM) < 4) return false;
+    // the staging ring of the fused preparation must leave room for the pipeline: it does not with an eight-chunk A tile
+    // (D > 448) outside the CTA-pair mode (whole-tile codebook stages: fewer than four frame tiles, or VQB_TC_MODE=1)
+    const int64_t tiles = (int64_t)B * ((W + tc::BM - 1) / tc::BM);
+    if (!tc_plan(true, false, false, (int)(tiles < (1 << 30) ? tiles : (1 << 30)), D).ok) return false;
     // 3-D TMA needs 16-byte global strides; short clips would waste most of every 128-frame tile on padding
     return (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (D % tc::SUB_DIMS) == 0 && (W % 128 == 0 || W >= 1024);
 }
@@ -1101,6 +1157,10 @@ bool tc_can_fuse(const float* z, int B, int D, int64_t W) {
 // 74.3 ms with the round-1 stand-alone tail, but the search kernel itself slows from 50.9 to 68.5 ms - the epilogue already
 // keeps the SM's non-tensor resources busy, so the tail's work costs about as much inside the kernel as outside it.
 // A stand-alone tail at HBM speed beats it, hence off by default.
+bool tc_fused_tail_fits(int B, int D, int64_t W) {   // does the kTail variant's extra shared memory leave a pipeline?
+    const int64_t tiles = (int64_t)B * ((W + tc::BM - 1) / tc::BM);
+    return tc_plan(true, true, false, (int)(tiles < (1 << 30) ? tiles : (1 << 30)), D).ok;
+}
 bool tc_fused_tail_enabled() {
     if (const char* env = getenv("VQB_TC_TAIL")) return env[0] == '1';
     return false;
@@ -1151,51 +1211,17 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     if (rc != 0) return rc;
     const int tiles_per_item = (int)((W + BM - 1) / BM);
     const int num_kb = (D + BK - 1) / BK;
-    // A ring.  Unfused: double-buffered for small D, else one tile.  Fused operand preparation: a full second tile when it fits
-    // (the converter then works a whole frame tile ahead of the tensor core: no bubble at the tile boundary, where otherwise
-    // the last chunks of the next tile can only be converted inside the last codebook tile), else two spare chunks.
-    int a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
-    if (z_fused != nullptr && num_kb > 2 && num_kb + 2 <= 6) a_slots = num_kb + 2;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > kTcMaxCtas) sms = kTcMaxCtas;
     const int num_m_tiles = fuse ? B * tiles_per_item : (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
-    // default: CTA pairs with cta_group::2 MMAs; VQB_TC_MODE=1: cta_group::1 with VQB_TC_CLUSTER-way codebook multicast
-    bool two = true;
-    if (const char* env = getenv("VQB_TC_MODE")) two = env[0] != '1';
-    int cs = 2;
-    if (const char* env = getenv("VQB_TC_CLUSTER")) cs = atoi(env);
-    if (cs != 1 && cs != 2 && cs != 4) cs = 2;
-    if (two) cs = 2;
-    if (num_m_tiles < 2 * cs) { cs = 1; two = false; }
-    const size_t stage_bytes = two ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
-    const size_t fixed_no_a = EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
-                              (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
-                              (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
-                              sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
-    if (z_fused != nullptr && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
-        // the full second tile must leave three codebook stages (it does for CTA pairs at D = 256: 3 x 16 KiB half-tile stages)
-        bool full_second_tile = fixed_no_a + (size_t)2 * num_kb * A_CHUNK_BYTES + 3 * stage_bytes <= 227 * 1024;
-        if (const char* env = getenv("VQB_TC_ASLOTS")) full_second_tile = full_second_tile && atoi(env) >= 2 * num_kb;   // experiments
-        if (full_second_tile) a_slots = 2 * num_kb;   // pays with one codebook stage (3 instead of 4: measured equal)
-    }
-    const size_t fixed = (size_t)a_slots * A_CHUNK_BYTES + fixed_no_a;
-    // shared-memory part of the event stacks: whatever four codebook stages leave, at most 3 entries per epilogue thread
-    const size_t ev_entry_bytes = (size_t)EPI_THREADS * EV_WORDS * 4;   // one entry for every epilogue thread: 24 KiB
-    int ev_sm = 0;
-    if (!with_tail && !scores_dbg && 227 * 1024 > fixed + 4 * stage_bytes) {
-        ev_sm = (int)((227 * 1024 - fixed - 4 * stage_bytes) / ev_entry_bytes);
-        if (ev_sm > 3) ev_sm = 3;
-    }
-    if (const char* env = getenv("VQB_TC_EVSM")) { const int v = atoi(env); if (v >= 0 && v < ev_sm) ev_sm = v; }   // experiments
-    const size_t fixed_ev = fixed + (size_t)ev_sm * ev_entry_bytes;
-    int b_stages = (int)((227 * 1024 - fixed_ev) / stage_bytes);
-    if (b_stages > (two ? 8 : 4)) b_stages = two ? 8 : 4;
-    if (const char* env = getenv("VQB_TC_STAGES")) { const int v = atoi(env); if (v >= 2 && v < b_stages) b_stages = v; }   // experiments
-    if (b_stages < 2 || a_slots > MAX_A_SLOTS) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
-    const size_t smem = fixed_ev + (size_t)b_stages * stage_bytes;
+    const TcPlan plan = tc_plan(fuse, with_tail, scores_dbg != nullptr, num_m_tiles, D);
+    if (!plan.ok) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
+    const bool two = plan.two;
+    const int cs = plan.cs, a_slots = plan.a_slots, b_stages = plan.b_stages, ev_sm = plan.ev_sm;
+    const size_t smem = plan.smem;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_search_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
