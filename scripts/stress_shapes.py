@@ -6,6 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import vq_b200
+from vq_b200 import functional as F
 from oracle import vq_oracle as O
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
@@ -43,6 +44,18 @@ for case in range(n_cases):
     ok &= np.allclose(vq.codebook.weight.grad.cpu().numpy(), dE, rtol=1e-4, atol=1e-6 * max(np.abs(dE).max(), 1e-30))
     if np.array_equal(got, ref.indices):
         ok &= np.array_equal(q.detach().cpu().numpy(), ref.quantized)
+    # index export (no `quantized`, no residual sums) and the host-buffer entry point must give the same indices / statistics
+    cbt = vq.codebook.weight.detach()
+    idx2, _, st2 = F.vq_forward(zt.detach(), cbt, precision=precision, want_q=False, want_resid=False)
+    ok &= bool(torch.equal(idx2, idx.reshape(-1)))
+    if case % 4 == 0:
+        zh = torch.from_numpy(z).pin_memory()
+        idx_h = torch.empty(B * W, dtype=torch.int64).pin_memory()
+        st_h = torch.empty(K * (D + 1) + 2, dtype=torch.float32).pin_memory()
+        F.vq_forward_host(zh, torch.from_numpy(cb).pin_memory(), precision=precision, want_resid=True, idx_out=idx_h, stats_out=st_h)
+        ok &= np.array_equal(idx_h.numpy(), got)
+        ok &= np.allclose(st_h.numpy()[:K], st2.cpu().numpy()[:K])
+        ok &= np.allclose(st_h.numpy()[K + K * D], st2.cpu().numpy()[K + K * D], rtol=1e-5)
     if not ok:
         bad += 1
         print("MISMATCH", dict(B=B, D=D, W=W, K=K), flush=True)
