@@ -219,6 +219,17 @@ def test_stage_timing_reports_every_stage_of_the_forward():
     lib.vqb_debug_kernel_timing(0)
 
 
+@pytest.mark.parametrize("precision,seed", [("bf16", 101), ("fp32", 102)])
+def test_random_shapes_against_oracle(precision, seed):
+    """scripts/stress_shapes.py: 80 random (B, D, W, K) incl. ragged / tiny / large-D shapes, forward + backward + index export +
+    host path against the oracle.  (It found the launch-plan bugs fixed in round 1: D = 256 / 512 with fewer than four frame tiles.)"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "stress_shapes.py"), "80", str(seed), precision],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_trained_like_latents_use_single_candidate_shortlists():
     """Clustered latents (codeword + noise): the shortlist is a single code for almost every frame and nothing falls back."""
     K, D = 2048, 128
