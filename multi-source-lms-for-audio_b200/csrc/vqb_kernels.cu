@@ -421,11 +421,13 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
                                 unsigned long long* best64, cudaStream_t s) {
     const int64_t N = (int64_t)B * W;
     const size_t smem = ((size_t)D * XT_M + XT_K * XT_LD + XT_M) * 4 + XT_M * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done_dev[64] = {};             // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done_dev[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(exact_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done_dev[dev & 63] = true;
     }
     const int64_t tiles = (N + XT_M - 1) / XT_M;
     const int per_sm = (int)(220 * 1024 / (smem + 1024)) > 0 ? (int)(220 * 1024 / (smem + 1024)) : 1;
@@ -956,17 +958,19 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
         // batches).  All instances share one signature, hence ONE instantiation of this lambda: the kernel pointer is part of the key.
         static thread_local size_t cached_smem = ~(size_t)0;
         static thread_local const void* cached_kernel = nullptr;
-        static thread_local int cached_blocks = 0;
+        static thread_local int cached_blocks = 0, cached_dev = -1;
         cudaError_t e = cudaSuccess;
-        if (cached_smem != smem || cached_kernel != reinterpret_cast<const void*>(kernel)) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cached_smem != smem || cached_kernel != reinterpret_cast<const void*>(kernel) || cached_dev != dev) {
             if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
-            int per_sm = 1, dev = 0, sms = 148;
+            int per_sm = 1, sms = 148;
             if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * NW, smem)) != cudaSuccess) return e;
-            cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cached_blocks = sms * (per_sm < 1 ? 1 : per_sm);
             cached_smem = smem;
             cached_kernel = reinterpret_cast<const void*>(kernel);
+            cached_dev = dev;
         }
         int64_t grid = cached_blocks;
         if (grid > n_partials) grid = n_partials;
@@ -1226,17 +1230,19 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
         auto go = [&](auto kernel) -> cudaError_t {
             static thread_local size_t cached_smem = ~(size_t)0;   // see launch_tail_tma_t
             static thread_local const void* cached_kernel = nullptr;
-            static thread_local int cached_blocks = 0;
+            static thread_local int cached_blocks = 0, cached_dev = -1;
             cudaError_t e2 = cudaSuccess;
-            if (cached_smem != smem || cached_kernel != reinterpret_cast<const void*>(kernel)) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cached_smem != smem || cached_kernel != reinterpret_cast<const void*>(kernel) || cached_dev != dev) {
                 if ((e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess) return e2;
-                int per_sm = 1, dev = 0, sms = 148;
+                int per_sm = 1, sms = 148;
                 if ((e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem)) != cudaSuccess) return e2;
-                cudaGetDevice(&dev);
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
                 cached_blocks = sms * (per_sm < 1 ? 1 : per_sm);
                 cached_smem = smem;
                 cached_kernel = reinterpret_cast<const void*>(kernel);
+                cached_dev = dev;
             }
             int64_t grid = cached_blocks;
             if (grid > num_tiles) grid = num_tiles;

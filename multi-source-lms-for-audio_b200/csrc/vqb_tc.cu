@@ -1222,7 +1222,8 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     const bool two = plan.two;
     const int cs = plan.cs, a_slots = plan.a_slots, b_stages = plan.b_stages, ev_sm = plan.ev_sm;
     const size_t smem = plan.smem;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};             // function attributes are per device (one process may drive several GPUs)
+    bool& attr_done = attr_done_dev[dev & 63];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_search_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
