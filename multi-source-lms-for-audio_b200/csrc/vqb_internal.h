@@ -114,6 +114,7 @@ cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int6
 
 // 3-D TMA view of a [B, D, W] fp32 tensor (vqb_tc.cu): box = box_frames x box_dims of one batch item; swizzle128 needs
 // box_frames == 32 (128-byte rows) and a 1024-byte aligned destination
+bool latents_read_once(size_t latent_bytes);   // stream the latents with an L2 evict-first policy? (vqb_kernels.cu)
 int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims,
                     bool swizzle128 = false);
 

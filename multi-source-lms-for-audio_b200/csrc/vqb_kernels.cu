@@ -777,7 +777,7 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restr
                 int tiles_per_item, int64_t num_tiles, int box_dims, const int* __restrict__ idx32,
                 const uint8_t* __restrict__ cand_cnt, const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
                 float* __restrict__ q_out, int* __restrict__ counts, float* __restrict__ resid,
-                double* __restrict__ sse_partials, WsMeta* meta, float* resid_rep, int n_rep, size_t rep_stride) {
+                double* __restrict__ sse_partials, WsMeta* meta, float* resid_rep, int n_rep, size_t rep_stride, int l2_once) {
     resid = pick_resid_replica(resid, resid_rep, n_rep, rep_stride);
     using namespace ptx;
     constexpr int TT_WARPS = NW;
@@ -807,8 +807,10 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restr
         const int b = (int)(tile / tiles_per_item), w0 = (int)(tile - (int64_t)b * tiles_per_item) * TL_F;
         const uint32_t bar = smem_u32(&full[buf]);
         mbar_expect_tx(bar, box_bytes);
-        for (int d0 = 0; d0 < D; d0 += box_dims)
-            tma_load_3d(smem_u32(box + ((size_t)buf * D + d0) * TL_F), &tmap_z, bar, w0, d0, b);
+        for (int d0 = 0; d0 < D; d0 += box_dims) {
+            if (l2_once) tma_load_3d_once(smem_u32(box + ((size_t)buf * D + d0) * TL_F), &tmap_z, bar, w0, d0, b);
+            else tma_load_3d(smem_u32(box + ((size_t)buf * D + d0) * TL_F), &tmap_z, bar, w0, d0, b);
+        }
     };
     int64_t tile = blockIdx.x;
     if (threadIdx.x == 0 && tile < num_tiles) issue(tile, 0);
@@ -938,6 +940,13 @@ int resid_replicas(int K, int D) {
 // BASELINE config 3 step), 0 = 8 warps and two boxes (2 blocks per SM: 14.6 ms).  A third form without block barriers (every
 // warp transposing its own 8 frames out of a 128-byte-swizzled box, rescoring pairs dealt out over the lane groups) measured
 // 14.7 ms and was dropped: after the residual replicas the pass is bound by its L2 / DRAM traffic, not by the barriers.
+// Latents far larger than L2 are streamed with an evict-first policy (tma_load_3d_once); small batches keep the default, so
+// that the tail still finds in L2 what the search kernel read (and the backward pass what the tail read).  VQB_L2_ONCE=0/1
+// overrides (experiments).
+bool latents_read_once(size_t latent_bytes) {
+    if (const char* env = getenv("VQB_L2_ONCE")) return env[0] != '0';
+    return latent_bytes > ((size_t)96 << 20);
+}
 static int tail_tma_variant() {
     if (const char* env = getenv("VQB_TAIL_VARIANT")) return atoi(env);
     return 1;
@@ -977,7 +986,8 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
         if (grid > num_tiles) grid = num_tiles;
         if (grid < 1) grid = 1;
         kernel<<<(unsigned)grid, 32 * NW, smem, s>>>(map, codebook, e2, D, W, tiles_per_item, num_tiles, box_dims, idx32, cand_cnt, cand_idx,
-                                                           idx_out, q_out, counts, resid, part, meta, resid_rep, n_rep, rep_stride);
+                                                           idx_out, q_out, counts, resid, part, meta, resid_rep, n_rep, rep_stride,
+                                                           latents_read_once((size_t)num_tiles * TL_F * D * 4) ? 1 : 0);
         return cudaGetLastError();
     };
     return resid ? go(tail_tma_kernel<LPF, J, true, NW, NB>) : go(tail_tma_kernel<LPF, J, false, NW, NB>);

@@ -40,6 +40,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// Polling wait (no hardware suspend): for the two barriers of the accumulator hand-shake, where the wake-up latency of a
+// suspended warp sits on the critical path when one codebook tile is only a few hundred tensor-core cycles (small D).
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((it & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) __trap();
+        }
+    }
+}
 // One lane of a converged warp; ptxas recognises the elect.sync predicate and issues the following tcgen05 / TMA
 // instructions directly instead of wrapping each one in an elect-and-retry loop.
 __device__ __forceinline__ bool elect_one() {
@@ -56,6 +77,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// The same load with an L2 evict-first policy: latents are read once per pass, and as evict-normal lines they push the hot
+// working set (codebook, |e|^2, residual-sum replicas) out of L2 (ncu, tail at BASELINE config 3: 53 % of the residual
+// reductions missed L2).  0x12F0... is the fixed encoding of createpolicy.fractional.L2::evict_first with fraction 1.0.
+__device__ __forceinline__ void tma_load_3d_once(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(0x12F0000000000000ull)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {

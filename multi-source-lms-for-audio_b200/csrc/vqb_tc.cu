@@ -39,7 +39,7 @@ constexpr int UMMA_K = 16;
 constexpr int A_CHUNK_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int EH_SLICE_BYTES = BN * 16;      // 4 KiB: (h1,h2,h3,0,0,0,0,0) bf16 per code = K-half 0 of the bias operand
-constexpr int EH_SLOTS = 2;
+constexpr int EH_SLOTS = 2, MAX_EH_SLOTS = 8;   // default / maximum depth of the bias-operand ring (runtime: eh_slots)
 constexpr int AX_BYTES = BM * 16;            // 2 KiB: K-half 0 of the constant A operand
 constexpr int ZERO_BYTES = EH_SLICE_BYTES;   // shared all-zero K-half 1 of both bias operands
 // fused operand preparation: fp32 latents arrive straight from the reference's [B, D, W] layout as 3-D TMA boxes of
@@ -67,7 +67,7 @@ constexpr int kCandFill = 12;                // shortlist entries published per 
 struct Barriers {
     unsigned long long b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
     unsigned long long a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
-    unsigned long long eh_full[EH_SLOTS], eh_empty[EH_SLOTS], tmem_full[2], tmem_empty[2];
+    unsigned long long eh_full[MAX_EH_SLOTS], eh_empty[MAX_EH_SLOTS], tmem_full[2], tmem_empty[2];
     unsigned long long stg_full[STG_SLOTS], stg_empty[STG_SLOTS];
     unsigned int tmem_base;
     unsigned int pad;
@@ -262,7 +262,7 @@ __device__ __forceinline__ float slab_max32(const uint32_t (&r)[32]) {
 // The four threads that share a frame (one per column quarter, in four different warps) pool their running maximum in
 // shared memory (`smax`): every thread's threshold tracks the best score ANY quarter has seen, which cuts the number of
 // appended chunks per frame from 4 x ln(K/32) to ln(K/8)-ish.
-__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, float hband, float& thr, EventStack& ev, int* smax) {
+__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, float hband, float& thr, EventStack& ev, int* smax, int dbg = 0) {
     thr = fmaxf(thr, ord2f(*reinterpret_cast<volatile int*>(smax)) - hband);
     float t[4];
 #pragma unroll
@@ -273,7 +273,7 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, f
         t[g] = fmaxf(m, __uint_as_float(r[g * 8 + 7]));
     }
     const float slab_max = fmaxf(fmaxf(fmaxf(t[0], t[1]), t[2]), t[3]);
-    if (slab_max > thr) {
+    if (slab_max > thr && !(dbg & 256)) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) ev.push_if(t[g] > thr, t[g], chunk0 + g, &r[g * 8]);
         thr = fmaxf(thr, slab_max - hband);
@@ -438,13 +438,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
-                 const TailArgs tail, const int tail_dbg, const int ev_sm) {
+                 const TailArgs tail, const int tail_dbg, const int ev_sm, const int l2_once, const int eh_slots) {
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
     unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB (16 KiB half tiles in 2-CTA mode)
-    unsigned char* sEH = sB + (size_t)b_stages * (kTwo ? B_STAGE_BYTES / 2 : B_STAGE_BYTES);   // EH_SLOTS x 4 KiB bias operand B (K-half 0)
-    unsigned char* sAX = sEH + EH_SLOTS * EH_SLICE_BYTES;                // 2 KiB constant bias operand A (K-half 0)
+    unsigned char* sEH = sB + (size_t)b_stages * (kTwo ? B_STAGE_BYTES / 2 : B_STAGE_BYTES);   // eh_slots x 4 KiB bias operand B (K-half 0)
+    unsigned char* sAX = sEH + eh_slots * EH_SLICE_BYTES;                // 2 KiB constant bias operand A (K-half 0)
     unsigned char* sZero = sAX + AX_BYTES;                               // 4 KiB of zeros: K-half 1 of both bias operands
     unsigned char* sStg = sZero + ZERO_BYTES;                            // fused mode: STG_SLOTS x 8 KiB fp32 boxes [16 dims][128 frames]
     float* sBand = reinterpret_cast<float*>(sStg + (kFuse ? STG_SLOTS * STG_BYTES : 0));   // fused mode: [2][128] guard bands
@@ -488,7 +488,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
         }
         for (int i = 0; i < STG_SLOTS; ++i) { mbar_init(smem_u32(&bars->stg_full[i]), 1); mbar_init(smem_u32(&bars->stg_empty[i]), 2); }
-        for (int i = 0; i < EH_SLOTS; ++i) {
+        for (int i = 0; i < eh_slots; ++i) {
             mbar_init(smem_u32(&bars->eh_full[i]), 1);
             mbar_init(smem_u32(&bars->eh_empty[i]), 1);
         }
@@ -549,7 +549,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                 }
                 __syncwarp();
-                if (++es == EH_SLOTS) { es = 0; e_ph ^= 1; }
+                if (++es == (uint32_t)eh_slots) { es = 0; e_ph ^= 1; }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     uint32_t slot = a_slot0 + kb, a_phk = a_ph;          // ring position of chunk kb of this tile
                     if (slot >= (uint32_t)a_slots) { slot -= a_slots; a_phk ^= 1; }
@@ -598,7 +598,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t bar_tfull = smem_u32(&bars->tmem_full[0]), bar_tempty = smem_u32(&bars->tmem_empty[0]);
         for (int rd = 0; rd < rounds; ++rd) {
             for (int nt = 0; nt < num_n_tiles; ++nt) {
-                mbar_wait(bar_tempty + as * 8, t_ph ^ 1);
+                if (tail_dbg & 8192) mbar_wait_poll(bar_tempty + as * 8, t_ph ^ 1);
+                else mbar_wait(bar_tempty + as * 8, t_ph ^ 1);
                 const uint32_t tmem_d = tmem_base + as * BN;
                 const bool last_nt = nt == num_n_tiles - 1;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -648,7 +649,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                 }
                 __syncwarp();
-                if (++es == EH_SLOTS) { es = 0; e_ph ^= 1; }
+                if (++es == (uint32_t)eh_slots) { es = 0; e_ph ^= 1; }
                 as ^= 1;
                 if (as == 0) t_ph ^= 1;
             }
@@ -682,7 +683,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int b_ = mt_ / tiles_per_item, w0_ = (mt_ - b_ * tiles_per_item) * BM;
                 if (elect_one()) {
                     mbar_expect_tx(bar_sfull + sl_ * 8, STG_BYTES);
-                    tma_load_3d(sS_u + sl_ * STG_BYTES, &tmap_x, bar_sfull + sl_ * 8, w0_, sub_ * SUB_DIMS, b_);   // frames past W arrive as zeros
+                    // frames past W arrive as zeros
+                    if (l2_once) tma_load_3d_once(sS_u + sl_ * STG_BYTES, &tmap_x, bar_sfull + sl_ * 8, w0_, sub_ * SUB_DIMS, b_);
+                    else tma_load_3d(sS_u + sl_ * STG_BYTES, &tmap_x, bar_sfull + sl_ * 8, w0_, sub_ * SUB_DIMS, b_);
                 }
                 __syncwarp();
                 ++issued;
@@ -903,7 +906,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             ev.n = 0;
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1;
-                mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
+                if (tail_dbg & 8192) mbar_wait_poll(smem_u32(&bars->tmem_full[as]), ph);
+                else mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
                 tc_fence_after();
                 if (kFuse && nt == 0) {                   // the converter published this tile's bands before the first MMA could start
                     band = sBand[(rd & 1) * BM + row_in_tile];
@@ -912,7 +916,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t taddr = tmem_base + t_lane + as * BN + colq * COLS_PER_WARP;
                 const int code0 = nt * BN + colq * COLS_PER_WARP;
                 uint32_t ra[32];
-                if (nt == 0 && !scores_dbg) {
+                if (nt == 0 && !scores_dbg && !(tail_dbg & 1024)) {
                     // First codebook tile of a frame tile: the threshold is still -inf and everything would be appended.  Take
                     // the tile's maximum first (the accumulator stays in TMEM), then scan it with a tight threshold.
                     float pre = -INFINITY;
@@ -932,7 +936,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (scores_dbg) {
                         if (row < N) dump_slab(ra, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
                     } else {
-                        scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev, smax);
+                        if (!(tail_dbg & 2048)) scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev, smax, tail_dbg);
                     }
                 }
                 tc_fence_before();
@@ -954,7 +958,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 uint16_t* dst = kTail ? sCand + (tbuf * BM + row_in_tile) * kCandFill : cand_idx + (size_t)row * kCandMax;
                 const int n_ev = ev.n < EV_CAP ? ev.n : EV_CAP;
                 bool lost = ev.n > EV_CAP || !(band < INFINITY);
-                for (int e0 = 0; e0 < n_ev; e0 += 8) {
+                if ((tail_dbg & 4096) && colq == 0) { dst[0] = 0; sCnt[row_in_tile] = 1; }   // timing experiments: code 0 for everybody
+                for (int e0 = 0; e0 < ((tail_dbg & 512) ? 0 : n_ev); e0 += 8) {
                     uint2 hd[8];     // headers (chunk maximum, chunk id) of 8 events fetched together: one L2 latency, not eight
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
@@ -1093,7 +1098,7 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 // (tc_can_fuse, tc_fused_tail_fits).
 struct TcPlan {
     bool ok, two;
-    int cs, a_slots, b_stages, ev_sm;
+    int cs, a_slots, b_stages, ev_sm, eh_slots;
     size_t smem;
 };
 
@@ -1115,7 +1120,13 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     // the last chunks of the next tile can only be converted inside the last codebook tile), else two spare chunks.
     p.a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
     if (fuse && num_kb > 2 && num_kb + 2 <= 6) p.a_slots = num_kb + 2;
-    const size_t fixed_no_a = EH_SLOTS * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
+    // Bias-operand ring.  The producer walks the codebook tiles in order and waits for the bias slot of tile j before it
+    // loads anything of tile j, so this ring bounds how far ALL operand loads run ahead of the tensor core.  Two slots are
+    // plenty when one codebook tile takes the tensor core microseconds (D = 256); with one or two K blocks per tile
+    // (D <= 128) the loads must be several tiles ahead to cover the L2 -> shared latency.
+    p.eh_slots = num_kb <= 2 ? MAX_EH_SLOTS : EH_SLOTS;
+    if (const char* env = getenv("VQB_TC_EHSLOTS")) { const int v = atoi(env); if (v >= 2 && v <= MAX_EH_SLOTS) p.eh_slots = v; }   // experiments
+    const size_t fixed_no_a = (size_t)p.eh_slots * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
                               (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
                               (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
                               sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
@@ -1256,12 +1267,13 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     TimingSlot* slot = timing_begin(s);
     cudaError_t le;
     const TailArgs targs = with_tail ? *tail_args : TailArgs{};
+    const int l2_once = (fuse && latents_read_once((size_t)N * D * 4)) ? 1 : 0;   // stream the latents past the L2-resident working set
     int tail_dbg = 0;                              // experiments only: switch parts of the fused tail off (results are then wrong)
     if (const char* env = getenv("VQB_TAIL_DBG")) tail_dbg = atoi(env);
 #define VQB_TC_LAUNCH(TWO, FUSE, TAIL)                                                                                                       \
     le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
                             num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \
-                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, tail_dbg, ev_sm)
+                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, tail_dbg, ev_sm, l2_once, plan.eh_slots)
     if (two && with_tail) VQB_TC_LAUNCH(true, true, true);
     else if (with_tail) VQB_TC_LAUNCH(false, true, true);
     else if (two && fuse) VQB_TC_LAUNCH(true, true, false);
