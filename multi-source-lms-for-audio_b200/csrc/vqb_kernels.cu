@@ -640,17 +640,19 @@ __device__ __forceinline__ void tail_frame(float* Xs, int ld, int f, int64_t n, 
         for (int j = 0; j < J; ++j) {
             const int d = 4 * sl + 4 * LPF * j;
             if (d < D) {
-                float4 df, st;
-                df.x = __fsub_rn(qv[j].x, xv[j].x); df.y = __fsub_rn(qv[j].y, xv[j].y);
-                df.z = __fsub_rn(qv[j].z, xv[j].z); df.w = __fsub_rn(qv[j].w, xv[j].w);
-                fs = fmaf(df.x, df.x, fs); fs = fmaf(df.y, df.y, fs); fs = fmaf(df.z, df.z, fs); fs = fmaf(df.w, df.w, fs);
-                st.x = __fadd_rn(xv[j].x, df.x); st.y = __fadd_rn(xv[j].y, df.y);      // straight-through VALUE (:48)
-                st.z = __fadd_rn(xv[j].z, df.z); st.w = __fadd_rn(xv[j].w, df.w);
+                // r = fl(x - e) is exactly -fl(e - x): the residual sums want r, and the straight-through VALUE
+                // fl(x + fl(e - x)) (:48) equals fl(x - r) bit for bit - no negations
+                float4 r, st;
+                r.x = __fsub_rn(xv[j].x, qv[j].x); r.y = __fsub_rn(xv[j].y, qv[j].y);
+                r.z = __fsub_rn(xv[j].z, qv[j].z); r.w = __fsub_rn(xv[j].w, qv[j].w);
+                fs = fmaf(r.x, r.x, fs); fs = fmaf(r.y, r.y, fs); fs = fmaf(r.z, r.z, fs); fs = fmaf(r.w, r.w, fs);
+                st.x = __fsub_rn(xv[j].x, r.x); st.y = __fsub_rn(xv[j].y, r.y);
+                st.z = __fsub_rn(xv[j].z, r.z); st.w = __fsub_rn(xv[j].w, r.w);
                 *reinterpret_cast<float4*>(Xs + f * ld + d) = st;
                 if (kResid) {
                     float* rp = resid + (size_t)k * D + d;
-                    if (resid_v4) red_add_v4(rp, -df.x, -df.y, -df.z, -df.w);
-                    else { atomicAdd(rp, -df.x); atomicAdd(rp + 1, -df.y); atomicAdd(rp + 2, -df.z); atomicAdd(rp + 3, -df.w); }
+                    if (resid_v4) red_add_v4(rp, r.x, r.y, r.z, r.w);
+                    else { atomicAdd(rp, r.x); atomicAdd(rp + 1, r.y); atomicAdd(rp + 2, r.z); atomicAdd(rp + 3, r.w); }
                 }
             }
         }

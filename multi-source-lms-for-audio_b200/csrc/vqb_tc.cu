@@ -1121,10 +1121,10 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     p.a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
     if (fuse && num_kb > 2 && num_kb + 2 <= 6) p.a_slots = num_kb + 2;
     // Bias-operand ring.  The producer walks the codebook tiles in order and waits for the bias slot of tile j before it
-    // loads anything of tile j, so this ring bounds how far ALL operand loads run ahead of the tensor core.  Two slots are
-    // plenty when one codebook tile takes the tensor core microseconds (D = 256); with one or two K blocks per tile
-    // (D <= 128) the loads must be several tiles ahead to cover the L2 -> shared latency.
-    p.eh_slots = num_kb <= 2 ? MAX_EH_SLOTS : EH_SLOTS;
+    // loads anything of tile j, so this ring bounds how far ALL operand loads run ahead of the tensor core.  Measured at
+    // K = 1024, D = 64 (where a codebook tile is only ~640 tensor-core cycles): 2, 4 and 8 slots give the same kernel time -
+    // the operand loads are not what bounds small shapes.
+    p.eh_slots = EH_SLOTS;
     if (const char* env = getenv("VQB_TC_EHSLOTS")) { const int v = atoi(env); if (v >= 2 && v <= MAX_EH_SLOTS) p.eh_slots = v; }   // experiments
     const size_t fixed_no_a = (size_t)p.eh_slots * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
                               (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
