@@ -173,10 +173,12 @@ def test_fused_tail_variant_matches_oracle(B, D, W, K, cb_scale, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"VQB_TAIL_TMA": "0"}, {"VQB_TAIL_VARIANT": "0"}, {"VQB_RESID_REPLICAS": "1"},
-                                 {"VQB_RESID_REPLICAS": "8"}, {"VQB_DX_TILES": "1"}, {"VQB_TC_ASLOTS": "6"}])
+                                 {"VQB_RESID_REPLICAS": "8"}, {"VQB_DX_TILES": "1"}, {"VQB_TC_ASLOTS": "6"},
+                                 {"VQB_L2_ONCE": "1"}, {"VQB_TC_EHSLOTS": "5"}, {"VQB_TAIL_DBG": "8192"}])
 def test_kernel_variants_agree_with_the_default_path(env, monkeypatch):
     """The experiment switches select other forms of the same kernels (register-staged tail, 8-warp TMA tail, one / eight
-    residual-sum replicas, tile-staged backward, two spare A chunks): indices and `quantized` must be identical, statistics and
+    residual-sum replicas, tile-staged backward, two spare A chunks, evict-first latent loads, a deeper bias-operand ring,
+    polling accumulator hand-shake): indices and `quantized` must be identical, statistics and
     gradients equal up to the summation order of the atomics.  A hot code (a quarter of the frames) stresses the replicas."""
     B, D, W, K, beta = 3, 256, 1536, 700, 0.25
     cb = seeded(11, (K, D))
