@@ -1086,9 +1086,18 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
     const cuuint64_t strides[2] = {W * 4, D * W * 4};
     const cuuint32_t box[3] = {box_frames, box_dims, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    // L2 promotion no wider than a box row: with 128-byte rows (the tail's 32-frame boxes) a 256-byte promotion also fetches the
+    // neighbouring tile's sectors, which another block wants at another time - under the evict-first policy they were gone
+    // by then and came from DRAM twice (ncu: +3 GB of evict-first misses at BASELINE config 3)
+    CUtensorMapL2promotion promo = box_frames * 4 >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* env = getenv("VQB_TMA_PROMO")) {   // experiments: 0 none, 64, 128, 256
+        const int v = atoi(env);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(z), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(z) failed with CUresult %d", (int)r); return 1000 + (int)r; }
     return 0;
 }
