@@ -1279,6 +1279,9 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     const int l2_once = (fuse && latents_read_once((size_t)N * D * 4)) ? 1 : 0;   // stream the latents past the L2-resident working set
     int tail_dbg = 0;                              // experiments only: switch parts of the fused tail off (results are then wrong)
     if (const char* env = getenv("VQB_TAIL_DBG")) tail_dbg = atoi(env);
+    // every bit except 8192 (polling hand-shake) produces WRONG results: they are honoured only together with an explicit opt-in,
+    // so that a stray environment variable can never corrupt a run
+    if (!getenv("VQB_TIMING_EXPERIMENTS")) tail_dbg &= 8192;
 #define VQB_TC_LAUNCH(TWO, FUSE, TAIL)                                                                                                       \
     le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
                             num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \

@@ -3,7 +3,7 @@
 # (VQB_TAIL_DBG bits 256 / 512 / 1024 / 2048 switch parts of it off; results are then wrong, only the stage time is read)
 wl=${1:-cfg2}
 for spec in "0" "256" "512" "1024" "2048" "768" "3584" ; do
-  VQB_TAIL_DBG=$spec timeout 120 python bench.py --workload $wl --no-e2e --no-cpu --no-train --no-sampler 2>/dev/null | python -c "
+  VQB_TIMING_EXPERIMENTS=1 VQB_TAIL_DBG=$spec timeout 120 python bench.py --workload $wl --no-e2e --no-cpu --no-train --no-sampler 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('dbg=$spec', 'search %.4f ms' % d['stage_ms_per_step']['search'], 'step %.4f' % d['ms_per_step'], d['shortlist'])"
 done
