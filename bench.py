@@ -30,6 +30,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner to stdout under
+    NCCL_DEBUG=VERSION, which the GPU boxes set).  Keep a private handle on the real stdout for the JSON line and point
+    file descriptor 1 at stderr for everything else."""
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return out
+
 WORKLOADS = {
     # name: (B per GPU, D, W, K, description)
     "cfg3": (1024, 256, 16384, 8192, "quantizer-only N=2^24/GPU K=8192 D=256 (BASELINE.json configs[2])"),
@@ -41,6 +51,7 @@ WORKLOADS = {
     "cfg4": (64, 64, 11000, 512, "VQ-VAE training step, 64 clips/GPU of 4 x 44000 samples, K=512 D=64 (BASELINE.json configs[3])"),
 }
 BETA = 0.25
+JSON_OUT = sys.stdout
 
 
 def load_traffic(workload: str):
@@ -151,7 +162,7 @@ def run_reference(args):
             "config": {"workload": desc, "K": K, "D": D, "frames_per_step": n, "note": "CPU oracle port of the reference quantiser"},
             "cpu_baseline": {"value": value, "unit": "vectors/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 def run_vqvae_step(args):
@@ -283,7 +294,7 @@ def run_vqvae_step(args):
             "quantiser_ms_per_step": sum(stages.values()), "stage_ms_per_step": stages,
             "clips_per_s": B * world / (ms_per_step * 1e-3),
             "losses": {"total": float(loss.item()), "perplexity": float(ppl.item())}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -304,6 +315,8 @@ def main():
     ap.add_argument("--no-q", action="store_true", help="diagnostic: index export only (no quantized output)")
     ap.add_argument("--no-sampler", action="store_true", help="diagnostic: do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
+    global JSON_OUT
+    JSON_OUT = claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -493,7 +506,7 @@ def main():
             "shortlist": {"rescored_frames_per_step": counters["rescored"], "fallback_frames_per_step": counters["fallback"],
                           "mean_candidates": counters["shortlisted"] / max(1, N)},
             "losses": {"embedding": loss_vals[0], "commitment": loss_vals[1], "perplexity": loss_vals[2]}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
