@@ -34,3 +34,21 @@ def test_state_dict_keys_match_reference_checkpoint():
     assert not missing and not unexpected
     assert codebook_io.STATE_DICT_KEY in ref_sd
     assert torch.equal(codebook_io.codebook_from_state_dict(ref_sd), model.vector_quantizer.codebook.weight.detach())
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU port of the reference on the host cores): exactly one JSON line on stdout with
+    the contract's keys; under torchrun only rank 0 prints."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "0"})
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert out.returncode == 0 and len(lines) == 1, (out.returncode, out.stdout, out.stderr[-500:])
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
+    assert other.returncode == 0 and other.stdout.strip() == ""
