@@ -539,7 +539,8 @@ __global__ void __launch_bounds__(256) fold_resid_kernel(float* __restrict__ res
 // `given`: cl_lo.x already is the final code (exact search).  All 32 lanes of the warp must call this together.
 struct TailAcc { float sse, sse_c; unsigned int n_resc, n_short; };
 
-template <int LPF, int J, bool kResid>
+// kExact: D == 4 * LPF * J (D = 32, 64, 128, 256 ...): no dimension guards, no zero fill, constant strides.
+template <int LPF, int J, bool kResid, bool kExact = false>
 __device__ __forceinline__ void tail_frame(float* Xs, int ld, int f, int64_t n, bool live, int cnt_in, uint4 cl_lo, uint4 cl_hi, bool given,
                                            const float* __restrict__ E, const float* __restrict__ e2, int D,
                                            int64_t* __restrict__ idx_out, int* __restrict__ counts, float* __restrict__ resid,
@@ -552,7 +553,7 @@ __device__ __forceinline__ void tail_frame(float* Xs, int ld, int f, int64_t n, 
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         const int d = 4 * sl + 4 * LPF * j;
-        xv[j] = (d < D) ? *reinterpret_cast<const float4*>(Xs + f * ld + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[j] = (kExact || d < D) ? *reinterpret_cast<const float4*>(Xs + f * ld + d) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const int cnt = cnt_in;
     int k = given ? (int)cl_lo.x : (int)(cl_lo.x & 0xFFFFu);
@@ -590,7 +591,7 @@ __device__ __forceinline__ void tail_frame(float* Xs, int ld, int f, int64_t n, 
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int d = 4 * sl + 4 * LPF * j;
-            ev[j] = (d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kc * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ev[j] = (kExact || d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kc * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         for (int ci = 0; ci < cmax; ++ci) {
             const bool act = need && ci < cnt;
@@ -600,7 +601,7 @@ __device__ __forceinline__ void tail_frame(float* Xs, int ld, int f, int64_t n, 
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const int d = 4 * sl + 4 * LPF * j;
-                    en[j] = (d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kn * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    en[j] = (kExact || d < D) ? *reinterpret_cast<const float4*>(E + (size_t)kn * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             float dot = 0.f;
@@ -633,13 +634,13 @@ __device__ __forceinline__ void tail_frame(float* Xs, int ld, int f, int64_t n, 
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int d = 4 * sl + 4 * LPF * j;
-            qv[j] = (d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            qv[j] = (kExact || d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float fs = 0.f;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int d = 4 * sl + 4 * LPF * j;
-            if (d < D) {
+            if (kExact || d < D) {
                 // r = fl(x - e) is exactly -fl(e - x): the residual sums want r, and the straight-through VALUE
                 // fl(x + fl(e - x)) (:48) equals fl(x - r) bit for bit - no negations
                 float4 r, st;
@@ -773,15 +774,18 @@ __global__ void __launch_bounds__(32 * TAIL_WARPS, (J >= 6) ? 4 : 6) tail_kernel
 // the box into the frame-major tile, worked on and written back.  No thread ever waits on a global latent load, which is what
 // bounded tail_kernel (latency, 25 % occupancy).  Needs W % 4 == 0 (TMA global strides are multiples of 16 bytes).
 // NW warps per block, NB box buffers (1: the next box is requested right after the transposition freed the buffer).
-template <int LPF, int J, bool kResid, int NW, int NB>
+template <int LPF, int J, bool kResid, int NW, int NB, bool kExact>
 __global__ void __launch_bounds__(32 * NW, (NW == 4) ? ((J <= 2) ? 6 : ((J <= 4) ? 4 : 3)) : ((J >= 6) ? 2 : 3))
-tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restrict__ E, const float* __restrict__ e2, int D, int64_t W,
+tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restrict__ E, const float* __restrict__ e2, int D_arg, int64_t W,
                 int tiles_per_item, int64_t num_tiles, int box_dims, const int* __restrict__ idx32,
                 const uint8_t* __restrict__ cand_cnt, const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out,
                 float* __restrict__ q_out, int* __restrict__ counts, float* __restrict__ resid,
                 double* __restrict__ sse_partials, WsMeta* meta, float* resid_rep, int n_rep, size_t rep_stride, int l2_once) {
     resid = pick_resid_replica(resid, resid_rep, n_rep, rep_stride);
     using namespace ptx;
+    // kExact (D == 4 * LPF * J, the usual 64 / 128 / 256): D is a compile-time constant - row strides and codebook offsets fold
+    // into immediates and the per-lane dimension guards disappear (ncu: half of the per-frame instructions were such overhead)
+    const int D = kExact ? 4 * LPF * J : D_arg;
     constexpr int TT_WARPS = NW;
     extern __shared__ __align__(128) float tt_smem[];   // NB x [D][32] TMA boxes, then the frame-major tile [32][D + 4]
     __shared__ double red[TT_WARPS];
@@ -861,20 +865,28 @@ tail_tma_kernel(const __grid_constant__ CUtensorMap tmap_z, const float* __restr
 #pragma unroll
         for (int i = 0; i < ITER; ++i) {
             const int f = warp * (TL_F / TT_WARPS) + i * FPW + sub;
-            tail_frame<LPF, J, kResid>(Xs, ld, f, n0 + f, f < wlim, cnt_r[i], cl_lo[i], cl_hi[i], idx32 != nullptr, E, e2, D, idx_out, counts,
+            tail_frame<LPF, J, kResid, kExact>(Xs, ld, f, n0 + f, f < wlim, cnt_r[i], cl_lo[i], cl_hi[i], idx32 != nullptr, E, e2, D, idx_out, counts,
                                        resid, resid_v4, sl, acc);
         }
         if (q_out) {
             __syncthreads();
             if (lane < wlim) {
-                float* qp = q_out + (size_t)b * D * W + w0 + lane;
+                // four running row pointers (one 64-bit add each per step) instead of a 64-bit multiply per store
+                const size_t step = (size_t)(4 * TT_WARPS) * W;
+                float* p0 = q_out + ((size_t)b * D + warp * 4) * W + w0 + lane;
+                float* p1 = p0 + W;
+                float* p2 = p1 + W;
+                float* p3 = p2 + W;
+                const float* xs = Xs + lane * ld + warp * 4;
+#pragma unroll 4
                 for (int d0 = warp * 4; d0 < D; d0 += 4 * TT_WARPS) {
-                    const float4 v = *reinterpret_cast<const float4*>(Xs + lane * ld + d0);
-                    float* p = qp + (size_t)d0 * W;
-                    st_stream(p, v.x);
-                    st_stream(p + W, v.y);
-                    st_stream(p + 2 * W, v.z);
-                    st_stream(p + 3 * W, v.w);
+                    const float4 v = *reinterpret_cast<const float4*>(xs);
+                    st_stream(p0, v.x);
+                    st_stream(p1, v.y);
+                    st_stream(p2, v.z);
+                    st_stream(p3, v.w);
+                    p0 += step; p1 += step; p2 += step; p3 += step;
+                    xs += 4 * TT_WARPS;
                 }
             }
         }
@@ -992,7 +1004,13 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
                                                            latents_read_once((size_t)num_tiles * TL_F * D * 4) ? 1 : 0);
         return cudaGetLastError();
     };
-    return resid ? go(tail_tma_kernel<LPF, J, true, NW, NB>) : go(tail_tma_kernel<LPF, J, false, NW, NB>);
+    static const bool exact_ok = !(getenv("VQB_TAIL_EXACT") && getenv("VQB_TAIL_EXACT")[0] == '0');   // experiments
+    // The default single-box form gets the constant-D specialisation where it measured faster: D = 192 (-2.7 %) and D = 256
+    // (-3.3 %, 12.9 -> 12.5 ms at BASELINE config 3).  For D <= 128 the generic form is faster (D = 128: +6 %, D = 64: +24 %,
+    // D = 32: +21 % with the constant-D code), so J <= 4 keeps it.
+    if (D == 4 * LPF * J && NB == 1 && J >= 6 && exact_ok)
+        return resid ? go(tail_tma_kernel<LPF, J, true, NW, NB, NB == 1>) : go(tail_tma_kernel<LPF, J, false, NW, NB, NB == 1>);
+    return resid ? go(tail_tma_kernel<LPF, J, true, NW, NB, false>) : go(tail_tma_kernel<LPF, J, false, NW, NB, false>);
 }
 
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
