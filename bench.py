@@ -106,12 +106,25 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         rows = [r for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        note = None
+        if not rows:   # timed region shorter than the 100 ms polling period (tiny workloads): one query right after it
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=20).stdout
+                rows = [[c.strip() for c in l.split(",")] for l in out.splitlines()]
+                rows = [r for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+                note = "timed region shorter than the polling period: sampled once right after it"
+            except (OSError, subprocess.TimeoutExpired):
+                rows = []
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": statistics.median(float(r[0]) for r in rows), "sm_max_mhz": float(rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+        res = {"sm_mhz": statistics.median(float(r[0]) for r in rows), "sm_max_mhz": float(rows[0][1]),
+               "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+        if note:
+            res["note"] = note
+        return res
 
 
 def cpu_port_rate(K: int, D: int, rows_total: int, chunk: int, repeats: int = 1):
