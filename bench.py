@@ -511,7 +511,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 shortlist + fp32 rescoring" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": desc, "frames_per_gpu": N, "K": K, "D": D, "precision": args.precision, "parallelism": f"dp{world}",
-                       "l2": "inputs (>=268 MB per step) larger than the 126 MB L2; no explicit flush",
+                       "l2": (f"inputs ({N * D * 4 / 1e6:.0f} MB of latents per step) larger than the 126 MB L2; no explicit flush"
+                              if N * D * 4 > 126e6 else
+                              f"inputs ({N * D * 4 / 1e6:.1f} MB of latents per step) FIT in the 126 MB L2 and are not flushed: an L2-warm "
+                              "number (parity-case workload, not the bench configuration)"),
                        "step": ("index export (indices + BERT windows + masks)" if export_only else
                                 "training-mode forward (indices + quantized + stats + losses)")},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "roofline_tail": roofline_tail, "cpu_baseline": cpu, "train_step": train,
