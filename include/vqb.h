@@ -12,7 +12,13 @@
  *    positive = the cudaError_t / ncclResult_t (+1000) of a failed runtime call.  vqb_last_error() returns a
  *    thread-local human-readable message for the last non-zero return on this thread.
  *  - Calls only enqueue work on `stream`; they never synchronise the host and use no hidden streams, so a sequence of
- *    calls is CUDA-graph capturable.  Scalars (losses, perplexity) are written to device memory.
+ *    calls is CUDA-graph capturable.  Scalars (losses, perplexity) are written to device memory.  (Exceptions, named
+ *    below: vqb_forward_host and the vqb_debug_* readers synchronise.)
+ *  - Threading: the data-path calls keep no state between calls and may be issued concurrently from several threads,
+ *    devices and streams as long as each call has its own workspace.  NOT re-entrant: vqb_forward_host on one device
+ *    (serialised internally), and the vqb_debug_* timing / launch counters (process-global, for single-threaded benches).
+ *  - Index arguments are validated on the device: a code outside [0, K) touches no memory; its one-hot row stays zero,
+ *    its gathered codeword / gradient is NaN.
  *  - There is no CPU fallback.  A device that is not compute capability 10.x is a hard error (VQB_E_DEVICE).
  *  - Latents are fp32 in the reference's [B, D, W] ("BCW") layout; frame n = b*W + w (vector_quantizer.py:25-29).
  *    The codebook is fp32 [K, D] row-major (nn.Embedding weight, vector_quantizer.py:18).
@@ -27,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VQB_VERSION 100
+#define VQB_VERSION 200
 #if defined(__GNUC__)
 #define VQB_API __attribute__((visibility("default")))
 #else
@@ -38,7 +44,8 @@ extern "C" {
 #define VQB_PREC_MASK   0x0F
 #define VQB_PREC_FP32   0x00  /* exact: fp32 CUDA-core search in the reference's op order (parity anchor / fallback)    */
 #define VQB_PREC_BF16   0x01  /* tcgen05 bf16 shortlist + guard band, fp32 rescoring in the reference's op order        */
-#define VQB_PREC_TF32   0x02  /* tcgen05 tf32 shortlist (same structure, 8x tighter band)                               */
+#define VQB_PREC_TF32   0x02  /* tcgen05 kind::tf32 shortlist straight from the fp32 operands (no converted copies, tighter
+                                 band, half the tensor rate of bf16) + the same fp32 rescoring                           */
 #define VQB_WANT_Q      0x10  /* write the straight-through value fl(x + fl(q - x)) to q_bcw_out (v_q.py:42,48,52)      */
 #define VQB_WANT_RESID  0x20  /* accumulate per-code residual sums into stats (needed for the codebook gradient)        */
 
@@ -57,9 +64,13 @@ extern "C" {
 VQB_API int         vqb_version(void);
 VQB_API const char* vqb_last_error(void);
 
-/* Bytes of scratch vqb_forward needs for N = B*W frames.  (Replaces the N x K fp32 `distances` and `encodings`
- * temporaries of vector_quantizer.py:32-39, which are never materialised here.) */
+/* Bytes of scratch vqb_forward needs.  (Replaces the N x K fp32 `distances` and `encodings` temporaries of
+ * vector_quantizer.py:32-39, which are never materialised here.)
+ * vqb_workspace_bytes:    upper bound for ANY [B, W] with B * W = N (includes a bf16 latent copy that only shapes the
+ *                         tensor-core kernel cannot read directly need: W % 4 != 0, short clips).
+ * vqb_workspace_bytes_bw: exact for one [B, D, W] shape (16-byte aligned latents, which vqb_forward requires anyway). */
 VQB_API int vqb_workspace_bytes(int64_t N, int K, int D, int flags, size_t* bytes_out);
+VQB_API int vqb_workspace_bytes_bw(int B, int D, int64_t W, int K, int flags, size_t* bytes_out);
 
 /* Forward of the bottleneck: vector_quantizer.py:25-52 minus the dense one-hot.
  *   z_bcw      [B, D, W] fp32        codebook  [K, D] fp32
@@ -106,10 +117,13 @@ VQB_API int vqb_ema_update(const float* stats, float* codebook, float* cluster_s
                            float decay, float eps, void* stream);
 
 /* Host-buffer convenience used for end-to-end timing and by non-torch callers: copies z (pinned or pageable HOST
- * memory) to the device in chunks overlapped with compute, runs vqb_forward per chunk of whole batch items and
- * copies indices (and stats) back.  Allocates its own device scratch on first use (freed by vqb_host_release). */
+ * memory) to the device in chunks overlapped with compute, runs vqb_forward per chunk of whole batch items and copies
+ * the indices, with VQB_WANT_Q the straight-through output (what a call of the reference returns, vector_quantizer.py:54;
+ * full duplex with the uploads) and the statistics back.  `comm` (may be NULL) all-reduces the statistics over the ranks
+ * before they are copied back.  SYNCHRONOUS, on private streams of the CURRENT device; its device scratch is cached per
+ * device (vqb_host_release frees the current device's) and calls on the same device serialise on a mutex. */
 VQB_API int vqb_forward_host(const float* z_bcw_host, const float* codebook_host, int B, int D, int64_t W, int K, int flags,
-                     int64_t* idx_out_host, float* stats_out_host, int chunk_batches);
+                     int64_t* idx_out_host, float* q_bcw_out_host, float* stats_out_host, int chunk_batches, void* comm);
 VQB_API int vqb_host_release(void);
 
 /* ---- multi-GPU: the one exchange on the path (implicit DDP all-reduce of codebook.weight.grad in the reference,
@@ -130,6 +144,9 @@ VQB_API int vqb_debug_tc_scores(const float* z_bcw, const float* codebook, int B
 
 /* Number of this library's kernel launches since the last reset (bench.py's `gpu_launches`). */
 VQB_API long long vqb_debug_launch_count(int reset);
+/* The experiment switches of DESIGN.md section 8 (VQB_* environment variables) are read once and honoured only when
+ * VQB_EXPERIMENTS=1 is set; this re-reads them (tests flip them inside one process). */
+VQB_API int vqb_debug_reload_env(void);
 /* CUDA-event timing of the stages of vqb_forward on its launching stream: enable, run, then read the summed duration and
  * launch count of a stage (bench.py's roofline leg).  At most 2048 stage launches are recorded per enable.
  * vqb_debug_kernel_time_ms reads VQB_STAGE_SEARCH, the dominant kernel (tc_search_kernel). */

@@ -22,6 +22,7 @@ _SIGNATURES = {
     "vqb_version": (C.c_int, []),
     "vqb_last_error": (C.c_char_p, []),
     "vqb_workspace_bytes": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "vqb_workspace_bytes_bw": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "vqb_forward": (C.c_int, [_c_f32p, _c_f32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, _c_f32p, _c_f32p,
                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "vqb_finalize": (C.c_int, [_c_f32p, C.c_int, C.c_int, C.c_float, _c_f32p, C.c_void_p]),
@@ -31,7 +32,8 @@ _SIGNATURES = {
     "vqb_onehot": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _c_f32p, C.c_void_p]),
     "vqb_gather": (C.c_int, [_c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, _c_f32p, C.c_void_p]),
     "vqb_window_indices": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_void_p, _c_f32p, C.c_void_p]),
-    "vqb_forward_host": (C.c_int, [_c_f32p, _c_f32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, _c_f32p, C.c_int]),
+    "vqb_forward_host": (C.c_int, [_c_f32p, _c_f32p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, _c_f32p, _c_f32p,
+                                   C.c_int, C.c_void_p]),
     "vqb_host_release": (C.c_int, []),
     "vqb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "vqb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -39,6 +41,7 @@ _SIGNATURES = {
     "vqb_comm_destroy": (C.c_int, [C.c_void_p]),
     "vqb_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "vqb_debug_launch_count": (C.c_longlong, [C.c_int]),
+    "vqb_debug_reload_env": (C.c_int, []),
     "vqb_debug_kernel_timing": (C.c_int, [C.c_int]),
     "vqb_debug_kernel_time_ms": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "vqb_debug_stage_time_ms": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -65,6 +68,7 @@ def lib() -> C.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python multi-source-lms-for-audio_b200/build.py` "
                 "(or __graft_entry__.build()).  The vector-quantiser hot path is CUDA-only; there is no fallback.")
+        import torch  # noqa: F401  (brings libcudart.so.12 into the process: the library links the CUDA runtime dynamically)
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)   # AttributeError here means the .so is stale

@@ -37,7 +37,7 @@ def _stamp() -> str:
         if os.path.isfile(p):
             h.update(name.encode())
             h.update(open(p, "rb").read())
-    h.update(" ".join(ARCH + NVCC_FLAGS).encode())
+    h.update(" ".join(ARCH + NVCC_FLAGS + ["cudart-shared"]).encode())
     return h.hexdigest()
 
 
@@ -63,7 +63,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [exe, *ARCH, "-shared", "-o", LIB, *objs, "-ldl"]
+    # --cudart shared: reuse the CUDA runtime the host process (torch) already carries instead of embedding a second, static
+    # copy with its whole export table; _lib.lib() imports torch first, so libcudart.so.12 is resolved by soname
+    cmd = [exe, *ARCH, "-shared", "--cudart", "shared", "-o", LIB, *objs, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

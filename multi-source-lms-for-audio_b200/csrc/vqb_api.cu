@@ -4,7 +4,11 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
+#include <mutex>
 
 namespace vqb {
 
@@ -21,12 +25,40 @@ int cuda_fail(cudaError_t e, const char* what) {
     return (int)e;
 }
 
-static long long g_launches = 0;
+// ---- experiment switches: one table, filled once -----------------------------------------------------------------------
+static const char* const kEnvNames[ENV_COUNT] = {
+    "VQB_TC_MODE", "VQB_TC_CLUSTER", "VQB_TC_FUSE", "VQB_TC_STAGES", "VQB_TC_ASLOTS", "VQB_TC_EVSM", "VQB_TC_EHSLOTS", "VQB_TC_TAIL",
+    "VQB_TMA_PROMO", "VQB_TILE_LDG", "VQB_RESID_REPLICAS", "VQB_L2_ONCE", "VQB_TAIL_VARIANT", "VQB_TAIL_TMA", "VQB_TAIL_EXACT",
+    "VQB_DX_TILES", "VQB_TC_EPI", "VQB_TAIL_FORM"};
+static int g_env_val[ENV_COUNT];
+static bool g_env_set[ENV_COUNT];
+static std::atomic<bool> g_env_loaded{false};
+static std::mutex g_env_mutex;
+
+void env_reload() {
+    std::lock_guard<std::mutex> lock(g_env_mutex);
+    const char* gate = getenv("VQB_EXPERIMENTS");
+    const bool on = gate && gate[0] == '1';
+    for (int i = 0; i < ENV_COUNT; ++i) {
+        const char* v = on ? getenv(kEnvNames[i]) : nullptr;
+        g_env_set[i] = v != nullptr && v[0] != 0;
+        g_env_val[i] = g_env_set[i] ? atoi(v) : 0;
+    }
+    g_env_loaded.store(true, std::memory_order_release);
+}
+int env_get(EnvKey key, int unset_value) {
+    if (!g_env_loaded.load(std::memory_order_acquire)) env_reload();
+    return g_env_set[key] ? g_env_val[key] : unset_value;
+}
+
+static std::atomic<long long> g_launches{0};
 void note_launch(int n) { g_launches += n; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-WsLayout ws_layout(int64_t N, int K, int D, int flags) {
+// need_xb: reserve the bf16 latent copy (only the unfused operand preparation touches it: 2 N D bytes, 8.6 GB at BASELINE
+// config 3); ev_ctas: CTAs of the search kernel the event scratch must serve (<= kTcMaxCtas).
+WsLayout ws_layout(int64_t N, int K, int D, int flags, bool need_xb, int ev_ctas) {
     WsLayout L{};
     const int prec = flags & VQB_PREC_MASK;
     L.k_pad = (K + kTileCodes - 1) / kTileCodes * kTileCodes;
@@ -51,8 +83,8 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags) {
         L.x2 = take((size_t)L.n_pad * 4);
         L.eb = take((size_t)L.k_pad * D * 2);
         L.eh = take((size_t)L.k_pad * 16);
-        L.xb = take((size_t)L.n_pad * D * 2);
-        L.ev = take(tc_event_scratch_bytes());
+        L.xb = need_xb ? take((size_t)L.n_pad * D * 2) : 0;
+        L.ev = take(tc_event_scratch_bytes(ev_ctas));
     }
     L.total = off;
     return L;
@@ -93,6 +125,16 @@ static int check_shape(int B, int D, int64_t W, int K) {
         if (e__ != cudaSuccess) return cuda_fail(e__, what);   \
     } while (0)
 
+// Exact layout for one [B, D, W] call.  z == nullptr: a 16-byte aligned tensor (vqb_forward insists on that anyway).
+WsLayout ws_layout_for(const float* z, int B, int D, int64_t W, int K, int flags) {
+    const int prec = flags & VQB_PREC_MASK;
+    const int64_t N = (int64_t)B * W;
+    if (prec == VQB_PREC_FP32) return ws_layout(N, K, D, flags, false, 0);
+    const bool fuse = tc_can_fuse(z, B, D, W, prec);
+    const int64_t tiles = fuse ? (int64_t)B * ((W + kTileRows - 1) / kTileRows) : (N + kTileRows - 1) / kTileRows;
+    return ws_layout(N, K, D, flags, !fuse, (int)(tiles < kTcMaxCtas ? tiles : kTcMaxCtas));
+}
+
 // accumulate: keep counts / resid / SSE / N from earlier chunks (used by the host-buffer path)
 int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W, int K, int flags, int64_t* idx_out,
                  float* q_out, float* stats_out, void* workspace, size_t ws_bytes, cudaStream_t s, bool accumulate,
@@ -105,8 +147,8 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
     }
     if ((rc = check_shape(B, D, W, K)) != 0) return rc;
     const int prec = flags & VQB_PREC_MASK;
-    if (prec != VQB_PREC_FP32 && prec != VQB_PREC_BF16) {
-        set_error("vqb_forward: precision %d is not built in this version (use VQB_PREC_FP32 or VQB_PREC_BF16)", prec);
+    if (prec != VQB_PREC_FP32 && prec != VQB_PREC_BF16 && prec != VQB_PREC_TF32) {
+        set_error("vqb_forward: unknown precision %d (VQB_PREC_FP32, VQB_PREC_BF16 or VQB_PREC_TF32)", prec);
         return VQB_E_FLAGS;
     }
     if ((flags & VQB_WANT_Q) && !q_out) {
@@ -118,7 +160,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         return VQB_E_ALIGN;
     }
     const int64_t N = (int64_t)B * W;
-    const WsLayout L = ws_layout(N, K, D, flags);
+    const WsLayout L = ws_layout_for(z, B, D, W, K, flags);
     if (ws_bytes < L.total) {
         set_error("vqb_forward: workspace has %zu bytes, %zu needed", ws_bytes, L.total);
         return VQB_E_WORKSPACE;
@@ -212,8 +254,18 @@ int vqb_workspace_bytes(int64_t N, int K, int D, int flags, size_t* bytes_out) {
         return VQB_E_SHAPE;
     }
     const int prec = flags & VQB_PREC_MASK;
-    if (prec != VQB_PREC_FP32 && prec != VQB_PREC_BF16) { set_error("vqb_workspace_bytes: unknown precision %d", prec); return VQB_E_FLAGS; }
-    *bytes_out = ws_layout(N, K, D, flags).total;
+    if (prec != VQB_PREC_FP32 && prec != VQB_PREC_BF16 && prec != VQB_PREC_TF32) { set_error("vqb_workspace_bytes: unknown precision %d", prec); return VQB_E_FLAGS; }
+    *bytes_out = ws_layout(N, K, D, flags, true, kTcMaxCtas).total;   // upper bound over every [B, W] with B * W = N
+    return 0;
+}
+
+int vqb_workspace_bytes_bw(int B, int D, int64_t W, int K, int flags, size_t* bytes_out) {
+    if (!bytes_out) { set_error("vqb_workspace_bytes_bw: NULL output"); return VQB_E_NULL; }
+    int rc;
+    if ((rc = check_shape(B, D, W, K)) != 0) return rc;
+    const int prec = flags & VQB_PREC_MASK;
+    if (prec != VQB_PREC_FP32 && prec != VQB_PREC_BF16 && prec != VQB_PREC_TF32) { set_error("vqb_workspace_bytes_bw: unknown precision %d", prec); return VQB_E_FLAGS; }
+    *bytes_out = ws_layout_for(nullptr, B, D, W, K, flags).total;
     return 0;
 }
 
@@ -289,9 +341,12 @@ int vqb_window_indices(const int64_t* idx, int B, int64_t L, int window, int64_t
 }
 
 long long vqb_debug_launch_count(int reset) {
-    const long long v = g_launches;
-    if (reset) g_launches = 0;
-    return v;
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int vqb_debug_reload_env(void) {
+    env_reload();
+    return 0;
 }
 
 int vqb_debug_counters(const void* workspace, int64_t* counters_out_host) {

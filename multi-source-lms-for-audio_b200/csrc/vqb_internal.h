@@ -34,10 +34,11 @@ struct WsLayout {
     int64_t n_pad;
     int    n_partials;
 };
-WsLayout ws_layout(int64_t N, int K, int D, int flags);
+WsLayout ws_layout(int64_t N, int K, int D, int flags, bool need_xb, int ev_ctas);
+WsLayout ws_layout_for(const float* z, int B, int D, int64_t W, int K, int flags);   // z may be null (= 16-byte aligned)
 
 constexpr int kTcMaxCtas = 160;         // persistent grid bound of the tensor-core search (event scratch is sized for it)
-size_t tc_event_scratch_bytes();
+size_t tc_event_scratch_bytes(int ctas);
 constexpr int kTailGridMax = 148 * 8;   // persistent grid of the fused tail kernel (sse partial slots)
 constexpr int kResidReplicasMax = 8;     // residual-sum replicas against same-address atomic serialisation (see pick_resid_replica)
 constexpr int kFallbackTailGrid = 148;  // fused-tail mode: sse slots [kTcMaxCtas, kTcMaxCtas + kFallbackTailGrid) belong to fallback_tail_kernel
@@ -45,6 +46,16 @@ constexpr int kFallbackTailGrid = 148;  // fused-tail mode: sse slots [kTcMaxCta
 // CUDA-event pair around one stage of vqb_forward when vqb_debug_kernel_timing(1) is on (else begin returns null, end is a no-op)
 void* stage_timing_begin(cudaStream_t s, int stage);
 void  stage_timing_end(void* slot, cudaStream_t s);
+
+// Experiment switches.  They are read ONCE (first use, or vqb_debug_reload_env()) and honoured only when
+// VQB_EXPERIMENTS=1 is set: a stray variable can never change production behaviour and the launch path never calls getenv.
+enum EnvKey {
+    ENV_TC_MODE, ENV_TC_CLUSTER, ENV_TC_FUSE, ENV_TC_STAGES, ENV_TC_ASLOTS, ENV_TC_EVSM, ENV_TC_EHSLOTS, ENV_TC_TAIL, ENV_TMA_PROMO,
+    ENV_TILE_LDG, ENV_RESID_REPLICAS, ENV_L2_ONCE, ENV_TAIL_VARIANT, ENV_TAIL_TMA, ENV_TAIL_EXACT, ENV_DX_TILES, ENV_TC_EPI, ENV_TAIL_FORM,
+    ENV_COUNT
+};
+int  env_get(EnvKey key, int unset_value);         // value of the switch, or unset_value when it is not set / not enabled
+void env_reload();
 
 void set_error(const char* fmt, ...);
 void note_launch(int n = 1);                       // counts this library's kernel launches (vqb_debug_launch_count)
@@ -120,7 +131,7 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 
 // ---- tensor-core search (vqb_tc.cu) ---------------------------------------------------------------------------
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.
-bool tc_can_fuse(const float* z, int B, int D, int64_t W);   // can the tensor-core kernel read the fp32 [B, D, W] latents itself?
+bool tc_can_fuse(const float* z, int B, int D, int64_t W, int prec = VQB_PREC_BF16);   // can the tensor-core kernel read the fp32 [B, D, W] latents itself?
 bool tc_fused_tail_fits(int B, int D, int64_t W);            // ... and its shared memory leaves room for the tile pipeline
 bool tc_fused_tail_enabled();                               // VQB_TC_TAIL=0 keeps the stand-alone tail kernel (experiments)
 // z_fused != nullptr: fused operand preparation (xb / band unused); else xb / band from latent_prep_bf16_kernel

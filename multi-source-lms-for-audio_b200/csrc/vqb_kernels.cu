@@ -31,6 +31,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 // better() / ref_distance() / red_add_v4(): vqb_internal.h (shared with the fused tail of the tensor-core kernel)
 
+// Caller-supplied indices (BERT-predicted tokens, bert.py:72-78) are never trusted: a code outside [0, K) touches no memory.
+// Its one-hot row stays all-zero, its gathered codeword / gradient is NaN (loud in the data); the Python wrappers also
+// validate on the host and raise IndexError (the reference's scatter_ / one-hot matmul raise a device assert).
+__device__ __forceinline__ bool code_ok(int64_t k, int K) { return (unsigned long long)k < (unsigned long long)K; }
+
 // ------------------------------------------------------------------------------------------------ codebook prep
 // One warp per code: |e_k|^2 in fp32 (vector_quantizer.py:33), bf16 copy for the tensor-core tiles, max |e|^2 for the
 // guard band, non-finite flag.  Rows K..K_pad-1 get e2 = +inf (never shortlisted) and zero operands.
@@ -92,9 +97,7 @@ cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D,
 }
 
 static int tile_ldg_mode() {   // tile loads: register-staged LDG batches (default, measured faster) or cp.async (VQB_TILE_LDG=0)
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("VQB_TILE_LDG"); mode = (e && e[0] == '0') ? 0 : 1; }
-    return mode;
+    return env_get(ENV_TILE_LDG, 1) == 0 ? 0 : 1;
 }
 
 // ------------------------------------------------------------------------------------------------ frame tiles
@@ -439,8 +442,10 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
         note_launch();
         return cudaGetLastError();
     }
+    // one 64-code tile per slice up to K = 8192: the list is a handful of frames, so the kernel's duration is the serial chain of
+    // one block (codebook chunk load -> barrier -> 16 FMA steps, per 16 dims) - 4 tiles per slice were 0.2 ms of every step
     int ksplit = (K + XT_N - 1) / XT_N;
-    if (ksplit > 32) ksplit = 32;
+    if (ksplit > 128) ksplit = 128;
     if (grid > 148) grid = 148;
     exact_search_kernel<<<dim3((unsigned)grid, (unsigned)ksplit), 256, smem, s>>>(z, codebook, e2, D, W, N, K, rows, row_count, nullptr,
                                                                                  best64);
@@ -943,7 +948,7 @@ static cudaError_t launch_tail_t(const float* z, const float* codebook, const fl
 // between 2 and kResidReplicasMax.  Measured at BASELINE config 3 (8 MiB per copy): 21.0 ms with one copy, 13.7 ms with two, no
 // further gain from four or eight; small codebooks (the reference's K = 512) have hotter codes and get all eight.
 int resid_replicas(int K, int D) {
-    if (const char* env = getenv("VQB_RESID_REPLICAS")) { const int v = atoi(env); if (v >= 1 && v <= kResidReplicasMax) return v; }
+    if (const int v = env_get(ENV_RESID_REPLICAS, 0); v >= 1 && v <= kResidReplicasMax) return v;
     const size_t per_copy = (size_t)K * D * 4;
     size_t n = (16u << 20) / (per_copy ? per_copy : 1);
     if (n < 2) n = 2;
@@ -958,16 +963,14 @@ int resid_replicas(int K, int D) {
 // that the tail still finds in L2 what the search kernel read (and the backward pass what the tail read).  VQB_L2_ONCE=0/1
 // overrides (experiments).
 bool latents_read_once(size_t latent_bytes) {
-    if (const char* env = getenv("VQB_L2_ONCE")) return env[0] != '0';
+    if (const int v = env_get(ENV_L2_ONCE, -1); v >= 0) return v != 0;
     return latent_bytes > ((size_t)96 << 20);
 }
 static int tail_tma_variant() {
-    if (const char* env = getenv("VQB_TAIL_VARIANT")) return atoi(env);
-    return 1;
+    return env_get(ENV_TAIL_VARIANT, 1);
 }
 static bool tail_tma_enabled() {   // VQB_TAIL_TMA=0 keeps the register-staged tail_kernel (experiments)
-    if (const char* env = getenv("VQB_TAIL_TMA")) return env[0] != '0';
-    return true;
+    return env_get(ENV_TAIL_TMA, 1) != 0;
 }
 
 template <int LPF, int J, int NW, int NB>
@@ -1004,7 +1007,7 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
                                                            latents_read_once((size_t)num_tiles * TL_F * D * 4) ? 1 : 0);
         return cudaGetLastError();
     };
-    static const bool exact_ok = !(getenv("VQB_TAIL_EXACT") && getenv("VQB_TAIL_EXACT")[0] == '0');   // experiments
+    const bool exact_ok = env_get(ENV_TAIL_EXACT, 1) != 0;   // experiments
     // The default single-box form gets the constant-D specialisation where it measured faster: D = 192 (-2.7 %) and D = 256
     // (-3.3 %, 12.9 -> 12.5 ms at BASELINE config 3).  For D <= 128 the generic form is faster (D = 128: +6 %, D = 64: +24 %,
     // D = 32: +21 % with the constant-D code), so J <= 4 keeps it.
@@ -1127,7 +1130,7 @@ template <int LPF, int J>
 __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                              const int64_t* __restrict__ idx, const float* __restrict__ Gq,
                                                              const float* __restrict__ g_c, float beta, int D, int64_t W,
-                                                             int64_t N, float* __restrict__ dX, int ldg) {
+                                                             int64_t N, int K, float* __restrict__ dX, int ldg) {
     extern __shared__ __align__(16) float Xs[];   // [32][D + 4] latents, then [32][D + 4] upstream gradient
     constexpr int FPW = 32 / LPF;
     constexpr int ITER = (TL_F / 8) / FPW;
@@ -1162,13 +1165,15 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) backward_dx_kernel(cons
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int f = warp * (TL_F / 8) + it * FPW + sub;
-            const float* er = E + (size_t)k_r[it] * D;
+            const bool ok = code_ok(k_r[it], K);
+            const float* er = E + (size_t)(ok ? k_r[it] : 0) * D;
+            const float nanv = __int_as_float(0x7fc00000);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const int d = 4 * sl + 4 * LPF * j;
                 if (d < D) {
                     const float4 x = *reinterpret_cast<const float4*>(Xs + f * ld + d);
-                    const float4 q = *reinterpret_cast<const float4*>(er + d);
+                    const float4 q = ok ? *reinterpret_cast<const float4*>(er + d) : make_float4(nanv, nanv, nanv, nanv);
                     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (Gq) g = *reinterpret_cast<const float4*>(Gs + f * ld + d);
                     float4 o;
@@ -1194,7 +1199,7 @@ template <int J>
 __global__ void __launch_bounds__(256) backward_dx_rows_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                                const int64_t* __restrict__ idx, const float* __restrict__ Gq,
                                                                const float* __restrict__ g_c, float beta, int D, int64_t W, int64_t N,
-                                                               int tiles_per_item, int64_t num_tiles, float* __restrict__ dX) {
+                                                               int K, int tiles_per_item, int64_t num_tiles, float* __restrict__ dX) {
     extern __shared__ __align__(16) float Es[];   // [D][33] codeword components of the tile's frames, dim-major
     constexpr int LPF = 8, EP = TL_F + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1207,12 +1212,15 @@ __global__ void __launch_bounds__(256) backward_dx_rows_kernel(const float* __re
             const int f = warp * 4 + sub;
             const bool live = w0 + f < W;
             const int64_t k = live ? idx[(int64_t)b * W + w0 + f] : 0;
-            const float* er = E + (size_t)k * D;
+            const bool ok = code_ok(k, K);
+            const float* er = E + (size_t)(ok ? k : 0) * D;
+            const float nanv = __int_as_float(0x7fc00000);
             float4 ev[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const int d = 4 * sl + 4 * LPF * j;
-                ev[j] = (live && d < D) ? *reinterpret_cast<const float4*>(er + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ev[j] = (live && d < D) ? (ok ? *reinterpret_cast<const float4*>(er + d) : make_float4(nanv, nanv, nanv, nanv))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -1249,11 +1257,9 @@ __global__ void __launch_bounds__(256) backward_dx_rows_kernel(const float* __re
 
 cudaError_t launch_backward_dx(const float* z, const float* codebook, const int64_t* idx, const float* Gq, const float* g_c,
                                float beta, int B, int D, int64_t W, int K, float* dX, cudaStream_t s) {
-    (void)K;
     const int64_t N = (int64_t)B * W;
     cudaError_t e = cudaSuccess;
-    const char* old_env = getenv("VQB_DX_TILES");
-    if (D <= 256 && !(old_env && old_env[0] == '1')) {
+    if (D <= 256 && env_get(ENV_DX_TILES, 0) != 1) {
         const int tiles_per_item = (int)((W + TL_F - 1) / TL_F);
         const int64_t num_tiles = (int64_t)B * tiles_per_item;
         const size_t smem = (size_t)D * (TL_F + 1) * 4;
@@ -1277,7 +1283,7 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
             int64_t grid = cached_blocks;
             if (grid > num_tiles) grid = num_tiles;
             if (grid < 1) grid = 1;
-            kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, tiles_per_item, num_tiles, dX);
+            kernel<<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, K, tiles_per_item, num_tiles, dX);
             return cudaGetLastError();
         };
         if (D <= 32) e = go(backward_dx_rows_kernel<1>);
@@ -1297,7 +1303,7 @@ cudaError_t launch_backward_dx(const float* z, const float* codebook, const int6
 #define VQB_DX(LPF, J)                                                                                                          \
     do {                                                                                                                        \
         e = cudaFuncSetAttribute(backward_dx_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);          \
-        if (e == cudaSuccess) backward_dx_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, dX, tile_ldg_mode()); \
+        if (e == cudaSuccess) backward_dx_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(z, codebook, idx, Gq, g_c, beta, D, W, N, K, dX, tile_ldg_mode()); \
     } while (0)
     VQB_DISPATCH_D(D, VQB_DX);
 #undef VQB_DX
@@ -1377,7 +1383,10 @@ cudaError_t launch_ema_update(const float* stats, float* codebook, float* cluste
 // ------------------------------------------------------------------------------------------------ one-hot / gather / windows
 __global__ void __launch_bounds__(256) onehot_kernel(const int64_t* __restrict__ idx, int64_t N, int K, float* __restrict__ out) {
     const int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (n < N) out[(size_t)n * K + idx[n]] = 1.0f;
+    if (n < N) {
+        const int64_t k = idx[n];
+        if (code_ok(k, K)) out[(size_t)n * K + k] = 1.0f;
+    }
 }
 
 cudaError_t launch_onehot(const int64_t* idx, int64_t N, int K, float* out, cudaStream_t s) {
@@ -1390,7 +1399,7 @@ cudaError_t launch_onehot(const int64_t* idx, int64_t N, int K, float* out, cuda
 
 template <int LPF, int J>
 __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) gather_kernel(const float* __restrict__ E, const int64_t* __restrict__ idx, int D,
-                                                        int64_t W, int64_t N, float* __restrict__ out) {
+                                                        int64_t W, int64_t N, int K, float* __restrict__ out) {
     extern __shared__ __align__(16) float Xs[];   // [32][D + 4]
     constexpr int FPW = 32 / LPF;
     constexpr int ITER = (TL_F / 8) / FPW;
@@ -1409,11 +1418,14 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) gather_kernel(const flo
             const int f = warp * (TL_F / 8) + it * FPW + sub;
             const int64_t n = tile * TL_F + f;
             if (n < N) {
-                const float* er = E + (size_t)idx[n] * D;
+                const int64_t k = idx[n];
+                const bool ok = code_ok(k, K);
+                const float* er = E + (size_t)(ok ? k : 0) * D;
+                const float nanv = __int_as_float(0x7fc00000);
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const int d = 4 * sl + 4 * LPF * j;
-                    if (d < D) *reinterpret_cast<float4*>(Xs + f * ld + d) = *reinterpret_cast<const float4*>(er + d);
+                    if (d < D) *reinterpret_cast<float4*>(Xs + f * ld + d) = ok ? *reinterpret_cast<const float4*>(er + d) : make_float4(nanv, nanv, nanv, nanv);
                 }
             }
         }
@@ -1423,7 +1435,6 @@ __global__ void __launch_bounds__(256, (J >= 6) ? 2 : 3) gather_kernel(const flo
 }
 
 cudaError_t launch_gather(const float* codebook, const int64_t* idx, int B, int D, int64_t W, int K, float* out, cudaStream_t s) {
-    (void)K;
     const int64_t N = (int64_t)B * W;
     const size_t smem = (size_t)TL_F * (D + 4) * 4;
     const int64_t tiles = (N + TL_F - 1) / TL_F;
@@ -1433,7 +1444,7 @@ cudaError_t launch_gather(const float* codebook, const int64_t* idx, int B, int 
 #define VQB_GA(LPF, J)                                                                                                 \
     do {                                                                                                               \
         e = cudaFuncSetAttribute(gather_kernel<LPF, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);       \
-        if (e == cudaSuccess) gather_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(codebook, idx, D, W, N, out);    \
+        if (e == cudaSuccess) gather_kernel<LPF, J><<<(unsigned)grid, 256, smem, s>>>(codebook, idx, D, W, N, K, out); \
     } while (0)
     VQB_DISPATCH_D(D, VQB_GA);
 #undef VQB_GA

@@ -262,7 +262,7 @@ __device__ __forceinline__ float slab_max32(const uint32_t (&r)[32]) {
 // The four threads that share a frame (one per column quarter, in four different warps) pool their running maximum in
 // shared memory (`smax`): every thread's threshold tracks the best score ANY quarter has seen, which cuts the number of
 // appended chunks per frame from 4 x ln(K/32) to ln(K/8)-ish.
-__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, float hband, float& thr, EventStack& ev, int* smax, int dbg = 0) {
+__device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, float hband, float& thr, EventStack& ev, int* smax) {
     thr = fmaxf(thr, ord2f(*reinterpret_cast<volatile int*>(smax)) - hband);
     float t[4];
 #pragma unroll
@@ -273,7 +273,7 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, f
         t[g] = fmaxf(m, __uint_as_float(r[g * 8 + 7]));
     }
     const float slab_max = fmaxf(fmaxf(fmaxf(t[0], t[1]), t[2]), t[3]);
-    if (slab_max > thr && !(dbg & 256)) {
+    if (slab_max > thr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) ev.push_if(t[g] > thr, t[g], chunk0 + g, &r[g * 8]);
         thr = fmaxf(thr, slab_max - hband);
@@ -345,11 +345,8 @@ __device__ __forceinline__ void tail_issue(const RingPos& pos, int ahead, int di
     if (sl >= (uint32_t)TX_SLOTS) { sl -= TX_SLOTS; ph ^= 1u; }
     mbar_wait(bar_empty + sl * 8, ph ^ 1u);
     if (elect_one()) {
-        if (b < 0) mbar_arrive(bar_full + sl * 8);   // experiment: no load at all
-        else {
         mbar_expect_tx(bar_full + sl * 8, TX_BYTES);
         tma_load_3d(sTx_u + sl * TX_BYTES, map, bar_full + sl * 8, w0, dim0, b);
-        }
     }
     __syncwarp();
 }
@@ -438,7 +435,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
-                 const TailArgs tail, const int tail_dbg, const int ev_sm, const int l2_once, const int eh_slots) {
+                 const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots) {
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                            // a_slots x 16 KiB
@@ -598,8 +595,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t bar_tfull = smem_u32(&bars->tmem_full[0]), bar_tempty = smem_u32(&bars->tmem_empty[0]);
         for (int rd = 0; rd < rounds; ++rd) {
             for (int nt = 0; nt < num_n_tiles; ++nt) {
-                if (tail_dbg & 8192) mbar_wait_poll(bar_tempty + as * 8, t_ph ^ 1);
-                else mbar_wait(bar_tempty + as * 8, t_ph ^ 1);
+                mbar_wait(bar_tempty + as * 8, t_ph ^ 1);
                 const uint32_t tmem_d = tmem_base + as * BN;
                 const bool last_nt = nt == num_n_tiles - 1;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -792,13 +788,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int b = mt / tiles_per_item, w0 = (mt - b * tiles_per_item) * BM;
                 const int cnt = sCandCnt[tbuf * BM + f];
                 const uint16_t* cl = sCand + (tbuf * BM + tw * 32) * kCandFill;   // this warp's 32 shortlists
-                const int sweeps = (tail_dbg & 1) ? 0 : tail_max_sweeps(sCandCnt + tbuf * BM, lane);
+                const int sweeps = tail_max_sweeps(sCandCnt + tbuf * BM, lane);
                 if (loader) {                                // prime the ring: the first TX_AHEAD boxes of this tile
                     const int total_boxes = (sweeps + 1) * nbox;
                     for (int a = 0; a < TX_AHEAD && a < total_boxes; ++a) {
                         int gi = a;
                         while (gi >= nbox) gi -= nbox;
-                        tail_issue(pos, a, gi * TAIL_CHUNK, (tail_dbg & 64) ? -1 : b, w0, smem_u32(sTx), bar_full, bar_empty, &tmap_xt);
+                        tail_issue(pos, a, gi * TAIL_CHUNK, b, w0, smem_u32(sTx), bar_full, bar_empty, &tmap_xt);
                     }
                 }
                 int k = cnt ? (int)cl[lane * kCandFill] : 0;
@@ -827,7 +823,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     float dot = 0.f, x2 = 0.f;
                     tail_stream<false>(sTx, bar_full, bar_empty, pos, nbox, act, tw * 32 + fl,
                                        tail.codebook + (size_t)kc * D, lane, dot, x2, W, nullptr, nullptr,
-                                       false, pol_once, loader, (sweeps - sw) * nbox, (tail_dbg & 64) ? -1 : b, w0, &tmap_xt);
+                                       false, pol_once, loader, (sweeps - sw) * nbox, b, w0, &tmap_xt);
                     const float dist = act ? ref_distance(x2, tail.e2[kc], dot) : 0.f;
                     pair[lane] = make_float2(dist, __int_as_float(kc));
                     __syncwarp();
@@ -848,10 +844,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     atomicAdd(tail.counts + k, 1);
                 }
                 float fs = 0.f, unused = 0.f;
-                tail_stream<true>(sTx, bar_full, bar_empty, pos, nbox, cnt != 0 && !(tail_dbg & 16), f,
+                tail_stream<true>(sTx, bar_full, bar_empty, pos, nbox, cnt != 0, f,
                                   tail.codebook + (size_t)k * D, lane, fs, unused, W,
-                                  (tail.q_out && !(tail_dbg & 2)) ? tail.q_out + at : nullptr,
-                                  (tail.resid && !(tail_dbg & 4)) ? tail.resid + (size_t)k * D : nullptr, resid_v4, pol_once, loader, 0, (tail_dbg & 64) ? -1 : b,
+                                  tail.q_out ? tail.q_out + at : nullptr,
+                                  tail.resid ? tail.resid + (size_t)k * D : nullptr, resid_v4, pol_once, loader, 0, b,
                                   w0, &tmap_xt);
                 // per-warp running totals live in shared memory (lane 0 only): registers are scarce in this kernel
                 fs = cnt ? fs : 0.f;
@@ -906,8 +902,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             ev.n = 0;
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1;
-                if (tail_dbg & 8192) mbar_wait_poll(smem_u32(&bars->tmem_full[as]), ph);
-                else mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
+                mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
                 tc_fence_after();
                 if (kFuse && nt == 0) {                   // the converter published this tile's bands before the first MMA could start
                     band = sBand[(rd & 1) * BM + row_in_tile];
@@ -916,7 +911,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t taddr = tmem_base + t_lane + as * BN + colq * COLS_PER_WARP;
                 const int code0 = nt * BN + colq * COLS_PER_WARP;
                 uint32_t ra[32];
-                if (nt == 0 && !scores_dbg && !(tail_dbg & 1024)) {
+                if (nt == 0 && !scores_dbg) {
                     // First codebook tile of a frame tile: the threshold is still -inf and everything would be appended.  Take
                     // the tile's maximum first (the accumulator stays in TMEM), then scan it with a tight threshold.
                     float pre = -INFINITY;
@@ -936,7 +931,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (scores_dbg) {
                         if (row < N) dump_slab(ra, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
                     } else {
-                        if (!(tail_dbg & 2048)) scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev, smax, tail_dbg);
+                        scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev, smax);
                     }
                 }
                 tc_fence_before();
@@ -958,8 +953,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 uint16_t* dst = kTail ? sCand + (tbuf * BM + row_in_tile) * kCandFill : cand_idx + (size_t)row * kCandMax;
                 const int n_ev = ev.n < EV_CAP ? ev.n : EV_CAP;
                 bool lost = ev.n > EV_CAP || !(band < INFINITY);
-                if ((tail_dbg & 4096) && colq == 0) { dst[0] = 0; sCnt[row_in_tile] = 1; }   // timing experiments: code 0 for everybody
-                for (int e0 = 0; e0 < ((tail_dbg & 512) ? 0 : n_ev); e0 += 8) {
+                for (int e0 = 0; e0 < n_ev; e0 += 8) {
                     uint2 hd[8];     // headers (chunk maximum, chunk id) of 8 events fetched together: one L2 latency, not eight
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
@@ -1090,8 +1084,7 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
     // neighbouring tile's sectors, which another block wants at another time - under the evict-first policy they were gone
     // by then and came from DRAM twice (ncu: +3 GB of evict-first misses at BASELINE config 3)
     CUtensorMapL2promotion promo = box_frames * 4 >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    if (const char* env = getenv("VQB_TMA_PROMO")) {   // experiments: 0 none, 64, 128, 256
-        const int v = atoi(env);
+    if (const int v = env_get(ENV_TMA_PROMO, -1); v >= 0) {   // experiments: 0 none, 64, 128, 256
         promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
               : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     }
@@ -1117,9 +1110,9 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     const int num_kb = (D + BK - 1) / BK;
     // default: CTA pairs with cta_group::2 MMAs; VQB_TC_MODE=1: cta_group::1 with VQB_TC_CLUSTER-way codebook multicast
     p.two = true;
-    if (const char* env = getenv("VQB_TC_MODE")) p.two = env[0] != '1';
+    if (env_get(ENV_TC_MODE, 0) == 1) p.two = false;
     p.cs = 2;
-    if (const char* env = getenv("VQB_TC_CLUSTER")) p.cs = atoi(env);
+    p.cs = env_get(ENV_TC_CLUSTER, 2);
     if (p.cs != 1 && p.cs != 2 && p.cs != 4) p.cs = 2;
     if (p.two) p.cs = 2;
     if (num_m_tiles < 2 * p.cs) { p.cs = 1; p.two = false; }
@@ -1134,7 +1127,7 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     // K = 1024, D = 64 (where a codebook tile is only ~640 tensor-core cycles): 2, 4 and 8 slots give the same kernel time -
     // the operand loads are not what bounds small shapes.
     p.eh_slots = EH_SLOTS;
-    if (const char* env = getenv("VQB_TC_EHSLOTS")) { const int v = atoi(env); if (v >= 2 && v <= MAX_EH_SLOTS) p.eh_slots = v; }   // experiments
+    if (const int v = env_get(ENV_TC_EHSLOTS, 0); v >= 2 && v <= MAX_EH_SLOTS) p.eh_slots = v;   // experiments
     const size_t fixed_no_a = (size_t)p.eh_slots * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
                               (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
                               (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
@@ -1142,7 +1135,7 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     if (fuse && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
         // the full second tile must leave three codebook stages (it does for CTA pairs at D = 256: 3 x 16 KiB half-tile stages)
         bool full_second_tile = fixed_no_a + (size_t)2 * num_kb * A_CHUNK_BYTES + 3 * stage_bytes <= 227 * 1024;
-        if (const char* env = getenv("VQB_TC_ASLOTS")) full_second_tile = full_second_tile && atoi(env) >= 2 * num_kb;   // experiments
+        if (const int v = env_get(ENV_TC_ASLOTS, -1); v >= 0) full_second_tile = full_second_tile && v >= 2 * num_kb;   // experiments
         if (full_second_tile) p.a_slots = 2 * num_kb;   // pays with one codebook stage (3 instead of 4: measured equal)
     }
     const size_t fixed = (size_t)p.a_slots * A_CHUNK_BYTES + fixed_no_a;
@@ -1153,18 +1146,19 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
         p.ev_sm = (int)((227 * 1024 - fixed - 4 * stage_bytes) / ev_entry_bytes);
         if (p.ev_sm > 3) p.ev_sm = 3;
     }
-    if (const char* env = getenv("VQB_TC_EVSM")) { const int v = atoi(env); if (v >= 0 && v < p.ev_sm) p.ev_sm = v; }   // experiments
+    if (const int v = env_get(ENV_TC_EVSM, -1); v >= 0 && v < p.ev_sm) p.ev_sm = v;   // experiments
     const size_t fixed_ev = fixed + (size_t)p.ev_sm * ev_entry_bytes;
     p.b_stages = fixed_ev < 227 * 1024 ? (int)((227 * 1024 - fixed_ev) / stage_bytes) : 0;
     if (p.b_stages > (p.two ? 8 : 4)) p.b_stages = p.two ? 8 : 4;
-    if (const char* env = getenv("VQB_TC_STAGES")) { const int v = atoi(env); if (v >= 2 && v < p.b_stages) p.b_stages = v; }   // experiments
+    if (const int v = env_get(ENV_TC_STAGES, 0); v >= 2 && v < p.b_stages) p.b_stages = v;   // experiments
     p.ok = p.b_stages >= 2 && p.a_slots <= MAX_A_SLOTS;
     p.smem = fixed_ev + (size_t)p.b_stages * stage_bytes;
     return p;
 }
 
-bool tc_can_fuse(const float* z, int B, int D, int64_t W) {
-    if (const char* env = getenv("VQB_TC_FUSE")) if (env[0] == '0') return false;
+bool tc_can_fuse(const float* z, int B, int D, int64_t W, int prec) {
+    (void)prec;
+    if (env_get(ENV_TC_FUSE, 1) == 0) return false;
     // the staging ring of the fused preparation must leave room for the pipeline: it does not with an eight-chunk A tile
     // (D > 448) outside the CTA-pair mode (whole-tile codebook stages: fewer than four frame tiles, or VQB_TC_MODE=1)
     const int64_t tiles = (int64_t)B * ((W + tc::BM - 1) / tc::BM);
@@ -1182,11 +1176,14 @@ bool tc_fused_tail_fits(int B, int D, int64_t W) {   // does the kTail variant's
     return tc_plan(true, true, false, (int)(tiles < (1 << 30) ? tiles : (1 << 30)), D).ok;
 }
 bool tc_fused_tail_enabled() {
-    if (const char* env = getenv("VQB_TC_TAIL")) return env[0] == '1';
-    return false;
+    return env_get(ENV_TC_TAIL, 0) == 1;
 }
 
-size_t tc_event_scratch_bytes() { return (size_t)kTcMaxCtas * tc::EPI_THREADS * tc::EV_CAP * tc::EV_WORDS * 4; }
+size_t tc_event_scratch_bytes(int ctas) {
+    if (ctas < 2) ctas = 2;
+    if (ctas > kTcMaxCtas) ctas = kTcMaxCtas;
+    return (size_t)ctas * tc::EPI_THREADS * tc::EV_CAP * tc::EV_WORDS * 4;
+}
 
 // ---- optional CUDA-event timing of the stages of vqb_forward, on the launching stream (bench.py's roofline leg) -------
 struct TimingSlot { cudaEvent_t start, stop; int stage; };
@@ -1277,15 +1274,10 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     cudaError_t le;
     const TailArgs targs = with_tail ? *tail_args : TailArgs{};
     const int l2_once = (fuse && latents_read_once((size_t)N * D * 4)) ? 1 : 0;   // stream the latents past the L2-resident working set
-    int tail_dbg = 0;                              // experiments only: switch parts of the fused tail off (results are then wrong)
-    if (const char* env = getenv("VQB_TAIL_DBG")) tail_dbg = atoi(env);
-    // every bit except 8192 (polling hand-shake) produces WRONG results: they are honoured only together with an explicit opt-in,
-    // so that a stray environment variable can never corrupt a run
-    if (!getenv("VQB_TIMING_EXPERIMENTS")) tail_dbg &= 8192;
 #define VQB_TC_LAUNCH(TWO, FUSE, TAIL)                                                                                                       \
     le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
                             num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \
-                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, tail_dbg, ev_sm, l2_once, plan.eh_slots)
+                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, ev_sm, l2_once, plan.eh_slots)
     if (two && with_tail) VQB_TC_LAUNCH(true, true, true);
     else if (with_tail) VQB_TC_LAUNCH(false, true, true);
     else if (two && fuse) VQB_TC_LAUNCH(true, true, false);

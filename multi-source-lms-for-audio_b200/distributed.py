@@ -36,6 +36,48 @@ class TorchStatsComm:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
         return stats
 
+    def allreduce_async(self, stats: torch.Tensor):
+        """Global copy of `stats` (the local buffer is left untouched) + the event to wait for (None: already complete)."""
+        if stats.is_cuda:
+            return _side_stream_allreduce(self, stats)
+        out = stats.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out, None
+
+
+_side_streams: dict = {}
+
+
+def _side_stream_allreduce(comm, stats: torch.Tensor):
+    """All-reduce a COPY of `stats` on a per-device side stream: the caller's stream only pays for recording one event, the
+    exchange (and the wait for the slowest rank) overlaps whatever the caller enqueues next, and is joined by waiting on the
+    returned event.  comm.timings (if a list) receives a CUDA-event pair around the exchange."""
+    dev = stats.device
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
+    out = torch.empty_like(stats)
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    timed = getattr(comm, "timings", None)
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        t0 = t1 = None
+        if timed is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(side)
+        out.copy_(stats)
+        comm.allreduce(out)
+        if timed is not None:
+            t1.record(side)
+            timed.append((t0, t1))
+        done = torch.cuda.Event()
+        done.record(side)
+    stats.record_stream(side)
+    out.record_stream(side)
+    return out, done
+
 
 class StatsComm:
     """NCCL communicator held by libvqb_b200.so; all-reduces on the caller's current CUDA stream."""
@@ -55,6 +97,17 @@ class StatsComm:
         with torch.cuda.device(self.device):
             L.check("vqb_comm_init", L.lib().vqb_comm_init(ident, self.rank, self.world, C.byref(handle)))
         self._comm = handle
+
+    timings = None     # set to a list to collect (start, stop) CUDA-event pairs of the side-stream exchanges
+
+    def allreduce_async(self, stats: torch.Tensor):
+        """Global copy of `stats` on a side stream + the event to wait for (see _side_stream_allreduce)."""
+        return _side_stream_allreduce(self, stats)
+
+    @property
+    def handle(self):
+        """The raw communicator for C-ABI calls that take one (vqb_forward_host)."""
+        return self._comm
 
     def allreduce(self, stats: torch.Tensor) -> torch.Tensor:
         if not stats.is_cuda or stats.dtype != torch.float32 or not stats.is_contiguous():

@@ -4,6 +4,7 @@ Every function requires CUDA tensors and raises otherwise - the hot path has no 
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 from typing import Optional, Tuple
 
@@ -11,7 +12,10 @@ import torch
 
 from . import _lib as L
 
-_workspaces: dict = {}
+# (device, stream) -> scratch tensor, least recently used first.  Bounded: a process that cycles through many streams must not
+# pin the largest workspace it ever used on every one of them.
+_workspaces: "collections.OrderedDict" = collections.OrderedDict()
+_WORKSPACE_CACHE_ENTRIES = 4
 
 
 def _require_cuda(name: str, t: torch.Tensor, dtype) -> None:
@@ -35,18 +39,43 @@ def workspace_bytes(N: int, K: int, D: int, flags: int) -> int:
     return out.value
 
 
+def workspace_bytes_bw(B: int, D: int, W: int, K: int, flags: int) -> int:
+    """Exact scratch size for one [B, D, W] call (no bf16 latent copy when the tensor-core kernel reads the latents itself)."""
+    out = C.c_size_t(0)
+    L.check("vqb_workspace_bytes_bw", L.lib().vqb_workspace_bytes_bw(B, D, W, K, flags, C.byref(out)))
+    return out.value
+
+
 def _workspace(device, nbytes: int) -> torch.Tensor:
-    """Per (device, stream) scratch, grown on demand and reused (stream order makes reuse safe)."""
+    """Per (device, stream) scratch, grown on demand and reused (stream order makes reuse safe); at most
+    _WORKSPACE_CACHE_ENTRIES streams are remembered (least recently used dropped first), release_workspaces() drops all.
+
+    Inside CUDA-graph capture the scratch is a FRESH allocation that is not cached: it comes from the graph's private
+    memory pool and lives as long as the graph, so a later (larger) eager call can never free memory whose address is
+    baked into a captured graph."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
     key = (device.index, _stream_ptr(device))
-    ws = _workspaces.get(key)
+    ws = _workspaces.pop(key, None)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+    _workspaces[key] = ws                       # most recently used last
+    while len(_workspaces) > _WORKSPACE_CACHE_ENTRIES:
+        _workspaces.popitem(last=False)
     return ws
 
 
 def release_workspaces() -> None:
+    """Drop every cached scratch tensor (they are only a cache: the next call allocates again)."""
     _workspaces.clear()
+
+
+def _check_codes(idx: torch.Tensor, K: int) -> None:
+    """Caller-supplied indices (e.g. BERT-predicted tokens, bert.py:72-78): refuse codes outside [0, K) on the host - the
+    reference's scatter_ / one-hot matmul raise a device-side assert there.  One small reduction + sync; pass
+    validate=False on a hot path (the kernels are memory-safe either way: out-of-range codes give NaN / an all-zero row)."""
+    if idx.numel() and bool(((idx < 0) | (idx >= K)).any()):
+        raise IndexError(f"index out of range: codes must lie in [0, {K})")
 
 
 def vq_forward(z: torch.Tensor, codebook: torch.Tensor, *, precision: str = "bf16", want_q: bool = True,
@@ -68,8 +97,7 @@ def vq_forward(z: torch.Tensor, codebook: torch.Tensor, *, precision: str = "bf1
     N = B * W
     flags = L.PRECISIONS[precision] | (L.WANT_Q if want_q else 0) | (L.WANT_RESID if want_resid else 0)
     with torch.cuda.device(z.device):
-        nbytes = workspace_bytes(N, K, D, flags)
-        ws = workspace if workspace is not None else _workspace(z.device, nbytes)
+        ws = workspace if workspace is not None else _workspace(z.device, workspace_bytes_bw(B, D, W, K, flags))
         idx = torch.empty(N, dtype=torch.int64, device=z.device)
         q = torch.empty_like(z) if want_q else None
         if stats is None:
@@ -128,23 +156,27 @@ def ema_update(stats: torch.Tensor, codebook: torch.Tensor, cluster_size: torch.
                                                          K, D, float(decay), float(eps), _stream_ptr(codebook.device)))
 
 
-def onehot(idx: torch.Tensor, K: int) -> torch.Tensor:
+def onehot(idx: torch.Tensor, K: int, validate: bool = True) -> torch.Tensor:
     """Dense `encodings` [N, K] fp32 (vector_quantizer.py:38-39)."""
     _require_cuda("idx", idx, torch.int64)
     idx = idx.reshape(-1).contiguous()
+    if validate:
+        _check_codes(idx, K)
     out = torch.empty(idx.numel(), K, dtype=torch.float32, device=idx.device)
     with torch.cuda.device(idx.device):
         L.check("vqb_onehot", L.lib().vqb_onehot(idx.data_ptr(), idx.numel(), K, out.data_ptr(), _stream_ptr(idx.device)))
     return out
 
 
-def gather(codebook: torch.Tensor, idx: torch.Tensor, B: int, W: int) -> torch.Tensor:
+def gather(codebook: torch.Tensor, idx: torch.Tensor, B: int, W: int, validate: bool = True) -> torch.Tensor:
     """De-quantise: [B, D, W] with out[b, :, w] = codebook[idx[b*W + w]] (vector_quantizer.py:42, bert.py:75-78)."""
     _require_cuda("codebook", codebook, torch.float32)
     _require_cuda("idx", idx, torch.int64)
     codebook = codebook.contiguous()
     idx = idx.reshape(-1).contiguous()
     K, D = codebook.shape
+    if validate:
+        _check_codes(idx, K)
     if idx.numel() != B * W:
         raise ValueError(f"idx has {idx.numel()} entries, expected B*W = {B * W}")
     out = torch.empty(B, D, W, dtype=torch.float32, device=codebook.device)
@@ -171,9 +203,11 @@ def window_indices(idx: torch.Tensor, batch: int, window: int = 512, pad_id: int
 
 
 def vq_forward_host(z_host: torch.Tensor, codebook_host: torch.Tensor, *, precision: str = "bf16", want_resid: bool = False,
-                    chunk_batches: int = 0, idx_out: Optional[torch.Tensor] = None,
-                    stats_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Host-buffer path (vqb_forward_host): z/codebook in (ideally pinned) HOST memory -> idx, stats in host memory."""
+                    chunk_batches: int = 0, idx_out: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
+                    want_q: bool = False, q_out: Optional[torch.Tensor] = None, comm=None):
+    """Host-buffer path (vqb_forward_host): z/codebook in (ideally pinned) HOST memory -> idx, stats in host memory; with
+    want_q also the straight-through output [B, D, W] (returned as a third item).  `comm` (distributed.StatsComm): all-reduce
+    the statistics over the ranks before they are copied back.  Runs on the CURRENT CUDA device."""
     if z_host.is_cuda or codebook_host.is_cuda:
         raise RuntimeError("vq_forward_host takes host tensors; use vq_forward for device tensors")
     if not torch.cuda.is_available():
@@ -182,14 +216,18 @@ def vq_forward_host(z_host: torch.Tensor, codebook_host: torch.Tensor, *, precis
     codebook_host = codebook_host.contiguous()
     B, D, W = z_host.shape
     K = codebook_host.shape[0]
-    flags = L.PRECISIONS[precision] | (L.WANT_RESID if want_resid else 0)
+    flags = L.PRECISIONS[precision] | (L.WANT_RESID if want_resid else 0) | (L.WANT_Q if want_q else 0)
     if idx_out is None:
         idx_out = torch.empty(B * W, dtype=torch.int64).pin_memory()
     if stats_out is None:
         stats_out = torch.empty(L.stats_len(K, D), dtype=torch.float32).pin_memory()
+    if want_q and q_out is None:
+        q_out = torch.empty((B, D, W), dtype=torch.float32).pin_memory()
     L.check("vqb_forward_host", L.lib().vqb_forward_host(z_host.data_ptr(), codebook_host.data_ptr(), B, D, W, K, flags,
-                                                         idx_out.data_ptr(), stats_out.data_ptr(), chunk_batches))
-    return idx_out, stats_out
+                                                         idx_out.data_ptr(), q_out.data_ptr() if want_q else None,
+                                                         stats_out.data_ptr(), chunk_batches,
+                                                         comm.handle if comm is not None else None))
+    return (idx_out, stats_out, q_out) if want_q else (idx_out, stats_out)
 
 
 def debug_counters(device=None) -> dict:

@@ -19,16 +19,20 @@ class _VQFunction(torch.autograd.Function):
     """forward: vqb_forward [+ stats all-reduce] + vqb_finalize; backward: vqb_backward."""
 
     @staticmethod
-    def forward(ctx, inputs: torch.Tensor, weight: torch.Tensor, beta: float, precision: str, comm):
+    def forward(ctx, inputs: torch.Tensor, weight: torch.Tensor, beta: float, precision: str, comm, sync: str):
         z = inputs.contiguous()
         need_dw = ctx.needs_input_grad[1]
         idx, q, stats = F.vq_forward(z, weight.detach(), precision=precision, want_q=True, want_resid=need_dw)
-        if comm is not None:
+        pending = None
+        if comm is not None and sync == "forward":
             comm.allreduce(stats)             # the one exchange on the path (DDP's implicit all-reduce in the reference)
+        elif comm is not None and need_dw:    # "overlap": side stream, joined in backward (behind the decoder's fwd + bwd)
+            pending = comm.allreduce_async(stats)
         K, D = weight.shape
         losses = F.vq_finalize(stats, K, D, beta)
         emb, com, ppl = losses.unbind(0)
         ctx.beta = float(beta)
+        ctx.pending = pending
         ctx.save_for_backward(z, weight, idx, stats)
         ctx.mark_non_differentiable(ppl, idx)
         return emb, com, q, ppl, idx
@@ -37,8 +41,12 @@ class _VQFunction(torch.autograd.Function):
     def backward(ctx, g_emb, g_com, g_q, _g_ppl, _g_idx):
         z, weight, idx, stats = ctx.saved_tensors
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if ctx.pending is not None:           # global statistics from the side stream -> dE with the global N
+            stats, done = ctx.pending
+            if done is not None:
+                torch.cuda.current_stream(z.device).wait_event(done)
         dX, dE = F.vq_backward(z, weight.detach(), idx, stats, g_q, g_emb, g_com, ctx.beta, need_dx=need_dx, need_de=need_dw)
-        return dX, dE, None, None, None
+        return dX, dE, None, None, None, None
 
 
 class VectorQuantizer(nn.Module):
@@ -49,11 +57,24 @@ class VectorQuantizer(nn.Module):
                        "fp32": exact CUDA-core search.
       dense_encodings  "auto" (dense one-hot when N*K*4 bytes <= dense_limit_bytes, else a sparse COO tensor of the same
                        shape), True (always dense, like the reference) or False (always sparse).
-      stats_comm       object with .allreduce(stats) (see distributed.StatsComm) for batch-sharded multi-GPU training.
+      stats_comm       object with .allreduce(stats) / .allreduce_async(stats) (see distributed.StatsComm) for batch-sharded
+                       multi-GPU training: the latents shard by batch, the codebook is replicated.
+      stats_sync       "forward" (default): the statistics are all-reduced inside forward; losses, perplexity and the codebook
+                       gradient are GLOBAL (identical on every rank, equal to a single process on the concatenated batch).
+                       "overlap": forward returns this rank's LOCAL losses / perplexity (what the reference logs under DDP:
+                       no sync_dist, vqvae.py:68-69) and starts the all-reduce on a side stream; backward joins it, so the
+                       exchange hides behind the decoder's forward + backward.  The codebook gradient is the same global one.
+
+    Gradient contract under stats_comm (matches Lightning DDP around the reference, configs/trainer/default.yaml:9-10):
+    `codebook.weight.grad` is already the global mean gradient on every rank - do NOT let a DDP wrapper average it again with
+    something else (averaging identical tensors is harmless).  `inputs.grad` is normalised by this rank's OWN frame count, like
+    the reference's per-rank loss: the encoder gradients it produces are expected to be averaged over ranks by the DDP wrapper
+    of the encoder.  With unequal shards the two conventions differ by N_local * world / N_global per rank, exactly as they do
+    for the reference under DDP.
     """
 
     def __init__(self, num_embedding: int, embedding_dim: int, commitment_cost: float, *, precision: str = "bf16",
-                 dense_encodings="auto", dense_limit_bytes: int = 256 << 20, stats_comm=None):
+                 dense_encodings="auto", dense_limit_bytes: int = 256 << 20, stats_comm=None, stats_sync: str = "forward"):
         super().__init__()
         self.embedding_dim = embedding_dim
         self.num_embedding = num_embedding
@@ -65,6 +86,9 @@ class VectorQuantizer(nn.Module):
         self.dense_encodings = dense_encodings
         self.dense_limit_bytes = dense_limit_bytes
         self.stats_comm = stats_comm
+        if stats_sync not in ("forward", "overlap"):
+            raise ValueError(f"stats_sync must be 'forward' or 'overlap', got {stats_sync!r}")
+        self.stats_sync = stats_sync
 
     def _encodings(self, idx: torch.Tensor) -> torch.Tensor:
         N, K = idx.numel(), self.num_embedding
@@ -82,7 +106,7 @@ class VectorQuantizer(nn.Module):
         if inputs.dim() != 3 or inputs.shape[1] != self.embedding_dim:
             raise ValueError(f"expected inputs [B, {self.embedding_dim}, W], got {tuple(inputs.shape)}")
         emb, com, quantized, ppl, idx = _VQFunction.apply(inputs, self.codebook.weight, float(self.commitment_cost),
-                                                          self.precision, self.stats_comm)
+                                                          self.precision, self.stats_comm, self.stats_sync)
         encodings = self._encodings(idx)
         return emb, com, quantized, ppl, encodings, idx.unsqueeze(1)
 
@@ -96,4 +120,4 @@ class VectorQuantizer(nn.Module):
     def decode(self, idx: torch.Tensor, batch: int) -> torch.Tensor:
         """Indices -> codewords in BCW (the one-hot matmul of vector_quantizer.py:42 / bert.py:75-78 as a gather)."""
         idx = idx.reshape(-1)
-        return F.gather(self.codebook.weight, idx, batch, idx.numel() // batch)
+        return F.gather(self.codebook.weight, idx, batch, idx.numel() // batch)   # raises IndexError on codes outside [0, K)

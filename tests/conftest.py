@@ -43,3 +43,25 @@ def golden(request):
     g = load_golden(request.param)
     g["name"] = request.param
     return g
+
+
+@pytest.fixture
+def experiment_env():
+    """Set VQB_* experiment switches for one test: they are honoured only with VQB_EXPERIMENTS=1 and are read once, so the
+    library is told to re-read them after every change (vqb_debug_reload_env) and again when the test is over."""
+    from vq_b200 import _lib
+    saved = {}
+
+    def set_env(**kv):
+        for k, v in {"VQB_EXPERIMENTS": "1", **kv}.items():
+            saved.setdefault(k, os.environ.get(k))
+            os.environ[k] = str(v)
+        _lib.lib().vqb_debug_reload_env()
+
+    yield set_env
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    _lib.lib().vqb_debug_reload_env()

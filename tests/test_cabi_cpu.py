@@ -22,14 +22,14 @@ def test_library_exports_every_declared_symbol():
     names = declared_symbols()
     assert len(names) >= 17
     assert sorted(_lib.EXPORTS) == names, "ctypes table and include/vqb.h disagree"
-    handle = C.CDLL(_lib.LIB_PATH)
+    handle = _lib.lib()
     for n in names:
         assert hasattr(handle, n), f"{n} declared in vqb.h but not exported by libvqb_b200.so"
 
 
 def test_version_and_workspace_sizing():
     lib = _lib.lib()
-    assert lib.vqb_version() == 100
+    assert lib.vqb_version() == 200
     small = F.workspace_bytes(1000, 512, 64, _lib.PREC_FP32)
     big = F.workspace_bytes(1 << 20, 1024, 64, _lib.PREC_BF16)
     assert 0 < small < big
@@ -75,3 +75,35 @@ def test_module_interface_matches_reference():
     assert isinstance(vq.codebook, torch.nn.Embedding) and list(vq.state_dict()) == ["codebook.weight"]
     w = vq.codebook.weight
     assert w.shape == (128, 32) and w.requires_grad and float(w.abs().max()) <= 1 / 128
+
+
+def test_experiment_switches_need_the_opt_in(monkeypatch):
+    """A stray VQB_* variable must not change production behaviour: without VQB_EXPERIMENTS=1 the switches are ignored
+    (here: VQB_TAIL_TMA=0 would select the register-staged tail, which needs no TMA-fed launch... observable through the
+    workspace plan of VQB_TC_FUSE=0, which reserves the bf16 latent copy)."""
+    flags = _lib.PREC_BF16
+    base = F.workspace_bytes_bw(4, 64, 4096, 512, flags)
+    monkeypatch.setenv("VQB_TC_FUSE", "0")
+    _lib.lib().vqb_debug_reload_env()
+    assert F.workspace_bytes_bw(4, 64, 4096, 512, flags) == base, "switch honoured without VQB_EXPERIMENTS=1"
+    monkeypatch.setenv("VQB_EXPERIMENTS", "1")
+    _lib.lib().vqb_debug_reload_env()
+    assert F.workspace_bytes_bw(4, 64, 4096, 512, flags) == base + 4 * 4096 * 64 * 2
+    monkeypatch.delenv("VQB_EXPERIMENTS")
+    monkeypatch.delenv("VQB_TC_FUSE")
+    _lib.lib().vqb_debug_reload_env()
+    assert F.workspace_bytes_bw(4, 64, 4096, 512, flags) == base
+
+
+def test_exact_workspace_drops_the_bf16_latent_copy():
+    """the exact per-shape size omits the bf16 latent copy when the tensor-core kernel reads the fp32 latents
+    itself (8.6 GB at BASELINE config 3) and sizes the event scratch by the grid; the N-only query stays an upper bound."""
+    flags = _lib.PREC_BF16 | _lib.WANT_Q | _lib.WANT_RESID
+    N, K, D = 1 << 24, 8192, 256
+    exact = F.workspace_bytes_bw(1024, D, 16384, K, flags)
+    upper = F.workspace_bytes(N, K, D, flags)
+    assert upper - exact >= N * D * 2 and exact < 1.2e9, (exact, upper)
+    ragged = F.workspace_bytes_bw(4, 64, 333, 512, _lib.PREC_BF16)           # W % 4 != 0: unfused, keeps the copy
+    assert ragged <= F.workspace_bytes(4 * 333, 512, 64, _lib.PREC_BF16)
+    tiny = F.workspace_bytes_bw(1, 64, 256, 512, _lib.PREC_BF16)             # two frame tiles: event scratch for two CTAs only
+    assert tiny < (4 << 20), tiny

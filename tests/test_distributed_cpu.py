@@ -37,14 +37,18 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        B, D, W, K, beta = 6, 32, 101, 64, 0.25
+        B, D, W, K, beta = 7, 32, 101, 64, 0.25              # 7 items over 2 ranks: UNEVEN shards (4 + 3)
         rng = np.random.default_rng(7)                       # same data on every rank; each takes its shard
         z = rng.standard_normal((B, D, W), dtype=np.float32)
         cb = rng.standard_normal((K, D), dtype=np.float32)
         lo, hi = shard_bounds(B, world, rank)
         fwd = O.vq_forward(z[lo:hi], cb, beta)
         stats = torch.from_numpy(O.shard_stats(z[lo:hi], cb, fwd.indices).astype(np.float32))
-        TorchStatsComm().allreduce(stats)                    # the one exchange on the path
+        local = stats.clone()
+        glob, done = TorchStatsComm().allreduce_async(stats)  # "overlap" mode: a global copy, the local buffer is untouched
+        assert done is None and torch.equal(stats, local)
+        TorchStatsComm().allreduce(stats)                    # the one exchange on the path, in place
+        assert torch.equal(stats, glob)
         mse, com, ppl, dE = O.finalize_from_stats(stats.numpy().astype(np.float64), K, D, beta)
         # single-process reference on the concatenated batch
         full = O.vq_forward(z, cb, beta)

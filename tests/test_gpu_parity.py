@@ -150,10 +150,10 @@ def test_oracle_parity(B, D, W, K, cb_scale, z_scale, precision):
 
 @pytest.mark.parametrize("B,D,W,K,cb_scale", [(2, 64, 11000, 512, None), (1, 256, 3000, 8192, 1.0), (3, 128, 1280, 700, 1.0),
                                               (2, 16, 1100, 40, 1.0)])
-def test_fused_tail_variant_matches_oracle(B, D, W, K, cb_scale, monkeypatch):
+def test_fused_tail_variant_matches_oracle(B, D, W, K, cb_scale, experiment_env):
     """VQB_TC_TAIL=1: the search kernel finishes the frames itself (rescoring, gather, straight-through value, statistics)
     and only the exact-search fallback frames go through the list kernel.  Same parity bar as the default path."""
-    monkeypatch.setenv("VQB_TC_TAIL", "1")
+    experiment_env(VQB_TC_TAIL="1")
     z = seeded(300 + D + K, (B, D, W))
     cb = (np.random.default_rng(5).uniform(-1 / K, 1 / K, (K, D)).astype(np.float32) if cb_scale is None
           else seeded(400 + D + K, (K, D), cb_scale))
@@ -174,11 +174,11 @@ def test_fused_tail_variant_matches_oracle(B, D, W, K, cb_scale, monkeypatch):
 
 @pytest.mark.parametrize("env", [{"VQB_TAIL_TMA": "0"}, {"VQB_TAIL_VARIANT": "0"}, {"VQB_RESID_REPLICAS": "1"},
                                  {"VQB_RESID_REPLICAS": "8"}, {"VQB_DX_TILES": "1"}, {"VQB_TC_ASLOTS": "6"},
-                                 {"VQB_L2_ONCE": "1"}, {"VQB_TC_EHSLOTS": "5"}, {"VQB_TAIL_DBG": "8192"}])
-def test_kernel_variants_agree_with_the_default_path(env, monkeypatch):
+                                 {"VQB_L2_ONCE": "1"}, {"VQB_TC_EHSLOTS": "5"}, {"VQB_TC_MODE": "1"}])
+def test_kernel_variants_agree_with_the_default_path(env, experiment_env):
     """The experiment switches select other forms of the same kernels (register-staged tail, 8-warp TMA tail, one / eight
     residual-sum replicas, tile-staged backward, two spare A chunks, evict-first latent loads, a deeper bias-operand ring,
-    polling accumulator hand-shake): indices and `quantized` must be identical, statistics and
+    cta_group::1 MMAs): indices and `quantized` must be identical, statistics and
     gradients equal up to the summation order of the atomics.  A hot code (a quarter of the frames) stresses the replicas."""
     B, D, W, K, beta = 3, 256, 1536, 700, 0.25
     cb = seeded(11, (K, D))
@@ -192,8 +192,7 @@ def test_kernel_variants_agree_with_the_default_path(env, monkeypatch):
         return (idx.reshape(-1).cpu().numpy(), q.detach().cpu().numpy(), emb.item(), ppl.item(), zt.grad.cpu().numpy(),
                 vq.codebook.weight.grad.cpu().numpy())
     ref = run()
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+    experiment_env(**env)
     got = run()
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
     assert (got[0] == 5).mean() > 0.2
@@ -328,13 +327,48 @@ def test_onehot_gather_window_match_oracle():
     assert np.array_equal(tok.cpu().numpy(), wt) and np.array_equal(mask.cpu().numpy(), wm)
 
 
-def test_host_buffer_path_matches_device_path():
+def test_out_of_range_indices_are_refused_and_never_dereferenced():
+    """caller-supplied indices (BERT-predicted tokens) outside [0, K).  The wrappers raise IndexError (the
+    reference's scatter_ / one-hot matmul raise a device assert); with validate=False the kernels stay memory-safe: the
+    one-hot row is all-zero, the gathered codeword and the gradient of that frame are NaN, every other frame is untouched."""
+    K, D, B, Lq = 50, 32, 2, 40
+    cb = torch.from_numpy(seeded(6, (K, D))).to(DEV)
+    idx = torch.from_numpy(np.random.default_rng(7).integers(0, K, B * Lq)).to(DEV)
+    bad = idx.clone()
+    bad[3], bad[57] = K, -1
+    for fn in (lambda: F.onehot(bad, K), lambda: F.gather(cb, bad, B, Lq),
+               lambda: vq_b200.VectorQuantizer(K, D, 0.25).to(DEV).decode(bad, B)):
+        with pytest.raises(IndexError):
+            fn()
+    enc = F.onehot(bad, K, validate=False)
+    assert float(enc[3].sum()) == 0 and float(enc[57].sum()) == 0 and float(enc.sum()) == B * Lq - 2
+    deq = F.gather(cb, bad, B, Lq, validate=False)
+    good = F.gather(cb, idx, B, Lq)
+    rows, rows_good = deq.permute(0, 2, 1).reshape(-1, D), good.permute(0, 2, 1).reshape(-1, D)
+    assert torch.isnan(rows[3]).all() and torch.isnan(rows[57]).all()
+    keep = torch.ones(B * Lq, dtype=torch.bool, device=DEV); keep[3] = keep[57] = False
+    assert torch.equal(rows[keep], rows_good[keep])
+    z = torch.from_numpy(seeded(8, (B, D, Lq))).to(DEV)
+    stats = torch.zeros(_lib.stats_len(K, D), device=DEV); stats[-1] = B * Lq
+    one = torch.ones((), device=DEV)
+    for W_ in (Lq,):
+        dX, _ = F.vq_backward(z, cb, bad, stats, None, one, one, 0.25)
+        dXg, _ = F.vq_backward(z, cb, idx, stats, None, one, one, 0.25)
+        r, rg = dX.permute(0, 2, 1).reshape(-1, D), dXg.permute(0, 2, 1).reshape(-1, D)
+        assert torch.isnan(r[3]).all() and torch.isnan(r[57]).all() and torch.equal(r[keep], rg[keep])
+
+
+@pytest.mark.parametrize("want_q", [False, True])
+def test_host_buffer_path_matches_device_path(want_q):
     B, D, W, K = 6, 64, 1500, 512
     z = torch.from_numpy(seeded(8, (B, D, W))).pin_memory()
     cb = torch.from_numpy(seeded(9, (K, D))).pin_memory()
-    idx_d, _, stats_d = F.vq_forward(z.to(DEV), cb.to(DEV), precision="bf16", want_q=False, want_resid=True)
-    idx_h, stats_h = F.vq_forward_host(z, cb, precision="bf16", want_resid=True, chunk_batches=4)   # 2 chunks: 4 + 2
+    idx_d, q_d, stats_d = F.vq_forward(z.to(DEV), cb.to(DEV), precision="bf16", want_q=want_q, want_resid=True)
+    out = F.vq_forward_host(z, cb, precision="bf16", want_resid=True, chunk_batches=4, want_q=want_q)   # 2 chunks: 4 + 2
+    idx_h, stats_h = out[0], out[1]
     assert torch.equal(idx_h, idx_d.cpu())
+    if want_q:
+        assert torch.equal(out[2], q_d.cpu()), "straight-through output of the host-buffer path"
     sd, sh = stats_d.cpu().numpy(), stats_h.numpy()
     assert np.array_equal(sd[:K], sh[:K])
     np.testing.assert_allclose(sh[K:], sd[K:], rtol=1e-4, atol=1e-3)
