@@ -95,6 +95,35 @@ def run_case(VQ, name: str, z: np.ndarray, codebook: np.ndarray | None, K: int, 
           f"-> {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def run_large_case(VQ, name: str, z: np.ndarray, K: int, D: int, beta: float):
+    """cfg-1-sized, tie-heavy fixture (VERDICT r01 'Next' #4): default-init codebook U(-1/K, 1/K), N = 176 000 frames.
+    Only what pins the index stream is stored: indices (int16), the reference's own fp32 top-2 margins, losses, perplexity, the
+    codebook (torch RNG, so it cannot be regenerated from numpy) and its gradient; the latents come back from the numpy seed
+    (sha256 guards generator drift)."""
+    torch.manual_seed(1234)
+    vq = VQ(num_embedding=K, embedding_dim=D, commitment_cost=beta)
+    cb0 = vq.codebook.weight.detach().clone()
+    zt = torch.from_numpy(z).clone().requires_grad_(True)
+    emb, com, q, ppl, enc, idx = vq(zt)
+    (emb + com).backward()
+    margin, dmin = reference_margins(torch.from_numpy(z), cb0)
+    x = torch.einsum("bcw -> bwc", torch.from_numpy(z)).contiguous().view(-1, D)
+    d64 = (x.double() ** 2).sum(1, keepdim=True) + ((cb0.double() ** 2).sum(1) - 2 * x.double() @ cb0.double().t())
+    idx64 = torch.argmin(d64, dim=1)
+    out = dict(beta=np.float32(beta), K=np.int64(K), D=np.int64(D), shape=np.array(z.shape, dtype=np.int64),
+               embedding_loss=emb.detach().numpy(), commitment_loss=com.detach().numpy(), perplexity=ppl.detach().numpy(),
+               indices=idx.detach().numpy().reshape(-1).astype(np.int16), margin=margin.astype(np.float32),
+               codebook=cb0.numpy(), dE=vq.codebook.weight.grad.detach().numpy(), z_sha=np.array(_sha(z)),
+               quantized_sha=np.array(_sha(q.detach().numpy())), dX_sha=np.array(_sha(zt.grad.detach().numpy())),
+               exact_ties=np.int64(int((margin == 0).sum())), fp32_ne_fp64=np.int64(int((idx64 != idx.reshape(-1)).sum())),
+               torch_version=np.array(torch.__version__))
+    os.makedirs(os.path.join(OUT, "large"), exist_ok=True)     # its own directory: a different schema than the small fixtures
+    path = os.path.join(OUT, "large", name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: N={enc.shape[0]} K={K} D={D} emb={float(emb.detach()):.6g} ppl={float(ppl.detach()):.5g} "
+          f"exact_ties={int(out['exact_ties'])} fp32!=fp64={int(out['fp32_ne_fp64'])} -> {os.path.getsize(path)/1024:.0f} KiB")
+
+
 def _sha(a: np.ndarray) -> str:
     import hashlib
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
@@ -175,6 +204,17 @@ def vqvae_case():
           f"-> {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def large_cases():
+    VQ = load_reference()
+    torch.set_num_threads(8)
+    # BASELINE config 1 at full clip length x 16 clips: N = 176 000, tie-heavy default-init codebook
+    run_large_case(VQ, "large_default_init_k512_d64_n176000", seeded(21, (16, 64, 11000)), 512, 64, 0.25)
+
+
 if __name__ == "__main__":
-    main()
-    vqvae_case()
+    if "--large-only" in sys.argv:
+        large_cases()
+    else:
+        main()
+        vqvae_case()
+        large_cases()

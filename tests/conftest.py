@@ -65,3 +65,13 @@ def experiment_env():
         else:
             os.environ[k] = v
     _lib.lib().vqb_debug_reload_env()
+
+
+def load_large_golden(name="large_default_init_k512_d64_n176000"):
+    """The N = 176 000 tie-heavy fixture (oracle/make_golden.py::run_large_case): latents regenerated from the numpy seed."""
+    import hashlib
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "large", name + ".npz"), allow_pickle=False))
+    z = _seeded(21, tuple(int(v) for v in g["shape"]))
+    assert hashlib.sha256(np.ascontiguousarray(z).tobytes()).hexdigest() == str(g["z_sha"]), "numpy generator drift"
+    g["z"] = z
+    return g

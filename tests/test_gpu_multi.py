@@ -40,3 +40,38 @@ def test_one_process_two_devices_agree():
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
         assert abs(o[2] - outs[0][2]) <= 1e-6 * abs(outs[0][2]) and torch.allclose(o[3], outs[0][3], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_host_buffer_path_on_a_second_device():
+    """ADVICE r01 / VERDICT #4: the host-buffer path keeps its streams and scratch PER DEVICE - cuda:0, then cuda:1, then
+    cuda:0 again in one process, and both devices from two threads at once."""
+    import threading
+    import numpy as np
+    from vq_b200 import _lib, functional as F
+    g = torch.Generator().manual_seed(9)
+    z = torch.randn(5, 64, 2048, generator=g).pin_memory()
+    cb = torch.randn(512, 64, generator=g).pin_memory()
+    ref = None
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            idx, stats, q = F.vq_forward_host(z, cb, want_resid=True, want_q=True, chunk_batches=2)
+            idx_d, q_d, _ = F.vq_forward(z.to(f"cuda:{dev}"), cb.to(f"cuda:{dev}"), want_q=True)
+            assert torch.equal(idx, idx_d.cpu()) and torch.equal(q, q_d.cpu())
+        ref = idx.clone() if ref is None else ref
+        assert torch.equal(idx, ref)
+    out = {}
+
+    def work(dev):
+        with torch.cuda.device(dev):
+            for _ in range(3):
+                out[dev] = F.vq_forward_host(z, cb, want_resid=True, chunk_batches=1)[0].clone()
+    threads = [threading.Thread(target=work, args=(d,)) for d in (0, 1, 0)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert torch.equal(out[0], ref) and torch.equal(out[1], ref)
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            _lib.check("vqb_host_release", _lib.lib().vqb_host_release())
