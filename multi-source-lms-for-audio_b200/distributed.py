@@ -57,7 +57,7 @@ def _side_stream_allreduce(comm, stats: torch.Tensor):
     if side is None:
         side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
     cur = torch.cuda.current_stream(dev)
-    out = torch.empty_like(stats)
+    out = stats.clone()                       # on the caller's stream (a few microseconds): `stats` may be reused right away
     ready = torch.cuda.Event()
     ready.record(cur)
     timed = getattr(comm, "timings", None)
@@ -67,16 +67,23 @@ def _side_stream_allreduce(comm, stats: torch.Tensor):
         if timed is not None:
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record(side)
-        out.copy_(stats)
         comm.allreduce(out)
         if timed is not None:
             t1.record(side)
             timed.append((t0, t1))
         done = torch.cuda.Event()
         done.record(side)
-    stats.record_stream(side)
     out.record_stream(side)
     return out, done
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    """The per-device side stream the overlapped exchanges run on (created on first use)."""
+    dev = torch.device(device)
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return side
 
 
 class StatsComm:
