@@ -53,20 +53,22 @@ def main():
             xs = z[lo:hi].clone().requires_grad_(True)
             e, c, qs, p, _, ix = vq(xs)
             (e + c + (qs * Gq[lo:hi]).sum()).backward()
-            good = torch.equal(ix.reshape(-1), idx.reshape(-1)[lo * W:hi * W]) and torch.equal(qs, q[lo:hi])
+            checks = {"idx": torch.equal(ix.reshape(-1), idx.reshape(-1)[lo * W:hi * W]), "q": torch.equal(qs, q[lo:hi])}
             dE_ref = ref.codebook.weight.grad
-            good &= torch.allclose(vq.codebook.weight.grad, dE_ref, rtol=1e-4, atol=1e-6 * float(dE_ref.abs().max()))
-            good &= torch.allclose(xs.grad.double(), dx_ref, rtol=1e-5, atol=2e-7 * float(dx_ref.abs().max()))
+            checks["dE"] = torch.allclose(vq.codebook.weight.grad, dE_ref, rtol=1e-4, atol=1e-6 * float(dE_ref.abs().max()))
+            checks["dX"] = torch.allclose(xs.grad.double(), dx_ref, rtol=1e-5, atol=2e-7 * float(dx_ref.abs().max()))
             if sync == "forward":                               # global losses: identical to the single-process run
-                good &= close(e.item(), emb.item(), 1e-5) and close(c.item(), com.item(), 1e-5) and close(p.item(), ppl.item(), 1e-5)
+                checks["losses"] = (close(e.item(), emb.item(), 1e-5) and close(c.item(), com.item(), 1e-5)
+                                    and close(p.item(), ppl.item(), 1e-5))
             else:                                               # local losses: this shard alone (reference under DDP)
                 loc = vq_b200.VectorQuantizer(K, D, beta).to(dev)
                 with torch.no_grad():
                     loc.codebook.weight.copy_(cb)
                 el, cl, _, pl, _, _ = loc(z[lo:hi])
-                good &= close(e.item(), el.item(), 1e-6) and close(p.item(), pl.item(), 1e-6)
+                checks["local_losses"] = close(e.item(), el.item(), 1e-6) and close(p.item(), pl.item(), 1e-6)
+            good = all(checks.values())
             if not good:
-                print(f"rank {rank}: MISMATCH in {name} at B={B}", flush=True)
+                print(f"rank {rank}: MISMATCH in {name} at B={B}: failed {[k for k, v in checks.items() if not v]}", flush=True)
             ok &= bool(good)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
