@@ -78,6 +78,17 @@ __device__ __forceinline__ float ref_distance(float x2, float e2, float dot) {
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void st_stream(float* p, float v) {   // written once, not read again by this kernel: keep it out of L1
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// Residual-sum replicas (see launch_tail): the blocks of different SMs add into one of n_rep copies, chosen by SM id
+__device__ __forceinline__ float* pick_resid_replica(float* resid, float* resid_rep, int n_rep, size_t rep_stride) {
+    if (!resid || n_rep <= 1) return resid;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned int r = smid % (unsigned int)n_rep;
+    return r ? resid_rep + (size_t)(r - 1) * rep_stride : resid;
+}
 #endif
 
 // What the tensor-core search needs to finish frames itself (fused tail, see vqb_tc.cu): everything the stand-alone
@@ -105,6 +116,12 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                         int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s);
+// second form of the tail (vqb_tail2.cu): D = 32 J compile-time, dealt rescoring, 16-frame tiles for large D, run-length atomics
+bool tail2_supports(int D);
+cudaError_t launch_tail2(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K, const int* idx32,
+                         const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out, int* counts, float* resid,
+                         double* part, int n_partials, WsMeta* meta, float* resid_rep, int n_rep, size_t rep_stride, int form,
+                         cudaStream_t s);
 int resid_replicas(int K, int D);   // copies of the residual sums the tail kernels spread their atomics over (workspace holds kResidReplicasMax - 1)
 // fused-tail mode: finishes the (rare) frames the exact fallback search decided - one warp per frame of the list
 cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, int D, int64_t W, int K, const int* rows,

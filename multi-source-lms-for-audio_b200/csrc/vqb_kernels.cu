@@ -21,9 +21,6 @@ __device__ __forceinline__ float ld_stream(const float* p) {   // read-once data
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void st_stream(float* p, float v) {
-    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -521,13 +518,6 @@ cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, i
 // per address, so the most popular code bounds the whole pass (measured: 8 of 20 ms at BASELINE config 3 with a code that
 // takes ~1.5 % of the frames).  The blocks of different SMs therefore add into one of n_rep copies (copy 0 is the caller's
 // buffer, the others live in the workspace) and fold_resid_kernel sums the copies afterwards.
-__device__ __forceinline__ float* pick_resid_replica(float* resid, float* resid_rep, int n_rep, size_t rep_stride) {
-    if (!resid || n_rep <= 1) return resid;
-    unsigned int smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    const unsigned int r = smid % (unsigned int)n_rep;
-    return r ? resid_rep + (size_t)(r - 1) * rep_stride : resid;
-}
 __global__ void __launch_bounds__(256) fold_resid_kernel(float* __restrict__ resid, const float* __restrict__ resid_rep, int n_rep,
                                                          size_t rep_stride) {
     // the caller's buffer (stats + K) is only 4-byte aligned when K % 4 != 0: plain scalar accesses, the arrays are small
@@ -1033,6 +1023,13 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
         note_launch();
         return cudaGetLastError();
     };
+    const int form = env_get(ENV_TAIL_FORM, 2);     // 2 (default): tail2_kernel where it applies; 0: round-1 kernels; 216 / 232: tile size
+    if (form != 0 && tail_tma_enabled() && tail2_supports(D) && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+        e = launch_tail2(z, codebook, e2, B, D, W, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta,
+                         resid_rep, n_rep, rep_stride, form, s);
+        note_launch();
+        return e != cudaSuccess ? e : fold();
+    }
     if (tail_tma_enabled() && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
         // TMA-fed tail: tiles of 32 frames that never straddle a batch item
         const int box_dims = D <= 256 ? D : D / 2;

@@ -1083,7 +1083,8 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
     // L2 promotion no wider than a box row: with 128-byte rows (the tail's 32-frame boxes) a 256-byte promotion also fetches the
     // neighbouring tile's sectors, which another block wants at another time - under the evict-first policy they were gone
     // by then and came from DRAM twice (ncu: +3 GB of evict-first misses at BASELINE config 3)
-    CUtensorMapL2promotion promo = box_frames * 4 >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    CUtensorMapL2promotion promo = box_frames * 4 >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                 : box_frames * 4 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
     if (const int v = env_get(ENV_TMA_PROMO, -1); v >= 0) {   // experiments: 0 none, 64, 128, 256
         promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
               : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
