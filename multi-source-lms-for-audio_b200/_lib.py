@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libvqb_b200.so")
 PREC_FP32, PREC_BF16, PREC_TF32 = 0x00, 0x01, 0x02
 WANT_Q, WANT_RESID = 0x10, 0x20
 UNIQUE_ID_BYTES = 128
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32}
 
 _c_f32p = C.c_void_p
 _SIGNATURES = {

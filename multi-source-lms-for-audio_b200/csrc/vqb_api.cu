@@ -130,7 +130,8 @@ WsLayout ws_layout_for(const float* z, int B, int D, int64_t W, int K, int flags
     const int prec = flags & VQB_PREC_MASK;
     const int64_t N = (int64_t)B * W;
     if (prec == VQB_PREC_FP32) return ws_layout(N, K, D, flags, false, 0);
-    const bool fuse = tc_can_fuse(z, B, D, W, prec);
+    bool fuse = tc_can_fuse(z, B, D, W, prec);
+    if (prec == VQB_PREC_TF32 && !fuse) fuse = tc_can_fuse(z, B, D, W, VQB_PREC_BF16);   // falls back to the bf16 shortlist
     const int64_t tiles = fuse ? (int64_t)B * ((W + kTileRows - 1) / kTileRows) : (N + kTileRows - 1) / kTileRows;
     return ws_layout(N, K, D, flags, !fuse, (int)(tiles < kTcMaxCtas ? tiles : kTcMaxCtas));
 }
@@ -146,11 +147,15 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         return VQB_E_NULL;
     }
     if ((rc = check_shape(B, D, W, K)) != 0) return rc;
-    const int prec = flags & VQB_PREC_MASK;
+    int prec = flags & VQB_PREC_MASK;
     if (prec != VQB_PREC_FP32 && prec != VQB_PREC_BF16 && prec != VQB_PREC_TF32) {
         set_error("vqb_forward: unknown precision %d (VQB_PREC_FP32, VQB_PREC_BF16 or VQB_PREC_TF32)", prec);
         return VQB_E_FLAGS;
     }
+    // tf32 reads the fp32 latents in place; shapes the tensor-core kernel cannot read that way (W % 4 != 0, short clips, D > 256)
+    // take the bf16 shortlist instead - the fp32 rescoring makes the result the same either way
+    if (prec == VQB_PREC_TF32 && !tc_can_fuse(z, B, D, W, VQB_PREC_TF32)) prec = VQB_PREC_BF16;
+    flags = (flags & ~VQB_PREC_MASK) | prec;
     if ((flags & VQB_WANT_Q) && !q_out) {
         set_error("vqb_forward: VQB_WANT_Q set but q_bcw_out is NULL");
         return VQB_E_NULL;
@@ -202,11 +207,12 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         __nv_bfloat16* eb = reinterpret_cast<__nv_bfloat16*>(ws + L.eb);
         __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + L.xb);
         __nv_bfloat16* eh = reinterpret_cast<__nv_bfloat16*>(ws + L.eh);
-        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, eb, eh, meta, s), "codebook_prep");
-        const bool fuse = tc_can_fuse(z, B, D, W);
+        const bool tf32 = prec == VQB_PREC_TF32;
+        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, tf32 ? nullptr : eb, eh, meta, s, tf32), "codebook_prep");
+        const bool fuse = tc_can_fuse(z, B, D, W, prec);
         // fused tail: the search kernel finishes the frames itself (index, quantized, statistics); only the frames it
         // sends to the exact search are finished by a small list kernel.  Otherwise the stand-alone tail kernel runs.
-        const bool fused_tail = fuse && !scores_dbg && tc_fused_tail_enabled() && (reinterpret_cast<uintptr_t>(codebook) & 31) == 0 &&
+        const bool fused_tail = fuse && !tf32 && !scores_dbg && tc_fused_tail_enabled() && (reinterpret_cast<uintptr_t>(codebook) & 31) == 0 &&
                                 tc_fused_tail_fits(B, D, W);
         double* part_d = reinterpret_cast<double*>(part);
         TailArgs targs{z, codebook, e2, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr, counts, resid, part_d};
@@ -214,7 +220,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         if (fused_tail) VQB_CUDA(cudaMemsetAsync(part, 0, (size_t)L.n_partials * sizeof(double), s), "memset sse partials");
         stage_timing_end(tprep, s);
         rc = launch_tc_search(fuse ? z : nullptr, B, W, xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, best64,
-                              scores_dbg, ws + L.ev, fused_tail ? &targs : nullptr, s);
+                              scores_dbg, ws + L.ev, fused_tail ? &targs : nullptr, tf32 ? codebook : nullptr, s);
         if (rc != 0) return rc;
         if (scores_dbg) return 0;
         void* tfb = stage_timing_begin(s, VQB_STAGE_FALLBACK);
@@ -362,7 +368,8 @@ int vqb_debug_counters(const void* workspace, int64_t* counters_out_host) {
 int vqb_debug_tc_scores(const float* z_bcw, const float* codebook, int B, int D, int64_t W, int K, int flags, float* scores_out,
                         void* workspace, size_t workspace_bytes, void* stream) {
     if (!scores_out) { set_error("vqb_debug_tc_scores: NULL output"); return VQB_E_NULL; }
-    return forward_impl(z_bcw, codebook, B, D, W, K, (flags & ~VQB_PREC_MASK) | VQB_PREC_BF16, nullptr, nullptr, nullptr, workspace,
+    const int prec = (flags & VQB_PREC_MASK) == VQB_PREC_TF32 ? VQB_PREC_TF32 : VQB_PREC_BF16;
+    return forward_impl(z_bcw, codebook, B, D, W, K, (flags & ~VQB_PREC_MASK) | prec, nullptr, nullptr, nullptr, workspace,
                         workspace_bytes, static_cast<cudaStream_t>(stream), false, scores_out);
 }
 

@@ -105,8 +105,9 @@ struct TailArgs {
 };
 
 // ---- launchers (vqb_kernels.cu) -------------------------------------------------------------------------------
+// tf32: the rounding-residual norms of the guard band are those of the tf32 operand (low 13 mantissa bits dropped); no bf16 copy
 cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb,
-                                 __nv_bfloat16* eh, WsMeta* meta, cudaStream_t s);
+                                 __nv_bfloat16* eh, WsMeta* meta, cudaStream_t s, bool tf32 = false);
 cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int64_t N_pad, __nv_bfloat16* xb, float* band,
                                     const WsMeta* meta, cudaStream_t s);
 // rows == nullptr: all N frames -> idx32[n]; else the frames listed in rows[0..*row_count) -> cand_cnt/cand_idx (count 1)
@@ -144,7 +145,7 @@ cudaError_t launch_window(const int64_t* idx, int B, int64_t L, int window, int6
 // box_frames == 32 (128-byte rows) and a 1024-byte aligned destination
 bool latents_read_once(size_t latent_bytes);   // stream the latents with an L2 evict-first policy? (vqb_kernels.cu)
 int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims,
-                    bool swizzle128 = false);
+                    bool swizzle128 = false, bool atom32 = false);   // atom32: 128B swizzle with 32-byte atoms (tf32 MN-major operand)
 
 // ---- tensor-core search (vqb_tc.cu) ---------------------------------------------------------------------------
 // Shortlist per frame from bf16 tcgen05 scores: cand_cnt/cand_idx, overflow frames appended to fallback_rows.
@@ -155,6 +156,7 @@ bool tc_fused_tail_enabled();                               // VQB_TC_TAIL=0 kee
 int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh,
                      const float* band, int64_t N, int64_t N_pad,
                      int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx, int* fallback_rows, WsMeta* meta,
-                     unsigned long long* best64, float* scores_dbg, void* ev_scratch, const TailArgs* tail, cudaStream_t s);
+                     unsigned long long* best64, float* scores_dbg, void* ev_scratch, const TailArgs* tail, const float* codebook_f32,
+                     cudaStream_t s);   // codebook_f32 != nullptr: kind::tf32 from the fp32 operands (needs z_fused, no fused tail)
 
 }  // namespace vqb

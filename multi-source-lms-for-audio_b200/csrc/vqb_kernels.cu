@@ -38,7 +38,7 @@ __device__ __forceinline__ bool code_ok(int64_t k, int K) { return (unsigned lon
 // guard band, non-finite flag.  Rows K..K_pad-1 get e2 = +inf (never shortlisted) and zero operands.
 __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restrict__ E, int K, int K_pad, int D,
                                                             float* __restrict__ e2, __nv_bfloat16* __restrict__ eb,
-                                                            __nv_bfloat16* __restrict__ eh, WsMeta* meta) {
+                                                            __nv_bfloat16* __restrict__ eh, WsMeta* meta, bool tf32) {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= K_pad) return;
@@ -46,7 +46,11 @@ __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restr
     for (int d = lane; d < D; d += 32) {
         const float v = (k < K) ? E[(size_t)k * D + d] : 0.f;
         s = __fadd_rn(s, __fmul_rn(v, v));
-        if (eb) {
+        if (tf32) {                               // what kind::tf32 reads: the low 13 mantissa bits dropped.  |e| bounds |tf32(e)| also
+            const float vt = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u), dv = v - vt;   // for a rounding unit (factor below)
+            st = fmaf(v, v, st);
+            sd = fmaf(dv, dv, sd);
+        } else if (eb) {
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const float vt = __bfloat162float(h), dv = v - vt;
             st = fmaf(vt, vt, st);
@@ -63,8 +67,8 @@ __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restr
             if (!isfinite(s)) atomicExch(&meta->cb_nonfinite, 1);
             else {
                 atomicMax(&meta->emax2_bits, __float_as_uint(s));
-                if (eb) {
-                    atomicMax(&meta->etmax2_bits, __float_as_uint(st));
+                if (eb || tf32) {
+                    atomicMax(&meta->etmax2_bits, __float_as_uint(tf32 ? st * 1.002f : st));   // |rn_tf32(e)| <= |e| (1 + 2^-11)
                     atomicMax(&meta->demax2_bits, __float_as_uint(sd));
                 }
             }
@@ -87,8 +91,8 @@ __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restr
 }
 
 cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb, __nv_bfloat16* eh,
-                                 WsMeta* meta, cudaStream_t s) {
-    codebook_prep_kernel<<<(K_pad + 7) / 8, 256, 0, s>>>(codebook, K, K_pad, D, e2, eb, eh, meta);
+                                 WsMeta* meta, cudaStream_t s, bool tf32) {
+    codebook_prep_kernel<<<(K_pad + 7) / 8, 256, 0, s>>>(codebook, K, K_pad, D, e2, eb, eh, meta, tf32);
     note_launch();
     return cudaGetLastError();
 }

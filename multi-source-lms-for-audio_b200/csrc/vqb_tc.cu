@@ -69,6 +69,7 @@ struct Barriers {
     unsigned long long a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
     unsigned long long eh_full[MAX_EH_SLOTS], eh_empty[MAX_EH_SLOTS], tmem_full[2], tmem_empty[2];
     unsigned long long stg_full[STG_SLOTS], stg_empty[STG_SLOTS];
+    unsigned long long a_land[2];     // tf32 mode: the TMA boxes of a whole fp32 A tile have landed (local; a_full follows the norm pass)
     unsigned int tmem_base;
     unsigned int pad;
 };
@@ -164,6 +165,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem]^T, fp32 operands read as tf32 (kind::tf32, K = 8 per instruction), fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -182,6 +200,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// MN-major tf32 operand (the fp32 [dims][frames] latent boxes as they lie in the reference's [B, D, W] layout).  For 32-bit
+// MN-major operands the only shared-memory layout the tensor core accepts is "128-byte swizzle with 32-byte atoms" (layout type 1;
+// TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B = 32 fp32 along MN, atoms of 4 K-rows (512 B) in which the
+// 32-byte chunk index is XORed with the row number.  `lbo` bytes between consecutive 32-element groups along MN, `sbo` bytes
+// between consecutive 4-row atoms along K (cute/atom/mma_traits_sm100.hpp, Layout_MN_SW128_32B_Atom).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) |
+           (1ull << 61);
+}
+// kind::tf32: a/b format TF32 (2<<7, 2<<10), A MN-major (bit 15), B K-major
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdescTf32_2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 // c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
@@ -427,7 +457,11 @@ __device__ __forceinline__ void tail_stream(const unsigned char* sTx, uint32_t b
 //               codeword gather, straight-through value, SSE, histogram, residual sums, index - one tile behind the tensor
 //               core.  The tile's latents are read a second time while they are still in L2, so the forward pass touches
 //               HBM once for the latents and once for `quantized`; no stand-alone tail kernel runs.
-template <bool kTwo, bool kFuse, bool kTail>
+// kTf32 = true (needs kFuse, no kTail): kind::tf32 MMAs straight from the fp32 operands.  The A tile is the tile's fp32 latents as four
+//               128-byte-swizzled TMA boxes [D dims][32 frames] (an MN-major operand: no conversion, no copy); the codebook tiles are
+//               fp32 boxes [codes][32 dims].  Warp 19 only loads A tiles, warp 18 measures |x| and |x - tf32(x)| of the landed tile
+//               (guard band) and then releases it to the MMA issuer.  tf32 runs at half the bf16 tensor rate, the band is ~3x tighter.
+template <bool kTwo, bool kFuse, bool kTail, bool kTf32 = false>
 __global__ void __launch_bounds__(kTail ? NUM_THREADS_TAIL : NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
                  const __grid_constant__ CUtensorMap tmap_eh, const __grid_constant__ CUtensorMap tmap_xt, const __nv_bfloat16* __restrict__ eh, int64_t W, int tiles_per_item, int D,
@@ -437,15 +471,19 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
                  const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots) {
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
+    static_assert(!kTf32 || (kFuse && !kTail), "tf32 reads the fp32 latents in place; no fused tail");
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sA = smem;                                            // a_slots x 16 KiB
-    unsigned char* sB = sA + (size_t)a_slots * A_CHUNK_BYTES;            // b_stages x 32 KiB (16 KiB half tiles in 2-CTA mode)
+    const uint32_t a_slot_bytes = kTf32 ? (uint32_t)BM * (uint32_t)D * 4u : (uint32_t)A_CHUNK_BYTES;   // tf32: a_slots whole fp32 tiles
+    unsigned char* sA = smem;                                            // a_slots x 16 KiB (tf32: a_slots x 128 D x 4 bytes)
+    unsigned char* sB = sA + (size_t)a_slots * a_slot_bytes;             // b_stages x 32 KiB (16 KiB half tiles in 2-CTA mode)
     unsigned char* sEH = sB + (size_t)b_stages * (kTwo ? B_STAGE_BYTES / 2 : B_STAGE_BYTES);   // eh_slots x 4 KiB bias operand B (K-half 0)
     unsigned char* sAX = sEH + eh_slots * EH_SLICE_BYTES;                // 2 KiB constant bias operand A (K-half 0)
     unsigned char* sZero = sAX + AX_BYTES;                               // 4 KiB of zeros: K-half 1 of both bias operands
     unsigned char* sStg = sZero + ZERO_BYTES;                            // fused mode: STG_SLOTS x 8 KiB fp32 boxes [16 dims][128 frames]
-    float* sBand = reinterpret_cast<float*>(sStg + (kFuse ? STG_SLOTS * STG_BYTES : 0));   // fused mode: [2][128] guard bands
-    float* sMin = sBand + (kFuse ? 2 * BM : 0);                          // [4][128] running maxima of the four column quarters
+    float* sBand = reinterpret_cast<float*>(sStg + ((kFuse && !kTf32) ? STG_SLOTS * STG_BYTES : 0));   // fused mode: [4][128] guard bands
+    // ([4][128]: the bands of round rd are written while the epilogue may still be up to two accumulator stages behind the tensor
+    // core - with one or two codebook tiles per frame tile that is up to three rounds back)
+    float* sMin = sBand + (kFuse ? 4 * BM : 0);                          // [4][128] running maxima of the four column quarters
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
     uint32_t* sEv = reinterpret_cast<uint32_t*>(sCnt + 3 * BM);          // [512][ev_sm] shared-memory part of the event stacks
     // fused tail: the shortlists of two frame tiles (the epilogue fills one while the tail warps consume the other)
@@ -469,6 +507,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
     constexpr uint32_t kStageBytes = kTwo ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;   // per-CTA bytes of one codebook stage
     constexpr uint32_t kEhBytes = kTwo ? EH_SLICE_BYTES / 2 : EH_SLICE_BYTES;
+    constexpr int kBK = kTf32 ? 32 : BK;         // elements per 128-byte swizzle row of a codebook stage: 32 fp32 or 64 bf16
     const bool leader = !kTwo || crank == 0;
     const int n_clusters = (int)gridDim.x / cs;
     const int cluster_id = (int)blockIdx.x / cs;
@@ -481,10 +520,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (warp == MMA_WARP && lane == 0) {
         for (int i = 0; i < b_stages; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), kTwo ? 1 : cs); }
         for (int i = 0; i < a_slots; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), kFuse ? (kTwo ? 4 : 2) : 1);   // fused: two converter warps per CTA (both CTAs in 2-CTA mode)
+            // fused: two converter warps per CTA (both CTAs in 2-CTA mode); tf32: one norm warp per CTA
+            mbar_init(smem_u32(&bars->a_full[i]), kTf32 ? (kTwo ? 2 : 1) : (kFuse ? (kTwo ? 4 : 2) : 1));
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
         }
         for (int i = 0; i < STG_SLOTS; ++i) { mbar_init(smem_u32(&bars->stg_full[i]), 1); mbar_init(smem_u32(&bars->stg_empty[i]), 2); }
+        mbar_init(smem_u32(&bars->a_land[0]), 1);
+        mbar_init(smem_u32(&bars->a_land[1]), 1);
         for (int i = 0; i < eh_slots; ++i) {
             mbar_init(smem_u32(&bars->eh_full[i]), 1);
             mbar_init(smem_u32(&bars->eh_empty[i]), 1);
@@ -564,13 +606,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         }
                         if (kTwo) {
                             if (leader) mbar_expect_tx(bar_bfull + b_st * 8, B_STAGE_BYTES);   // both halves
-                            tma_load_2d_2sm(sB_u + b_st * kStageBytes, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN + b_row_off);
+                            tma_load_2d_2sm(sB_u + b_st * kStageBytes, &tmap_e, bar_bfull + b_st * 8, kb * kBK, nt * BN + b_row_off);
                         } else {
                             mbar_expect_tx(bar_bfull + b_st * 8, B_STAGE_BYTES);   // own slice + the peers' slices
                             if (cs == 1)
-                                tma_load_2d(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN);
+                                tma_load_2d(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * kBK, nt * BN);
                             else
-                                tma_load_2d_mc(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * BK, nt * BN + b_row_off, cmask);
+                                tma_load_2d_mc(sB_u + b_st * B_STAGE_BYTES, &tmap_e, bar_bfull + b_st * 8, kb * kBK, nt * BN + b_row_off, cmask);
                         }
                     }
                     __syncwarp();
@@ -585,7 +627,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         //                                                                   in 2-CTA mode only the pair's leader)
         if (leader) {
         uint32_t a_slot0 = 0, a_ph = 0, b_st = 0, b_ph = 0, as = 0, t_ph = 0, es = 0, e_ph = 0;
-        const uint64_t dA0 = make_desc_sw128(smem_u32(sA)), dB0 = make_desc_sw128(smem_u32(sB));
+        const uint64_t dA0 = kTf32 ? make_desc_mn_sw128_32b(smem_u32(sA), (uint32_t)D * 128u, 512u) : make_desc_sw128(smem_u32(sA));
+        const uint64_t dB0 = make_desc_sw128(smem_u32(sB));
         // bias operands: 8-row groups 128 B apart, K-half 1 = the shared zero block
         const uint64_t dAX = make_desc_noswz(smem_u32(sAX), smem_u32(sZero) - smem_u32(sAX), 128);
         const uint32_t sEH_u = smem_u32(sEH), sZero_u = smem_u32(sZero);
@@ -599,6 +642,35 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const uint32_t tmem_d = tmem_base + as * BN;
                 const bool last_nt = nt == num_n_tiles - 1;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    if (kTf32) {
+                        // the A operand is one whole fp32 tile per round (slot = rd mod a_slots, released by the norm warp); a codebook
+                        // stage holds 32 dims = four K steps of 8 (fewer in the last stage when D % 32 != 0)
+                        const uint32_t tslot = (uint32_t)rd % (uint32_t)a_slots, t_phase = ((uint32_t)rd / (uint32_t)a_slots) & 1u;
+                        if (nt == 0 && kb == 0) mbar_wait(bar_afull + tslot * 8, t_phase);
+                        mbar_wait(bar_bfull + b_st * 8, b_ph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            // A: +64 (1024 bytes) per K step = the next group of 8 dims; B: +2 (32 bytes) per K step inside the 128-byte row
+                            const uint64_t da = dA0 + (uint64_t)(tslot * (a_slot_bytes >> 4)) + (uint64_t)(kb * 4 * 64);
+                            const uint64_t db = dB0 + (uint64_t)(b_st * (kStageBytes >> 4));
+                            const int steps = (D - kb * 32) >= 32 ? 4 : (D - kb * 32) / 8;
+                            for (int st = 0; st < steps; ++st) {
+                                if (kTwo) umma_tf32_2sm(tmem_d, da + (uint64_t)(st * 64), db + (uint64_t)(st * 2), kIdescTf32_2, (kb | st) ? 1u : 0u);
+                                else umma_tf32(tmem_d, da + (uint64_t)(st * 64), db + (uint64_t)(st * 2), kIdescTf32, (kb | st) ? 1u : 0u);
+                            }
+                            if (kTwo) {
+                                umma_commit_2sm(bar_bempty + b_st * 8, 3);
+                                if (last_nt && kb == num_kb - 1) umma_commit_2sm(bar_aempty + tslot * 8, 3);
+                            } else {
+                                if (cs == 1) umma_commit(bar_bempty + b_st * 8);
+                                else umma_commit_mc(bar_bempty + b_st * 8, cmask);
+                                if (last_nt && kb == num_kb - 1) umma_commit(bar_aempty + tslot * 8);
+                            }
+                        }
+                        __syncwarp();
+                        if (++b_st == (uint32_t)b_stages) { b_st = 0; b_ph ^= 1; }
+                        continue;
+                    }
                     uint32_t slot = a_slot0 + kb, a_phk = a_ph;
                     if (slot >= (uint32_t)a_slots) { slot -= a_slots; a_phk ^= 1; }
                     if (nt == 0) mbar_wait(bar_afull + slot * 8, a_phk);
@@ -653,7 +725,67 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (a_slot0 >= (uint32_t)a_slots) { a_slot0 -= a_slots; a_ph ^= 1; }
         }
         }
-    } else if (kFuse && (warp == CONVERT_WARP || warp == ALOAD_WARP)) {
+    } else if (kTf32 && warp == ALOAD_WARP) {
+        // ================================================================ tf32: loader of the fp32 A tiles.  One tile = four boxes
+        // [D dims][32 frames] (128-byte swizzle with 32-byte atoms), frame group fg at fg * D * 128 bytes of the slot: the MN-major
+        // canonical layout of a 32-bit operand.
+        const uint32_t bar_aempty = smem_u32(&bars->a_empty[0]), bar_land = smem_u32(&bars->a_land[0]), sA_u = smem_u32(sA);
+        for (int rd = 0; rd < rounds; ++rd) {
+            const uint32_t tslot = (uint32_t)rd % (uint32_t)a_slots, t_phase = ((uint32_t)rd / (uint32_t)a_slots) & 1u;
+            int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;
+            if (mt >= num_m_tiles) mt = 0;                                   // dummy tile: re-read tile 0, nothing is published
+            const int b_ = mt / tiles_per_item, w0_ = (mt - b_ * tiles_per_item) * BM;
+            mbar_wait(bar_aempty + tslot * 8, t_phase ^ 1);                  // the MMAs that read this slot last are done
+            if (elect_one()) {
+                mbar_expect_tx(bar_land + tslot * 8, a_slot_bytes);
+#pragma unroll
+                for (int fg = 0; fg < BM / 32; ++fg) {                       // frames past W arrive as zeros
+                    const uint32_t dst = sA_u + tslot * a_slot_bytes + (uint32_t)fg * (uint32_t)D * 128u;
+                    if (l2_once) tma_load_3d_once(dst, &tmap_x, bar_land + tslot * 8, w0_ + fg * 32, 0, b_);
+                    else tma_load_3d(dst, &tmap_x, bar_land + tslot * 8, w0_ + fg * 32, 0, b_);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (kTf32 && warp == CONVERT_WARP) {
+        // ================================================================ tf32: norm warp.  Lane l measures frames l, l + 32, l + 64,
+        // l + 96 of the landed tile (one per frame group: a row of the swizzled box holds 32 frames in a permuted order, so the 32
+        // lanes of a load never meet in a bank), publishes the guard bands and only then releases the tile to the MMA issuer - the
+        // epilogue therefore finds the bands of a tile as soon as it sees the tile's first accumulator.
+        const uint32_t bar_afull = smem_u32(&bars->a_full[0]), bar_land = smem_u32(&bars->a_land[0]);
+        const float etmax = sqrtf(__uint_as_float(meta_ro->etmax2_bits)) * 1.0001f;
+        const float demax = sqrtf(__uint_as_float(meta_ro->demax2_bits)) * 1.0001f;
+        const float emax = sqrtf(__uint_as_float(meta_ro->emax2_bits)) * 1.0001f;
+        for (int rd = 0; rd < rounds; ++rd) {
+            const uint32_t tslot = (uint32_t)rd % (uint32_t)a_slots, t_phase = ((uint32_t)rd / (uint32_t)a_slots) & 1u;
+            mbar_wait(bar_land + tslot * 8, t_phase);
+            const unsigned char* tile = sA + (size_t)tslot * a_slot_bytes;
+            float s2[4] = {0.f, 0.f, 0.f, 0.f}, sd2[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int d = 0; d < D; ++d) {
+                // 32-byte chunk (8 frames) of row d sits at chunk position (lane / 8) ^ (d % 4)
+                const uint32_t off = (uint32_t)d * 128u + ((((uint32_t)lane >> 3) ^ ((uint32_t)d & 3u)) << 5) + (((uint32_t)lane & 7u) << 2);
+#pragma unroll
+                for (int fg = 0; fg < 4; ++fg) {
+                    const float x = *reinterpret_cast<const float*>(tile + (size_t)fg * D * 128 + off);
+                    // what the tensor core drops: the low 13 mantissa bits (a round-to-nearest unit would drop no more than that)
+                    const float dx = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                    s2[fg] = fmaf(x, x, s2[fg]);
+                    sd2[fg] = fmaf(dx, dx, sd2[fg]);
+                }
+            }
+#pragma unroll
+            for (int fg = 0; fg < 4; ++fg) {
+                const float xn = sqrtf(s2[fg]) * 1.0001f, dxn = sqrtf(sd2[fg]) * 1.0001f;
+                sBand[(rd & 3) * BM + fg * 32 + lane] = 4.0f * (dxn * etmax + xn * demax) * 1.001f +
+                                                        8.0f * (float)(D + 16) * 2.3841858e-07f * xn * emax + 4.0e-7f * emax * emax + 1e-30f;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (kTwo && crank != 0) mbar_arrive_remote(bar_afull + tslot * 8, 0);
+                else mbar_arrive(bar_afull + tslot * 8);
+            }
+        }
+    } else if (!kTf32 && kFuse && (warp == CONVERT_WARP || warp == ALOAD_WARP)) {
         // ================================================================ fused operand preparation: two converter warps.
         // Warp 18 owns frames 0..63 of the tile, warp 19 frames 64..127 (two frames per lane).  Warp 19 is also the loader:
         // before it touches sub-chunk g it makes sure the TMA loads up to g + STG_SLOTS - 1 are issued.  A load waits only
@@ -745,7 +877,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const float xn = sqrtf(s2[i]) * 1.0001f, dxn = sqrtf(sd2[i]) * 1.0001f;
-                        sBand[(rd & 1) * BM + r0 + i] = 4.0f * (dxn * etmax + xn * demax) * 1.001f +
+                        sBand[(rd & 3) * BM + r0 + i] = 4.0f * (dxn * etmax + xn * demax) * 1.001f +
                                                          8.0f * (float)(D + 16) * 2.3841858e-07f * xn * emax + 4.0e-7f * emax * emax + 1e-30f;
                     }
                 }
@@ -905,7 +1037,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
                 tc_fence_after();
                 if (kFuse && nt == 0) {                   // the converter published this tile's bands before the first MMA could start
-                    band = sBand[(rd & 1) * BM + row_in_tile];
+                    band = sBand[(rd & 3) * BM + row_in_tile];
                     hband = 0.5f * band;
                 }
                 const uint32_t taddr = tmem_base + t_lane + as * BN + colq * COLS_PER_WARP;
@@ -1048,6 +1180,22 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
     return 0;
 }
 
+// fp32 codebook [K, D] row-major as the tf32 B operand: box = 32 dims (128 B) x box_rows codes, 128B swizzle; rows past K and
+// dims past D read as zeros (their bias operand keeps padded codes from ever winning)
+static int make_map_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t D, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VQB_E_DEVICE; }
+    const cuuint64_t dims[2] = {D, rows};
+    const cuuint64_t strides[1] = {D * 4};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(codebook fp32) failed with CUresult %d", (int)r); return 1000 + (int)r; }
+    return 0;
+}
+
 // bias operand [K_pad, 8] bf16 (16-byte rows, no swizzle): box = 128 codes = one CTA's half of a codebook tile
 static int make_map_eh(CUtensorMap* map, const void* base, uint64_t rows) {
     EncodeTiledFn fn = get_encode_fn();
@@ -1073,7 +1221,7 @@ static int make_map_z(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, 
 // 3-D TMA view of the [B, D, W] fp32 latents (or of `quantized`): box = box_frames x box_dims x 1, out-of-range frames read as
 // zeros and are clipped on stores.  Needs 16-byte global strides: W % 4 == 0 and a 16-byte aligned base.
 int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, uint64_t W, uint32_t box_frames, uint32_t box_dims,
-                    bool swizzle128) {
+                    bool swizzle128, bool atom32) {
     tc::EncodeTiledFn fn = tc::get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VQB_E_DEVICE; }
     const cuuint64_t dims[3] = {W, D, B};
@@ -1090,7 +1238,8 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
               : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     }
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(z), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle128 ? (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B) : CU_TENSOR_MAP_SWIZZLE_NONE,
                           promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(z) failed with CUresult %d", (int)r); return 1000 + (int)r; }
     return 0;
@@ -1105,10 +1254,10 @@ struct TcPlan {
     size_t smem;
 };
 
-static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int D) {
+static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int D, bool tf32 = false) {
     using namespace tc;
     TcPlan p{};
-    const int num_kb = (D + BK - 1) / BK;
+    const int num_kb = tf32 ? (D + 31) / 32 : (D + BK - 1) / BK;
     // default: CTA pairs with cta_group::2 MMAs; VQB_TC_MODE=1: cta_group::1 with VQB_TC_CLUSTER-way codebook multicast
     p.two = true;
     if (env_get(ENV_TC_MODE, 0) == 1) p.two = false;
@@ -1123,6 +1272,9 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     // the last chunks of the next tile can only be converted inside the last codebook tile), else two spare chunks.
     p.a_slots = num_kb <= 2 ? 2 * num_kb : num_kb;
     if (fuse && num_kb > 2 && num_kb + 2 <= 6) p.a_slots = num_kb + 2;
+    // tf32: the A ring holds whole fp32 tiles of 128 frames x D x 4 bytes - two when they leave three codebook stages, else one
+    const size_t a_unit = tf32 ? (size_t)BM * D * 4 : (size_t)A_CHUNK_BYTES;
+    if (tf32) p.a_slots = 2;
     // Bias-operand ring.  The producer walks the codebook tiles in order and waits for the bias slot of tile j before it
     // loads anything of tile j, so this ring bounds how far ALL operand loads run ahead of the tensor core.  Measured at
     // K = 1024, D = 64 (where a codebook tile is only ~640 tensor-core cycles): 2, 4 and 8 slots give the same kernel time -
@@ -1130,16 +1282,17 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     p.eh_slots = EH_SLOTS;
     if (const int v = env_get(ENV_TC_EHSLOTS, 0); v >= 2 && v <= MAX_EH_SLOTS) p.eh_slots = v;   // experiments
     const size_t fixed_no_a = (size_t)p.eh_slots * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
-                              (fuse ? STG_SLOTS * STG_BYTES + 2 * BM * 4 : 0) +
+                              (fuse ? (tf32 ? 0 : STG_SLOTS * STG_BYTES) + 4 * BM * 4 : 0) +
                               (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
                               sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
-    if (fuse && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
+    if (!tf32 && fuse && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
         // the full second tile must leave three codebook stages (it does for CTA pairs at D = 256: 3 x 16 KiB half-tile stages)
         bool full_second_tile = fixed_no_a + (size_t)2 * num_kb * A_CHUNK_BYTES + 3 * stage_bytes <= 227 * 1024;
         if (const int v = env_get(ENV_TC_ASLOTS, -1); v >= 0) full_second_tile = full_second_tile && v >= 2 * num_kb;   // experiments
         if (full_second_tile) p.a_slots = 2 * num_kb;   // pays with one codebook stage (3 instead of 4: measured equal)
     }
-    const size_t fixed = (size_t)p.a_slots * A_CHUNK_BYTES + fixed_no_a;
+    if (tf32 && fixed_no_a + 2 * a_unit + 3 * stage_bytes > 227 * 1024) p.a_slots = 1;
+    const size_t fixed = (size_t)p.a_slots * a_unit + fixed_no_a;
     // shared-memory part of the event stacks: whatever four codebook stages leave, at most 3 entries per epilogue thread
     const size_t ev_entry_bytes = (size_t)EPI_THREADS * EV_WORDS * 4;   // one entry for every epilogue thread: 24 KiB
     p.ev_sm = 0;
@@ -1152,14 +1305,19 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     p.b_stages = fixed_ev < 227 * 1024 ? (int)((227 * 1024 - fixed_ev) / stage_bytes) : 0;
     if (p.b_stages > (p.two ? 8 : 4)) p.b_stages = p.two ? 8 : 4;
     if (const int v = env_get(ENV_TC_STAGES, 0); v >= 2 && v < p.b_stages) p.b_stages = v;   // experiments
-    p.ok = p.b_stages >= 2 && p.a_slots <= MAX_A_SLOTS;
+    p.ok = p.b_stages >= 2 && p.a_slots <= MAX_A_SLOTS && !(tf32 && (with_tail || !fuse));
     p.smem = fixed_ev + (size_t)p.b_stages * stage_bytes;
     return p;
 }
 
 bool tc_can_fuse(const float* z, int B, int D, int64_t W, int prec) {
-    (void)prec;
     if (env_get(ENV_TC_FUSE, 1) == 0) return false;
+    if (prec == VQB_PREC_TF32) {
+        // the fp32 tile is the A operand itself: a box of D dims (TMA boxes hold at most 256 rows) per 32 frames
+        const int64_t t = (int64_t)B * ((W + tc::BM - 1) / tc::BM);
+        return D <= 256 && (D % 8) == 0 && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (W % 128 == 0 || W >= 1024) &&
+               tc_plan(true, false, false, (int)(t < (1 << 30) ? t : (1 << 30)), D, true).ok;
+    }
     // the staging ring of the fused preparation must leave room for the pipeline: it does not with an eight-chunk A tile
     // (D > 448) outside the CTA-pair mode (whole-tile codebook stages: fewer than four frame tiles, or VQB_TC_MODE=1)
     const int64_t tiles = (int64_t)B * ((W + tc::BM - 1) / tc::BM);
@@ -1213,10 +1371,12 @@ static void timing_end(TimingSlot* t, cudaStream_t s) { stage_timing_end(t, s); 
 int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16* xb, const __nv_bfloat16* eb, const __nv_bfloat16* eh,
                      const float* band, int64_t N, int64_t N_pad, int K, int K_pad, int D, uint8_t* cand_cnt, uint16_t* cand_idx,
                      int* fallback_rows, WsMeta* meta, unsigned long long* best64, float* scores_dbg, void* ev_scratch,
-                     const TailArgs* tail_args, cudaStream_t s) {
+                     const TailArgs* tail_args, const float* codebook_f32, cudaStream_t s) {
     using namespace tc;
     const bool fuse = z_fused != nullptr;          // the caller decided with tc_can_fuse(): A operand built in-kernel from fp32 BCW
     const bool with_tail = tail_args != nullptr;   // the kernel also finishes the frames (needs the fused operand preparation)
+    const bool tf32 = codebook_f32 != nullptr;     // kind::tf32 straight from the fp32 latents and the fp32 codebook
+    if (tf32 && (!fuse || with_tail)) { set_error("tc_search: tf32 needs the in-place fp32 operand path"); return VQB_E_FLAGS; }
     if (with_tail && (!fuse || scores_dbg)) { set_error("tc_search: the fused tail needs the fused operand preparation"); return VQB_E_FLAGS; }
     if (with_tail && ((reinterpret_cast<uintptr_t>(tail_args->codebook) & 31) || (D % 8))) {
         set_error("tc_search: the fused tail gathers codebook rows with 32-byte loads; the codebook must be 32-byte aligned");
@@ -1224,18 +1384,19 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     }
     CUtensorMap mx;
     int rc;
-    if (fuse) rc = make_map_z(&mx, z_fused, (uint64_t)B, (uint64_t)D, (uint64_t)W);
+    if (tf32) rc = make_latent_map(&mx, z_fused, (uint64_t)B, (uint64_t)D, (uint64_t)W, 32, (uint32_t)D, true, true);
+    else if (fuse) rc = make_map_z(&mx, z_fused, (uint64_t)B, (uint64_t)D, (uint64_t)W);
     else rc = make_map(&mx, xb, (uint64_t)N_pad, (uint64_t)D, BM);
     if (rc != 0) return rc;
     const int tiles_per_item = (int)((W + BM - 1) / BM);
-    const int num_kb = (D + BK - 1) / BK;
+    const int num_kb = tf32 ? (D + 31) / 32 : (D + BK - 1) / BK;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > kTcMaxCtas) sms = kTcMaxCtas;
     const int num_m_tiles = fuse ? B * tiles_per_item : (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
-    const TcPlan plan = tc_plan(fuse, with_tail, scores_dbg != nullptr, num_m_tiles, D);
+    const TcPlan plan = tc_plan(fuse, with_tail, scores_dbg != nullptr, num_m_tiles, D, tf32);
     if (!plan.ok) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
     const bool two = plan.two;
     const int cs = plan.cs, a_slots = plan.a_slots, b_stages = plan.b_stages, ev_sm = plan.ev_sm;
@@ -1249,13 +1410,16 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_search_kernel)");
         attr_done = true;
     }
     CUtensorMap me_c, meh, mxt;
     if (with_tail) { if ((rc = make_map_z(&mxt, z_fused, (uint64_t)B, (uint64_t)D, (uint64_t)W, TAIL_CHUNK)) != 0) return rc; }
     else mxt = mx;
-    if ((rc = make_map(&me_c, eb, (uint64_t)K_pad, (uint64_t)D, two ? BN / 2 : BN / cs)) != 0) return rc;
+    if (tf32) { if ((rc = make_map_f32(&me_c, codebook_f32, (uint64_t)K, (uint64_t)D, two ? BN / 2 : BN / cs)) != 0) return rc; }
+    else if ((rc = make_map(&me_c, eb, (uint64_t)K_pad, (uint64_t)D, two ? BN / 2 : BN / cs)) != 0) return rc;
     if ((rc = make_map_eh(&meh, eh, (uint64_t)K_pad)) != 0) return rc;
     int grid = num_m_tiles < sms ? num_m_tiles : sms;
     grid = grid / cs * cs;
@@ -1275,11 +1439,13 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     cudaError_t le;
     const TailArgs targs = with_tail ? *tail_args : TailArgs{};
     const int l2_once = (fuse && latents_read_once((size_t)N * D * 4)) ? 1 : 0;   // stream the latents past the L2-resident working set
-#define VQB_TC_LAUNCH(TWO, FUSE, TAIL)                                                                                                       \
-    le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
+#define VQB_TC_LAUNCH(TWO, FUSE, TAIL, ...)                                                                                                  \
+    le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL, ##__VA_ARGS__>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
                             num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \
                             scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, ev_sm, l2_once, plan.eh_slots)
-    if (two && with_tail) VQB_TC_LAUNCH(true, true, true);
+    if (tf32 && two) VQB_TC_LAUNCH(true, true, false, true);
+    else if (tf32) VQB_TC_LAUNCH(false, true, false, true);
+    else if (two && with_tail) VQB_TC_LAUNCH(true, true, true);
     else if (with_tail) VQB_TC_LAUNCH(false, true, true);
     else if (two && fuse) VQB_TC_LAUNCH(true, true, false);
     else if (two) VQB_TC_LAUNCH(true, false, false);

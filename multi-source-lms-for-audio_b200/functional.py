@@ -242,15 +242,15 @@ def debug_counters(device=None) -> dict:
     return {"rescored": out[0], "fallback": out[1], "shortlisted": out[2]}
 
 
-def debug_tc_scores(z: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
-    """Raw tensor-core scores |e|^2 - 2 bf16(x).bf16(e), [N, K]; test hook for the tcgen05 tile."""
+def debug_tc_scores(z: torch.Tensor, codebook: torch.Tensor, precision: str = "bf16") -> torch.Tensor:
+    """Raw tensor-core scores |e|^2 - 2 lp(x).lp(e), [N, K], lp = bf16 or tf32; test hook for the tcgen05 tile."""
     _require_cuda("z", z, torch.float32)
     _require_cuda("codebook", codebook, torch.float32)
     z = z.contiguous()
     codebook = codebook.contiguous()
     B, D, W = z.shape
     K = codebook.shape[0]
-    flags = L.PREC_BF16
+    flags = L.PRECISIONS[precision]
     with torch.cuda.device(z.device):
         ws = _workspace(z.device, workspace_bytes(B * W, K, D, flags))
         out = torch.full((B * W, K), float("nan"), dtype=torch.float32, device=z.device)

@@ -54,6 +54,8 @@ class VectorQuantizer(nn.Module):
 
     Extra keyword-only knobs (all default to reference behaviour):
       precision        "bf16": tcgen05 shortlist + fp32 rescoring (same indices as fp32, see DESIGN.md);
+                       "tf32": the same with kind::tf32 MMAs straight from the fp32 latents and codebook (no converted
+                       copies, ~3x tighter guard band, half the tensor rate: the choice for small D);
                        "fp32": exact CUDA-core search.
       dense_encodings  "auto" (dense one-hot when N*K*4 bytes <= dense_limit_bytes, else a sparse COO tensor of the same
                        shape), True (always dense, like the reference) or False (always sparse).

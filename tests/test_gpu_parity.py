@@ -11,7 +11,7 @@ from vq_b200 import _lib, functional as F
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 LOSS_RTOL = 1e-5
-PRECISIONS = ["fp32", "bf16"]
+PRECISIONS = ["fp32", "bf16", "tf32"]
 
 
 def seeded(seed, shape, scale=1.0):
@@ -47,6 +47,36 @@ def run_module(z, cb, beta, precision, Gq=None, **kw):
 
 
 # ----------------------------------------------------------------------------------------------- tensor-core tile
+@pytest.mark.parametrize("B,D,W,K", [(1, 64, 128, 256), (2, 64, 1024, 512), (1, 256, 640, 8192), (3, 128, 1280, 300), (1, 80, 256, 1000),
+                                     (1, 16, 2048, 64), (2, 192, 384, 700)])
+def test_tcgen05_tf32_scores(B, D, W, K):
+    """The kind::tf32 tile: the fp32 [dims][frames] boxes as an MN-major swizzled A operand, fp32 codebook boxes as B.  Raw scores
+    equal |e|^2 - 2 tf32(x).tf32(e) in float64, where tf32() is what the tensor core keeps of an fp32 operand (truncation of the low
+    13 mantissa bits, or round-to-nearest - the test accepts either and the guard band covers both)."""
+    if W % 4 or not (W % 128 == 0 or W >= 1024) or D > 256:
+        pytest.skip("shape takes the bf16 shortlist (tf32 reads the latents in place)")
+    z = torch.from_numpy(seeded(11, (B, D, W))).to(DEV)
+    cb = torch.from_numpy(seeded(12, (K, D))).to(DEV)
+    got = F.debug_tc_scores(z, cb, precision="tf32")
+    assert not torch.isnan(got).any(), "tile left scores unwritten"
+    rows = z.permute(0, 2, 1).reshape(-1, D)
+
+    def trunc(t):
+        return (t.view(torch.int32) & -8192).view(torch.float32).double()
+
+    def rne(t):
+        i = t.view(torch.int32)
+        return ((i + 0x0FFF + ((i >> 13) & 1)) & -8192).view(torch.float32).double()
+    e2 = (cb.double() ** 2).sum(1)[None, :]
+    errs = {}
+    for name, f in (("truncate", trunc), ("round", rne)):
+        want = e2 - 2.0 * f(rows) @ f(cb).T
+        errs[name] = ((got.double() - want).abs().max().item(), want.abs().max().item())
+    best = min(errs, key=lambda k: errs[k][0])
+    err, scale = errs[best]
+    assert err <= 2e-5 * scale + 1e-4, f"max |score error| {errs} (best: {best})"
+
+
 @pytest.mark.parametrize("B,D,W,K", [(1, 64, 128, 256), (2, 64, 333, 512), (1, 256, 640, 8192), (3, 128, 100, 300),
                                      (1, 80, 257, 1000), (1, 512, 130, 512), (1, 16, 200, 64)])
 def test_tcgen05_scores_match_bf16_matmul(B, D, W, K):
@@ -220,7 +250,7 @@ def test_stage_timing_reports_every_stage_of_the_forward():
     lib.vqb_debug_kernel_timing(0)
 
 
-@pytest.mark.parametrize("precision,seed", [("bf16", 101), ("fp32", 102)])
+@pytest.mark.parametrize("precision,seed", [("bf16", 101), ("fp32", 102), ("tf32", 103)])
 def test_random_shapes_against_oracle(precision, seed):
     """scripts/stress_shapes.py: 80 random (B, D, W, K) incl. ragged / tiny / large-D shapes, forward + backward + index export +
     host path against the oracle.  (It found the launch-plan bugs fixed in round 1: D = 256 / 512 with fewer than four frame tiles.)"""
