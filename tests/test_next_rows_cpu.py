@@ -48,7 +48,10 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference": the unmodified reference module (from /root/reference, baseline/_ref or oracle/_ref); "port" only if none is there
+    from oracle import make_ref
+    want_kind = "reference" if make_ref.find_reference_file() else "port"
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
     assert other.returncode == 0 and other.stdout.strip() == ""
