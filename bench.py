@@ -643,15 +643,43 @@ def main():
                     "what": ("vqb_forward_host: pinned host latents -> chunked H2D overlapped with compute -> D2H indices + stats"
                              + (" + straight-through output `quantized` (what a call of the reference returns, vector_quantizer.py:54)"
                                 if want_q else "") + ("; statistics all-reduced over the ranks before the D2H" if world > 1 else ""))}
+        def dma_ceiling(duplex):
+            """What the host can feed: the same pinned buffers copied H2D (and, duplex, a same-sized buffer D2H at the same time)
+            with NO kernel in between, all ranks at once - the ceiling the end-to-end number is measured against."""
+            d_in = torch.empty((B, D, W), dtype=torch.float32, device=dev)
+            s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            q_host = torch.empty((B, D, W), dtype=torch.float32, pin_memory=True) if duplex else None
+            d_out = torch.empty((B, D, W), dtype=torch.float32, device=dev) if duplex else None
+            best = float("inf")
+            for _ in range(2):
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s_up):
+                    d_in.copy_(z_host, non_blocking=True)
+                if duplex:
+                    with torch.cuda.stream(s_dn):
+                        q_host.copy_(d_out, non_blocking=True)
+                torch.cuda.synchronize(dev)
+                best = min(best, time.perf_counter() - t0)
+            lo, hi = reduce_ranks(dev, world, z_host.numel() * 4 / best / 1e9)[::-1]
+            return {"gbs_per_rank_each_direction": {"min": lo, "max": hi}, "duplex": duplex,
+                    "vectors_per_s_if_dma_bound": N_job / reduce_ranks(dev, world, best)[0]}
+
         if not export_only:
             e2e = e2e_leg(True)
+            e2e["host_dma_ceiling"] = dma_ceiling(True)
+            e2e["frac_of_dma_ceiling"] = e2e["value"] / e2e["host_dma_ceiling"]["vectors_per_s_if_dma_bound"]
         e2e_index_only = e2e_leg(False)
+        e2e_index_only["host_dma_ceiling"] = dma_ceiling(False)
+        e2e_index_only["frac_of_dma_ceiling"] = e2e_index_only["value"] / e2e_index_only["host_dma_ceiling"]["vectors_per_s_if_dma_bound"]
         if e2e is None:
             e2e = e2e_index_only
         if e2e.get("h2d_gbs_per_rank") and world > 1:
-            e2e["limiter"] = ("host side: every rank streams its shard over its own PCIe Gen5 x16 link (~55 GB/s alone); the "
-                              "per-rank rate above falls as ranks are added because all GPUs hang off one NUMA node / root complex "
-                              "and share its DRAM bandwidth (topology in SCALE.topology)")
+            e2e["limiter"] = ("host side, not the kernels: every rank streams its shard over its own PCIe Gen5 x16 link (~55 GB/s alone, "
+                              "~46 GB/s each way full duplex); the per-rank rate falls as ranks are added because all GPUs hang off one "
+                              "NUMA node and share its DRAM bandwidth - host_dma_ceiling is the same traffic with no kernel at all")
         _lib.check("vqb_host_release", lib.vqb_host_release())
         del z_host, idx_host
     else:
