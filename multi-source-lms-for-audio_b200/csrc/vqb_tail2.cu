@@ -6,15 +6,18 @@
 // What changed against tail_tma_kernel, each answering a line of its ncu profile (profiles/r01_tail_cfg3_ncu_full.txt:
 // 18.6 % warps active, 16 % of the stall samples at the block barrier, 12 + 7 % on codebook gathers, 3.9 G warp instructions):
 //  * D = 32 J is a compile-time constant for every instance and the per-frame phase streams - it never holds the latent, the
-//    codeword of this round, the codeword of the next round and the winner at once (142 registers): 16-frame tiles and < 100
-//    registers put 5-6 blocks (20-24 warps) on an SM instead of 3 (12 warps).
-//  * Rescoring is DEALT: the (frame, code) pairs of a warp's frames go one per 8-lane group and round, so a warp runs
-//    ceil(pairs / 4) rounds instead of the longest shortlist among its concurrent frames (2.5 -> 1.3 rounds on randn latents),
-//    and the four warps of a block reach the write-back barrier at about the same time.
+//    codeword of this round, the codeword of the next round and the winner at once.
+//  * Rescoring is DEALT: the (frame, code) pairs of a warp's frames go one per 8-lane group and round (software-pipelined two
+//    deep), so a warp runs ceil(pairs / 4) rounds instead of the longest shortlist among its concurrent frames, and the four
+//    warps of a block reach the write-back barrier at about the same time.
+//  * The tile's shortlists are staged in shared memory before the box wait: a candidate code is never a global load that the
+//    codeword gather has to wait for.
 //  * |x|^2 is evaluated once per frame that has pairs, not once per pair.
 //  * Runs of frames with the same code (collapsed codebooks early in training: BASELINE config 4 starts at perplexity 1.75;
 //    real audio: neighbouring frames) keep their histogram count and, for D <= 128, their residual sum in registers and issue
-//    ONE set of atomics per run instead of one per frame - same-address atomics were the whole tail at K = 512.
+//    ONE set of atomics per run instead of one per frame - same-address atomics were the whole tail at K = 512 (0.81 -> 0.10 ms).
+// Measured (profiles/r02_exp_tail_forms.jsonl): D = 256 equal to tail_tma_kernel within 3 % at any occupancy - the pass is bound
+// by the SM's L1TEX data pipe (every phase goes through shared memory), see DESIGN.md section 3.3.
 #include "vqb_internal.h"
 #include "vqb_ptx.cuh"
 
@@ -380,15 +383,14 @@ static cudaError_t launch_t(const CUtensorMap& map, const float* codebook, const
 
 bool tail2_supports(int D) { return D % 32 == 0 && (D / 32 <= 4 || D == 192 || D == 256); }
 
-// Tile size: 16 frames for D >= 192 (two more blocks per SM; VQB_TAIL_FORM=232 forces 32, 216 forces 16), 32 below.
+// Tile size: 32 frames (VQB_TAIL_FORM=216 selects 16-frame tiles: 5 blocks per SM instead of 3 at D = 256, measured 8 % SLOWER -
+// the pass is bound by the L1TEX data pipe, not by latency).
 cudaError_t launch_tail2(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K, const int* idx32,
                          const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out, int* counts, float* resid,
                          double* part, int n_partials, WsMeta* meta, float* resid_rep, int n_rep, size_t rep_stride, int form,
                          cudaStream_t s) {
     (void)K;
-    int tf = D >= 192 ? 16 : 32;
-    if (form == 232) tf = 32;
-    if (form == 216) tf = 16;
+    const int tf = form == 216 ? 16 : 32;
     CUtensorMap map;
     if (make_latent_map(&map, z, (uint64_t)B, (uint64_t)D, (uint64_t)W, (uint32_t)tf, (uint32_t)D) != 0) return cudaErrorInvalidValue;
     const int tiles_per_item = (int)((W + tf - 1) / tf);
