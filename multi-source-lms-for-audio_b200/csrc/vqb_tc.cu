@@ -311,6 +311,41 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, f
     }
 }
 
+// ---- small codebooks: per-WARP capture ring in shared memory ---------------------------------------------------------------
+// With K <= 2048 every 32-frame x 32-code slab of a warp holds an event on average (ncu at K = 1024: the per-thread stack path
+// above ran on 93 % of the slabs and its resolution was a quarter of the kernel).  The ring form makes the slow path short and the
+// resolution parallel: a lane whose slab maximum beats its threshold stores the slab RAW - 32 accumulators + (maximum, first code |
+// lane) - into the next free entry of its warp's ring (slot = ballot prefix, no atomics); after the sweep the ring's entries are
+// dealt one per lane, whatever frame they belong to, and filtered against that frame's final maximum.
+constexpr int RING_ENTRY = 144;    // bytes: 32 x 4 raw + 8 header, rows stay 16-byte aligned (and conflict-free for 16-byte reads)
+__device__ __forceinline__ void scan_slab_ring(const uint32_t (&r)[32], int code0, float hband, float& thr, int* smax, uint32_t ring_u,
+                                               int ring_cap, int& ring_n, bool& lost, int lane) {
+    thr = fmaxf(thr, ord2f(*reinterpret_cast<volatile int*>(smax)) - hband);
+    const float sm = slab_max32(r);
+    const bool hit = sm > thr;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        if (hit) {
+            const int pos = ring_n + __popc(m & ((1u << lane) - 1u));
+            if (pos < ring_cap) {
+                const uint32_t a = ring_u + (uint32_t)pos * RING_ENTRY;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16 * q), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]),
+                                 "r"(r[4 * q + 3])
+                                 : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 128), "r"(__float_as_uint(sm)), "r"((uint32_t)code0 | ((uint32_t)lane << 16))
+                             : "memory");
+            } else {
+                lost = true;                       // ring full: this frame goes to the exact search
+            }
+            thr = fmaxf(thr, sm - hband);
+            atomicMax(smax, f2ord(sm));
+        }
+        ring_n += __popc(m);
+    }
+}
+
 __device__ __forceinline__ void dump_slab(const uint32_t (&r)[32], int code0, int K, float* row_out) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -461,7 +496,9 @@ __device__ __forceinline__ void tail_stream(const unsigned char* sTx, uint32_t b
 //               128-byte-swizzled TMA boxes [D dims][32 frames] (an MN-major operand: no conversion, no copy); the codebook tiles are
 //               fp32 boxes [codes][32 dims].  Warp 19 only loads A tiles, warp 18 measures |x| and |x - tf32(x)| of the landed tile
 //               (guard band) and then releases it to the MMA issuer.  tf32 runs at half the bf16 tensor rate, the band is ~3x tighter.
-template <bool kTwo, bool kFuse, bool kTail, bool kTf32 = false>
+// kRing = true (needs kFuse, no kTail): the epilogue captures whole slabs into per-warp shared-memory rings (scan_slab_ring) instead
+//               of 8-code chunks into per-thread stacks; chosen by tc_plan for small codebooks when shared memory leaves room.
+template <bool kTwo, bool kFuse, bool kTail, bool kTf32 = false, bool kRing = false>
 __global__ void __launch_bounds__(kTail ? NUM_THREADS_TAIL : NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
                  const __grid_constant__ CUtensorMap tmap_eh, const __grid_constant__ CUtensorMap tmap_xt, const __nv_bfloat16* __restrict__ eh, int64_t W, int tiles_per_item, int D,
@@ -469,9 +506,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
-                 const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots) {
+                 const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots, const int ring_cap) {
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     static_assert(!kTf32 || (kFuse && !kTail), "tf32 reads the fp32 latents in place; no fused tail");
+    static_assert(!kRing || (kFuse && !kTail), "the ring epilogue reads the guard bands from shared memory; no fused tail");
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t a_slot_bytes = kTf32 ? (uint32_t)BM * (uint32_t)D * 4u : (uint32_t)A_CHUNK_BYTES;   // tf32: a_slots whole fp32 tiles
     unsigned char* sA = smem;                                            // a_slots x 16 KiB (tf32: a_slots x 128 D x 4 bytes)
@@ -487,7 +525,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
     uint32_t* sEv = reinterpret_cast<uint32_t*>(sCnt + 3 * BM);          // [512][ev_sm] shared-memory part of the event stacks
     // fused tail: the shortlists of two frame tiles (the epilogue fills one while the tail warps consume the other)
-    uint16_t* sCand = reinterpret_cast<uint16_t*>(sEv + (size_t)EPI_THREADS * ev_sm * EV_WORDS);   // [2][128][kCandFill] codes
+    // ring epilogue: [16 warps][ring_cap] capture entries, then the tile's shortlists [128][kCandMax] (written out as 32-byte rows)
+    unsigned char* sRing = reinterpret_cast<unsigned char*>(sEv + (size_t)EPI_THREADS * ev_sm * EV_WORDS);
+    uint16_t* sList = reinterpret_cast<uint16_t*>(sRing + (kRing ? (size_t)EPI_WARPS * ring_cap * RING_ENTRY : 0));
+    uint16_t* sCand = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(sList) + (kRing ? BM * kCandMax * 2 : 0));   // [2][128][kCandFill] codes
     uint8_t* sCandCnt = reinterpret_cast<uint8_t*>(sCand + (kTail ? 2 * BM * kCandFill : 0));   // [2][128] 0 = not for the tail
     float2* sPair = reinterpret_cast<float2*>(sCandCnt + (kTail ? 2 * BM : 0));                  // [4][32] (distance, code) hand-back
     unsigned char* sTx = reinterpret_cast<unsigned char*>(sPair + (kTail ? TAIL_WARPS * 32 + 16 : 0));   // (+128 B of per-warp totals) TX_SLOTS x 4 KiB latent boxes
@@ -1016,6 +1057,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         ev.n = 0;
         if (colq == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; sCnt[2 * BM + row_in_tile] = f2ord(-INFINITY); }
         int* smax = sCnt + 2 * BM + row_in_tile;
+        unsigned char* ring = sRing + (size_t)ew * (kRing ? ring_cap : 0) * RING_ENTRY;   // this warp's capture ring
+        const uint32_t ring_u = smem_u32(ring);
+        int ring_n = 0;
+        bool ring_lost = false;
         asm volatile("bar.sync 1, 512;" ::: "memory");
         uint32_t n_it = 0;
         for (int rd = 0; rd < rounds; ++rd) {
@@ -1060,18 +1105,82 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 for (int sb = 0; sb < COLS_PER_WARP / 32; ++sb) {
                     tmem_ld32(taddr + sb * 32, ra);
                     tmem_ld_wait(ra);
+                    if (sb == COLS_PER_WARP / 32 - 1) {
+                        // the last slab of this accumulator stage is in registers: hand the stage back BEFORE scanning it - the
+                        // hand-off round trip (release -> MMA issue -> commit -> wake-up -> read-out), not the scan, is what a
+                        // 700-cycle tile at D = 64 waits for
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (kTwo && crank != 0) mbar_arrive_remote(smem_u32(&bars->tmem_empty[as]), 0);   // the leader issues the pair's MMAs
+                            else mbar_arrive(smem_u32(&bars->tmem_empty[as]));
+                        }
+                    }
                     if (scores_dbg) {
                         if (row < N) dump_slab(ra, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
+                    } else if (kRing) {
+                        scan_slab_ring(ra, code0 + sb * 32, hband, thr, smax, ring_u, ring_cap, ring_n, ring_lost, lane);
                     } else {
                         scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev, smax);
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (kTwo && crank != 0) mbar_arrive_remote(smem_u32(&bars->tmem_empty[as]), 0);   // the leader issues the pair's MMAs
-                    else mbar_arrive(smem_u32(&bars->tmem_empty[as]));
+            }
+            if (kRing && !scores_dbg) {
+                // ---- ring form: the four warps that share these 32 frames meet on their own named barrier (the other lane quarters
+                // run on), then every warp deals ITS ring's entries one per lane and filters them against the final maximum of the
+                // frame each entry belongs to; the shortlists collect in shared memory and leave as 32-byte rows
+                sMin[colq * BM + row_in_tile] = thr + hband;
+                if (ring_lost || !(band < INFINITY)) sCnt[BM + row_in_tile] = 1;
+                asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
+                const int n_ev = ring_n < ring_cap ? ring_n : ring_cap;
+                for (int e = lane; e < n_ev; e += 32) {
+                    const unsigned char* en = ring + (size_t)e * RING_ENTRY;
+                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 128);
+                    const int r = quarter * 32 + (int)(hd.y >> 16);
+                    const float gmax = fmaxf(fmaxf(sMin[r], sMin[BM + r]), fmaxf(sMin[2 * BM + r], sMin[3 * BM + r]));
+                    const float cutoff = gmax - 0.5f * sBand[(rd & 3) * BM + r];
+                    if (__uint_as_float(hd.x) >= cutoff) {
+                        const int k0 = (int)(hd.y & 0xFFFFu);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(en + 16 * q);
+                            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                if (__uint_as_float(av[c]) >= cutoff) {
+                                    const int pos = atomicAdd(&sCnt[r], 1);
+                                    if (pos < kCandFill) sList[r * kCandMax + pos] = (uint16_t)(k0 + 4 * q + c);
+                                    else sCnt[BM + r] = 1;
+                                }
+                            }
+                        }
+                    }
                 }
+                ring_n = 0;
+                ring_lost = false;
+                if (colq == 0) *smax = f2ord(-INFINITY);   // nobody reads the pooled maximum between the two barriers
+                asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
+                if (colq == 0) {
+                    if (row < N) {
+                        const int cnt = sCnt[row_in_tile];
+                        if (force_fallback || cnt == 0 || sCnt[BM + row_in_tile]) {
+                            cand_cnt[row] = kCandFinal;          // the exact search fills in the final code
+                            const int fp = atomicAdd(&meta->fallback_count, 1);
+                            fallback_rows[fp] = (int)row;
+                            best64[fp] = ~0ull;
+                            atomicAdd(&meta->fallback_total, 1ull);
+                        } else {
+                            cand_cnt[row] = (uint8_t)(cnt < kCandFill ? cnt : kCandFill);
+                            const uint4* src = reinterpret_cast<const uint4*>(sList + row_in_tile * kCandMax);
+                            uint4* dst = reinterpret_cast<uint4*>(cand_idx + (size_t)row * kCandMax);
+                            dst[0] = src[0];
+                            dst[1] = src[1];
+                        }
+                    }
+                    sCnt[row_in_tile] = 0;
+                    sCnt[BM + row_in_tile] = 0;
+                }
+                continue;
             }
             // ---- resolve this thread's chunks against the frame's final maximum and publish the shortlist
             sMin[colq * BM + row_in_tile] = thr + hband;                     // running maximum of this column quarter
@@ -1250,11 +1359,12 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 // (tc_can_fuse, tc_fused_tail_fits).
 struct TcPlan {
     bool ok, two;
-    int cs, a_slots, b_stages, ev_sm, eh_slots;
+    int cs, a_slots, b_stages, ev_sm, eh_slots, ring_cap;
     size_t smem;
 };
 
-static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int D, bool tf32 = false) {
+// K_pad = 0: the caller only asks whether a plan exists (the ring epilogue is an optimisation, never a requirement)
+static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int D, bool tf32 = false, int K_pad = 0) {
     using namespace tc;
     TcPlan p{};
     const int num_kb = tf32 ? (D + 31) / 32 : (D + BK - 1) / BK;
@@ -1301,7 +1411,23 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
         if (p.ev_sm > 3) p.ev_sm = 3;
     }
     if (const int v = env_get(ENV_TC_EVSM, -1); v >= 0 && v < p.ev_sm) p.ev_sm = v;   // experiments
-    const size_t fixed_ev = fixed + (size_t)p.ev_sm * ev_entry_bytes;
+    // Ring epilogue (small codebooks, K <= 2048): per-warp capture rings + the tile's shortlists instead of the shared-memory part of
+    // the per-thread stacks, when four codebook stages leave room for at least 24 entries per warp (about 22 events per warp and frame
+    // tile at K = 1024, 16 at K = 512; a full ring only sends the frame to the exact search).  OPT-IN (VQB_TC_EPI=1): measured at cfg 2
+    // it executes 40 % fewer instructions and takes the SAME time - the kernel is bound by the accumulator hand-off round trip, not
+    // by the epilogue's instruction count - and its rings overflow on 0.6 - 3 % of the frames.
+    p.ring_cap = 0;
+    size_t ring_bytes = 0;
+    if (fuse && !with_tail && !dbg && K_pad > 0 && K_pad <= 2048 && env_get(ENV_TC_EPI, 0) == 1) {
+        const size_t list_bytes = (size_t)BM * kCandMax * 2;
+        const size_t base = fixed + 4 * stage_bytes + list_bytes;
+        if (227 * 1024 > base) {
+            int cap = (int)((227 * 1024 - base) / ((size_t)EPI_WARPS * RING_ENTRY));
+            if (cap > 64) cap = 64;
+            if (cap >= 24) { p.ring_cap = cap; p.ev_sm = 0; ring_bytes = (size_t)EPI_WARPS * cap * RING_ENTRY + list_bytes; }
+        }
+    }
+    const size_t fixed_ev = fixed + (size_t)p.ev_sm * ev_entry_bytes + ring_bytes;
     p.b_stages = fixed_ev < 227 * 1024 ? (int)((227 * 1024 - fixed_ev) / stage_bytes) : 0;
     if (p.b_stages > (p.two ? 8 : 4)) p.b_stages = p.two ? 8 : 4;
     if (const int v = env_get(ENV_TC_STAGES, 0); v >= 2 && v < p.b_stages) p.b_stages = v;   // experiments
@@ -1396,7 +1522,8 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     if (sms > kTcMaxCtas) sms = kTcMaxCtas;
     const int num_m_tiles = fuse ? B * tiles_per_item : (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
-    const TcPlan plan = tc_plan(fuse, with_tail, scores_dbg != nullptr, num_m_tiles, D, tf32);
+    const TcPlan plan = tc_plan(fuse, with_tail, scores_dbg != nullptr, num_m_tiles, D, tf32, K_pad);
+    const bool ring = plan.ring_cap > 0;
     if (!plan.ok) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
     const bool two = plan.two;
     const int cs = plan.cs, a_slots = plan.a_slots, b_stages = plan.b_stages, ev_sm = plan.ev_sm;
@@ -1412,6 +1539,10 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<false, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_search_kernel<true, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_search_kernel)");
         attr_done = true;
     }
@@ -1442,8 +1573,12 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
 #define VQB_TC_LAUNCH(TWO, FUSE, TAIL, ...)                                                                                                  \
     le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL, ##__VA_ARGS__>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
                             num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \
-                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, ev_sm, l2_once, plan.eh_slots)
-    if (tf32 && two) VQB_TC_LAUNCH(true, true, false, true);
+                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, ev_sm, l2_once, plan.eh_slots, plan.ring_cap)
+    if (ring && tf32 && two) VQB_TC_LAUNCH(true, true, false, true, true);
+    else if (ring && tf32) VQB_TC_LAUNCH(false, true, false, true, true);
+    else if (ring && two) VQB_TC_LAUNCH(true, true, false, false, true);
+    else if (ring) VQB_TC_LAUNCH(false, true, false, false, true);
+    else if (tf32 && two) VQB_TC_LAUNCH(true, true, false, true);
     else if (tf32) VQB_TC_LAUNCH(false, true, false, true);
     else if (two && with_tail) VQB_TC_LAUNCH(true, true, true);
     else if (with_tail) VQB_TC_LAUNCH(false, true, true);

@@ -52,6 +52,28 @@ def main():
         insts[src] += n
     ts, ti = sum(samples.values()), sum(insts.values())
     cache = {}
+    if "--waits" in sys.argv:
+        # inlined helpers (vqb_ptx.cuh: the mbarrier wait loop) hide which ROLE waits: attribute their samples to the next
+        # instruction that comes from another file, i.e. to the code that was waiting
+        ctx_s, ctx_i = collections.Counter(), collections.Counter()
+        srcs = [d[1] for d in dis]
+        for i, ((_, src), (_, n, smp)) in enumerate(zip(dis, sass)):
+            if src and src[0] == "vqb_ptx.cuh":
+                j = i
+                while j < len(srcs) and (srcs[j] is None or srcs[j][0] == "vqb_ptx.cuh"):
+                    j += 1
+                key = srcs[j] if j < len(srcs) else None
+                ctx_s[key] += smp
+                ctx_i[key] += n
+        print("-- vqb_ptx.cuh samples by the code that follows the wait:")
+        for key, v in ctx_s.most_common(14):
+            text = ""
+            if key:
+                path = os.path.join(ROOT, "multi-source-lms-for-audio_b200", "csrc", key[0])
+                if os.path.exists(path):
+                    cache.setdefault(path, open(path).read().splitlines())
+                    text = cache[path][key[1] - 1].strip()[:110]
+            print(f"   before {key[0] if key else '?'}:{key[1] if key else 0:<6d} samples {100 * v / ts:5.1f} %  instructions {100 * ctx_i[key] / ti:5.1f} %  {text}")
     print(f"{rep}: {ts} samples, {ti} warp instructions")
     for (src, s) in samples.most_common(top):
         text = ""
