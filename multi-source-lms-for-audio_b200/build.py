@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libvqb_b200.so")
-SOURCES = ["vqb_api.cu", "vqb_kernels.cu", "vqb_tail2.cu", "vqb_tc.cu", "vqb_comm.cu", "vqb_host.cu"]
+SOURCES = ["vqb_api.cu", "vqb_kernels.cu", "vqb_tail2.cu", "vqb_tail3.cu", "vqb_tc.cu", "vqb_comm.cu", "vqb_host.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]

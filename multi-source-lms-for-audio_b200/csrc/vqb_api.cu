@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 static const char* const kEnvNames[ENV_COUNT] = {
     "VQB_TC_MODE", "VQB_TC_CLUSTER", "VQB_TC_FUSE", "VQB_TC_STAGES", "VQB_TC_ASLOTS", "VQB_TC_EVSM", "VQB_TC_EHSLOTS", "VQB_TC_TAIL",
     "VQB_TMA_PROMO", "VQB_TILE_LDG", "VQB_RESID_REPLICAS", "VQB_L2_ONCE", "VQB_TAIL_VARIANT", "VQB_TAIL_TMA", "VQB_TAIL_EXACT",
-    "VQB_DX_TILES", "VQB_TC_EPI", "VQB_TAIL_FORM"};
+    "VQB_DX_TILES", "VQB_TC_EPI", "VQB_TAIL_FORM", "VQB_TAIL_LPF"};
 static int g_env_val[ENV_COUNT];
 static bool g_env_set[ENV_COUNT];
 static std::atomic<bool> g_env_loaded{false};
@@ -70,7 +70,8 @@ WsLayout ws_layout(int64_t N, int K, int D, int flags, bool need_xb, int ev_ctas
     L.e2 = take((size_t)L.k_pad * 4);
     L.counts = take((size_t)K * 4);
     L.sse_partials = take((size_t)L.n_partials * 8);
-    L.resid_rep = (flags & VQB_WANT_RESID) ? take((size_t)(kResidReplicasMax - 1) * K * D * 4) : 0;
+    L.resid_rep = (flags & VQB_WANT_RESID) ? take((size_t)kResidReplicasMax * K * D * 4) : 0;
+    L.ep = (D % 32 == 0) ? take((size_t)K * D * 4) : 0;   // permuted fp32 codebook copy for tail3_kernel
     if (prec == VQB_PREC_FP32) {
         L.idx32 = take((size_t)N * 4);
         L.cand_cnt = L.cand_idx = L.fallback_rows = L.best64 = L.x2 = L.eb = L.eh = L.xb = L.ev = 0;
@@ -177,6 +178,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
     float* part = reinterpret_cast<float*>(ws + L.sse_partials);
     float* resid = (flags & VQB_WANT_RESID) ? stats_out + K : nullptr;
     float* resid_rep = resid ? reinterpret_cast<float*>(ws + L.resid_rep) : nullptr;
+    float* ep = (D % 32 == 0) ? reinterpret_cast<float*>(ws + L.ep) : nullptr;
 
     void* tprep = stage_timing_begin(s, VQB_STAGE_PREP);
     if (!accumulate) {
@@ -189,14 +191,14 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
 
     if (prec == VQB_PREC_FP32) {
         int* idx32 = reinterpret_cast<int*>(ws + L.idx32);
-        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, nullptr, nullptr, meta, s), "codebook_prep");
+        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, nullptr, nullptr, meta, s, false, ep, tail3_lpf(D)), "codebook_prep");
         stage_timing_end(tprep, s);
         void* t0 = stage_timing_begin(s, VQB_STAGE_SEARCH);
         VQB_CUDA(launch_exact_search(z, codebook, e2, B, D, W, K, nullptr, nullptr, idx32, nullptr, nullptr, nullptr, s), "exact_search");
         stage_timing_end(t0, s);
         void* t1 = stage_timing_begin(s, VQB_STAGE_TAIL);
         VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, idx32, nullptr, nullptr, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
-                             counts, resid, part, L.n_partials, meta, resid_rep, s), "tail");
+                             counts, resid, part, L.n_partials, meta, resid_rep, s, ep), "tail");
         stage_timing_end(t1, s);
     } else {
         uint8_t* cand_cnt = reinterpret_cast<uint8_t*>(ws + L.cand_cnt);
@@ -208,7 +210,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + L.xb);
         __nv_bfloat16* eh = reinterpret_cast<__nv_bfloat16*>(ws + L.eh);
         const bool tf32 = prec == VQB_PREC_TF32;
-        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, tf32 ? nullptr : eb, eh, meta, s, tf32), "codebook_prep");
+        VQB_CUDA(launch_codebook_prep(codebook, K, L.k_pad, D, e2, tf32 ? nullptr : eb, eh, meta, s, tf32, ep, tail3_lpf(D)), "codebook_prep");
         const bool fuse = tc_can_fuse(z, B, D, W, prec);
         // fused tail: the search kernel finishes the frames itself (index, quantized, statistics); only the frames it
         // sends to the exact search are finished by a small list kernel.  Otherwise the stand-alone tail kernel runs.
@@ -234,7 +236,7 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
             stage_timing_end(tfb, s);
             void* tt = stage_timing_begin(s, VQB_STAGE_TAIL);
             VQB_CUDA(launch_tail(z, codebook, e2, B, D, W, K, nullptr, cand_cnt, cand_idx, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr,
-                                 counts, resid, part, L.n_partials, meta, resid_rep, s), "tail");
+                                 counts, resid, part, L.n_partials, meta, resid_rep, s, ep), "tail");
             stage_timing_end(tt, s);
         }
     }

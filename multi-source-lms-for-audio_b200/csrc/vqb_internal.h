@@ -29,7 +29,7 @@ struct WsMeta {
 };
 
 struct WsLayout {
-    size_t meta, e2, counts, sse_partials, resid_rep, idx32, cand_cnt, cand_idx, fallback_rows, best64, x2, eb, eh, xb, ev, total;
+    size_t meta, e2, counts, sse_partials, resid_rep, ep, idx32, cand_cnt, cand_idx, fallback_rows, best64, x2, eb, eh, xb, ev, total;
     int    k_pad;
     int64_t n_pad;
     int    n_partials;
@@ -52,6 +52,7 @@ void  stage_timing_end(void* slot, cudaStream_t s);
 enum EnvKey {
     ENV_TC_MODE, ENV_TC_CLUSTER, ENV_TC_FUSE, ENV_TC_STAGES, ENV_TC_ASLOTS, ENV_TC_EVSM, ENV_TC_EHSLOTS, ENV_TC_TAIL, ENV_TMA_PROMO,
     ENV_TILE_LDG, ENV_RESID_REPLICAS, ENV_L2_ONCE, ENV_TAIL_VARIANT, ENV_TAIL_TMA, ENV_TAIL_EXACT, ENV_DX_TILES, ENV_TC_EPI, ENV_TAIL_FORM,
+    ENV_TAIL_LPF,
     ENV_COUNT
 };
 int  env_get(EnvKey key, int unset_value);         // value of the switch, or unset_value when it is not set / not enabled
@@ -106,8 +107,9 @@ struct TailArgs {
 
 // ---- launchers (vqb_kernels.cu) -------------------------------------------------------------------------------
 // tf32: the rounding-residual norms of the guard band are those of the tf32 operand (low 13 mantissa bits dropped); no bf16 copy
+// ep != nullptr (D % 32 == 0): also the permuted fp32 copy tail3_kernel gathers from (vqb_tail3.cu)
 cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb,
-                                 __nv_bfloat16* eh, WsMeta* meta, cudaStream_t s, bool tf32 = false);
+                                 __nv_bfloat16* eh, WsMeta* meta, cudaStream_t s, bool tf32 = false, float* ep = nullptr, int ep_lpf = 8);
 cudaError_t launch_latent_prep_bf16(const float* z, int B, int D, int64_t W, int64_t N_pad, __nv_bfloat16* xb, float* band,
                                     const WsMeta* meta, cudaStream_t s);
 // rows == nullptr: all N frames -> idx32[n]; else the frames listed in rows[0..*row_count) -> cand_cnt/cand_idx (count 1)
@@ -116,14 +118,30 @@ cudaError_t launch_exact_search(const float* z, const float* codebook, const flo
                                 unsigned long long* best64, cudaStream_t s);
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
-                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s);
+                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s,
+                        const float* ep = nullptr);   // ep: permuted codebook copy (enables tail3_kernel)
+// third form of the tail (vqb_tail3.cu): swizzled TMA box read and written in place, TMA store of `quantized`, no block barriers;
+// gathers from the permuted codebook copy `ep`, accumulates the residual sums in n_rep permuted workspace replicas and ADDS their
+// un-permuted sum to `resid`
+bool tail3_supports(int D);
+bool tail3_preferred(int D);   // the shapes where it measured faster than tail2_kernel
+int  tail3_lpf(int D);         // lanes per frame tail3_kernel uses at this D: decides the permutation below
+// Position, inside a codebook / residual row, of dim d in the layout tail3_kernel reads with `lpf` lanes per frame: lane sl owns the
+// dims whose d % 8 lies in [S sl, S sl + S), S = 8 / lpf; its m-th dim (m = S (d / 8) + d % 8 % S) sits at (m / 4) 4 lpf + 4 sl + m % 4
+__host__ __device__ __forceinline__ int tail3_perm_pos(int d, int lpf) {
+    const int S = 8 / lpf, r = d & 7, sl = r / S, m = (d >> 3) * S + r % S;
+    return (m >> 2) * 4 * lpf + sl * 4 + (m & 3);
+}
+cudaError_t launch_tail3(const float* z, const float* ep, const float* e2, int B, int D, int64_t W, int K, const int* idx32,
+                         const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out, int* counts, float* resid,
+                         double* part, int n_partials, WsMeta* meta, float* resid_rep, int n_rep, cudaStream_t s);
 // second form of the tail (vqb_tail2.cu): D = 32 J compile-time, dealt rescoring, 16-frame tiles for large D, run-length atomics
 bool tail2_supports(int D);
 cudaError_t launch_tail2(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K, const int* idx32,
                          const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out, int* counts, float* resid,
                          double* part, int n_partials, WsMeta* meta, float* resid_rep, int n_rep, size_t rep_stride, int form,
                          cudaStream_t s);
-int resid_replicas(int K, int D);   // copies of the residual sums the tail kernels spread their atomics over (workspace holds kResidReplicasMax - 1)
+int resid_replicas(int K, int D);   // copies of the residual sums the tail kernels spread their atomics over (workspace holds kResidReplicasMax: tail3_kernel keeps all of them there)
 // fused-tail mode: finishes the (rare) frames the exact fallback search decided - one warp per frame of the list
 cudaError_t launch_fallback_tail(const float* z, const float* codebook, int B, int D, int64_t W, int K, const int* rows,
                                  const int* row_count, const unsigned long long* best64, int64_t* idx_out, float* q_out, int* counts,

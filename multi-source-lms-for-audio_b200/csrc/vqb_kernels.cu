@@ -38,7 +38,8 @@ __device__ __forceinline__ bool code_ok(int64_t k, int K) { return (unsigned lon
 // guard band, non-finite flag.  Rows K..K_pad-1 get e2 = +inf (never shortlisted) and zero operands.
 __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restrict__ E, int K, int K_pad, int D,
                                                             float* __restrict__ e2, __nv_bfloat16* __restrict__ eb,
-                                                            __nv_bfloat16* __restrict__ eh, WsMeta* meta, bool tf32) {
+                                                            __nv_bfloat16* __restrict__ eh, WsMeta* meta, bool tf32,
+                                                            float* __restrict__ ep, int ep_lpf) {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= K_pad) return;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restr
     for (int d = lane; d < D; d += 32) {
         const float v = (k < K) ? E[(size_t)k * D + d] : 0.f;
         s = __fadd_rn(s, __fmul_rn(v, v));
+        if (ep && k < K) ep[(size_t)k * D + tail3_perm_pos(d, ep_lpf)] = v;   // permuted fp32 copy for tail3_kernel
         if (tf32) {                               // what kind::tf32 reads: the low 13 mantissa bits dropped.  |e| bounds |tf32(e)| also
             const float vt = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u), dv = v - vt;   // for a rounding unit (factor below)
             st = fmaf(v, v, st);
@@ -91,8 +93,8 @@ __global__ void __launch_bounds__(256) codebook_prep_kernel(const float* __restr
 }
 
 cudaError_t launch_codebook_prep(const float* codebook, int K, int K_pad, int D, float* e2, __nv_bfloat16* eb, __nv_bfloat16* eh,
-                                 WsMeta* meta, cudaStream_t s, bool tf32) {
-    codebook_prep_kernel<<<(K_pad + 7) / 8, 256, 0, s>>>(codebook, K, K_pad, D, e2, eb, eh, meta, tf32);
+                                 WsMeta* meta, cudaStream_t s, bool tf32, float* ep, int ep_lpf) {
+    codebook_prep_kernel<<<(K_pad + 7) / 8, 256, 0, s>>>(codebook, K, K_pad, D, e2, eb, eh, meta, tf32, (D % 32 == 0) ? ep : nullptr, ep_lpf);
     note_launch();
     return cudaGetLastError();
 }
@@ -1012,13 +1014,23 @@ static cudaError_t launch_tail_tma_t(const CUtensorMap& map, const float* codebo
 
 cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, int B, int D, int64_t W, int K,
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
-                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s) {
+                        int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s,
+                        const float* ep) {
     const int64_t N = (int64_t)B * W;
     cudaError_t e = cudaMemsetAsync(sse_partials, 0, (size_t)n_partials * sizeof(double), s);
     if (e != cudaSuccess) return e;
     double* part = reinterpret_cast<double*>(sse_partials);
     const size_t rep_stride = (size_t)K * D;
     int n_rep = (resid && resid_rep) ? resid_replicas(K, D) : 1;
+    const int form = env_get(ENV_TAIL_FORM, 3);     // 3 (default): tail3_kernel where it applies; 2 / 216 / 232: tail2_kernel; 0: round-1 kernels
+    if (((form == 3 && tail3_preferred(D)) || form == 300) && ep && tail_tma_enabled() && tail3_supports(D) && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
+        (!q_out || (reinterpret_cast<uintptr_t>(q_out) & 15) == 0)) {
+        // all n_rep residual-sum replicas live in the workspace (permuted layout); their un-permuted sum is added to `resid`
+        if (resid && (!resid_rep || (e = cudaMemsetAsync(resid_rep, 0, (size_t)n_rep * rep_stride * 4, s)) != cudaSuccess))
+            return resid_rep ? e : cudaErrorInvalidValue;
+        return launch_tail3(z, ep, e2, B, D, W, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta, resid_rep,
+                            n_rep, s);
+    }
     if (n_rep > 1 && (e = cudaMemsetAsync(resid_rep, 0, (size_t)(n_rep - 1) * rep_stride * 4, s)) != cudaSuccess) return e;
     auto fold = [&]() -> cudaError_t {            // sum the residual replicas into the caller's buffer
         if (n_rep <= 1) return cudaSuccess;
@@ -1027,7 +1039,6 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
         note_launch();
         return cudaGetLastError();
     };
-    const int form = env_get(ENV_TAIL_FORM, 2);     // 2 (default): tail2_kernel where it applies; 0: round-1 kernels; 216 / 232: tile size
     if (form != 0 && tail_tma_enabled() && tail2_supports(D) && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
         e = launch_tail2(z, codebook, e2, B, D, W, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta,
                          resid_rep, n_rep, rep_stride, form, s);

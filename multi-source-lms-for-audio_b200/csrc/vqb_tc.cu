@@ -253,25 +253,50 @@ constexpr int EV_CAP = 32;
 constexpr int EV_WORDS = 12;   // 8 accumulators, chunk minimum, chunk id, 2 pad
 
 struct EventStack {
-    uint32_t* base;   // this thread's EV_CAP x EV_WORDS words in global scratch; an entry = 8 accumulators, chunk maximum, chunk id
-    uint32_t* sbase;  // the first `sm` entries live in shared memory instead (when the tile pipeline leaves room: small D).  With a
-    int       sm;     // small codebook there are few codebook tiles per frame tile, and two dependent L2 round trips to the stack
-                      // at the end of EVERY frame tile were ~45 % of the kernel at K = 1024, D = 64
-    int       n;      // chunks appended for the current frame tile (may exceed EV_CAP: overflow)
-    __device__ __forceinline__ uint32_t* slot(int i) const { return (i < sm ? sbase : base) + i * EV_WORDS; }
+    uint32_t* base;   // third level: this thread's EV_CAP x EV_WORDS words in global (L2-resident) scratch
+    uint32_t* sbase;  // first level: the thread's own `sm` entries in shared memory (when the tile pipeline leaves room: small D)
+    int       sm;
+    int       n;      // entries in the thread's own shared-memory slots (<= sm)
+    int       ng;     // entries in the global stack (may exceed EV_CAP: overflow -> the frame goes to the exact search)
+    // second level: a pool of the WARP in shared memory (entries carry their lane).  With a small codebook there are few codebook
+    // tiles per frame tile, and the end-of-round resolution used to wait for two dependent L2 round trips whenever ONE thread of the
+    // block had more events than own slots (timeline at K = 1024: 2 300 + 1 600 cycles of a 12 100-cycle round); the threads of a warp
+    // rarely need more than a handful of extra entries between them.
+    uint32_t  pool_u, pool_cnt_u, pool_cap, lane;
+    __device__ __forceinline__ const uint32_t* own(int i) const { return sbase + i * EV_WORDS; }
+    __device__ __forceinline__ const uint32_t* glob(int i) const { return base + i * EV_WORDS; }
     __device__ __forceinline__ void push_if(bool p, float tmin, int chunk, const uint32_t* a) {
-        const bool q = p && n < EV_CAP;
-        uint32_t* dst = slot(n);
+        const bool q = p && n < sm;
+        const uint32_t dst = smem_u32(sbase) + (uint32_t)n * (EV_WORDS * 4);
         asm volatile(
             "{\n\t.reg .pred q;\n\t"
             "setp.ne.u32 q, %0, 0;\n\t"
-            "@q st.v4.u32 [%1], {%2, %3, %4, %5};\n\t"
-            "@q st.v4.u32 [%1+16], {%6, %7, %8, %9};\n\t"
-            "@q st.v2.u32 [%1+32], {%10, %11};\n\t}" ::"r"((uint32_t)q),
-            "l"(dst), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(__float_as_uint(tmin)),
+            "@q st.shared.v4.u32 [%1], {%2, %3, %4, %5};\n\t"
+            "@q st.shared.v4.u32 [%1+16], {%6, %7, %8, %9};\n\t"
+            "@q st.shared.v2.u32 [%1+32], {%10, %11};\n\t}" ::"r"((uint32_t)q),
+            "r"(dst), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(__float_as_uint(tmin)),
             "r"((uint32_t)chunk)
             : "memory");
-        n += p ? 1 : 0;
+        n += q ? 1 : 0;
+        if (p && !q) {                             // rare: own slots are full
+            uint32_t pos = pool_cap;
+            if (pool_cap) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(pool_cnt_u) : "memory");
+            if (pos < pool_cap) {
+                const uint32_t d = pool_u + pos * (EV_WORDS * 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d + 16), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d + 32), "r"(__float_as_uint(tmin)), "r"((uint32_t)chunk), "r"(lane), "r"(0u)
+                             : "memory");
+            } else {
+                if (ng < EV_CAP) {
+                    uint32_t* g = base + ng * EV_WORDS;
+                    *reinterpret_cast<uint4*>(g) = make_uint4(a[0], a[1], a[2], a[3]);
+                    *reinterpret_cast<uint4*>(g + 4) = make_uint4(a[4], a[5], a[6], a[7]);
+                    *reinterpret_cast<uint2*>(g + 8) = make_uint2(__float_as_uint(tmin), (uint32_t)chunk);
+                }
+                ng += 1;
+            }
+        }
     }
 };
 
@@ -311,38 +336,69 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, f
     }
 }
 
-// ---- small codebooks: per-WARP capture ring in shared memory ---------------------------------------------------------------
-// With K <= 2048 every 32-frame x 32-code slab of a warp holds an event on average (ncu at K = 1024: the per-thread stack path
-// above ran on 93 % of the slabs and its resolution was a quarter of the kernel).  The ring form makes the slow path short and the
-// resolution parallel: a lane whose slab maximum beats its threshold stores the slab RAW - 32 accumulators + (maximum, first code |
-// lane) - into the next free entry of its warp's ring (slot = ballot prefix, no atomics); after the sweep the ring's entries are
-// dealt one per lane, whatever frame they belong to, and filtered against that frame's final maximum.
-constexpr int RING_ENTRY = 144;    // bytes: 32 x 4 raw + 8 header, rows stay 16-byte aligned (and conflict-free for 16-byte reads)
-__device__ __forceinline__ void scan_slab_ring(const uint32_t (&r)[32], int code0, float hband, float& thr, int* smax, uint32_t ring_u,
-                                               int ring_cap, int& ring_n, bool& lost, int lane) {
-    thr = fmaxf(thr, ord2f(*reinterpret_cast<volatile int*>(smax)) - hband);
-    const float sm = slab_max32(r);
-    const bool hit = sm > thr;
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (m) {
-        if (hit) {
-            const int pos = ring_n + __popc(m & ((1u << lane) - 1u));
-            if (pos < ring_cap) {
-                const uint32_t a = ring_u + (uint32_t)pos * RING_ENTRY;
+// ---- small codebooks (K <= 1024): two epilogue groups + per-WARP chunk queues in shared memory ------------------------------------
+// What the hand-off timeline (scripts/trace_tc.py, profiles/r03_trace_cfg2_*.txt) showed for the per-thread stacks at K = 1024, D = 64:
+// a frame-tile round of 12 700 cycles = 4 tiles x ~1 600 (all 16 warps wait for the same accumulator, read it at the same time - the
+// TMEM read of a slab takes ~200 cycles under that contention - and then run ~100 dependent instructions per slab, four warps per
+// scheduler in lock-step) + 5 450 cycles of end-of-round resolution (two 512-thread barriers around dependent L2 round trips to the
+// stack entries that did not fit shared memory); the tensor core needs 640 cycles per tile.  This form
+//  * splits the 16 epilogue warps into two groups of 8, one per accumulator stage: group g reads every tile with n_it % 2 = g, four
+//    32-column slabs per warp, the load of slab s + 1 in flight behind the scan of slab s - the groups run out of phase, so TMEM reads
+//    and scans of different warps overlap, and a warp waits for an accumulator half as often;
+//  * appends events as 8-code chunks (raw accumulators, chunk maximum, chunk id | lane) to a queue of the WARP (slot by shared-memory
+//    atomic), so the end-of-round resolution is one pass in which the queue's entries are dealt one per lane - no per-thread stacks,
+//    nothing in global memory, barriers of the 128 threads that share 32 frames instead of all 512;
+//  * takes the group's first tile of a round twice (maximum first), and pools the running maximum of a frame's four threads through
+//    shared memory once per tile.
+constexpr int Q_ENTRY = 48;        // bytes: 8 raw accumulators, (chunk maximum, chunk id | lane << 16), 8 pad: 16-byte aligned rows
+constexpr int Q_LANE_CAP = 12;     // entries one lane may append per round: a frame that floods (adversarial code order) only loses itself
+__device__ __forceinline__ void scan_slab_q(const uint32_t (&r)[32], int chunk0, float hband, float& thr, float& mymax, int* smax, uint32_t q_u,
+                                            uint32_t q_cap, uint32_t& qn, int& mine, int lane) {
+    float t[4];
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16 * q), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]),
-                                 "r"(r[4 * q + 3])
-                                 : "memory");
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 128), "r"(__float_as_uint(sm)), "r"((uint32_t)code0 | ((uint32_t)lane << 16))
-                             : "memory");
-            } else {
-                lost = true;                       // ring full: this frame goes to the exact search
+    for (int g = 0; g < 4; ++g) {      // depth-3 trees (the chain form of slab_max32 is 16 dependent instructions)
+        const float m0 = fmaxf(fmaxf(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1])), __uint_as_float(r[g * 8 + 2]));
+        const float m1 = fmaxf(fmaxf(__uint_as_float(r[g * 8 + 3]), __uint_as_float(r[g * 8 + 4])), __uint_as_float(r[g * 8 + 5]));
+        t[g] = fmaxf(fmaxf(fmaxf(m0, m1), __uint_as_float(r[g * 8 + 6])), __uint_as_float(r[g * 8 + 7]));
+    }
+    const float m = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
+    const bool hit = m >= thr;
+    if (__any_sync(0xffffffffu, hit)) {
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            // queue slot by ballot prefix: no atomics, and the fill `qn` stays a warp-uniform register
+            const bool want = hit && t[g] >= thr;
+            const bool hg = want && mine < Q_LANE_CAP;
+            if (want && !hg) mine = Q_LANE_CAP + 1;      // flooded: this frame goes to the exact search, it takes no more slots
+            const unsigned mk = __ballot_sync(0xffffffffu, hg);
+            if (mk) {
+                if (hg) {
+                    const uint32_t pos = qn + (uint32_t)__popc(mk & lt);
+                    if (pos < q_cap) {
+                        const uint32_t a = q_u + pos * Q_ENTRY;
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r[g * 8 + 0]), "r"(r[g * 8 + 1]), "r"(r[g * 8 + 2]),
+                                     "r"(r[g * 8 + 3])
+                                     : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(r[g * 8 + 4]), "r"(r[g * 8 + 5]), "r"(r[g * 8 + 6]),
+                                     "r"(r[g * 8 + 7])
+                                     : "memory");
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 32), "r"(__float_as_uint(t[g])),
+                                     "r"((uint32_t)(chunk0 + g) | ((uint32_t)lane << 16))
+                                     : "memory");
+                    }
+                    mine += 1;
+                }
+                qn += (uint32_t)__popc(mk);              // may pass q_cap: the round then sends the warp's 32 frames to the exact search
             }
-            thr = fmaxf(thr, sm - hband);
-            atomicMax(smax, f2ord(sm));
         }
-        ring_n += __popc(m);
+        if (hit) {
+            thr = fmaxf(thr, m - hband);
+            if (m > mymax) {
+                mymax = m;
+                atomicMax(smax, f2ord(m));
+            }
+        }
     }
 }
 
@@ -480,6 +536,25 @@ __device__ __forceinline__ void tail_stream(const unsigned char* sTx, uint32_t b
     }
 }
 
+// ---------------------------------------------------------------------------------------------- trace (debug builds only)
+// -DVQB_TC_TRACE (scripts/build_trace.py -> libvqb_b200_trace.so, never the shipped library): one lane per role of CTA 0 / 1 writes
+// SM-clock timestamps of its hand-offs into a global buffer (vqb_debug_set_trace): the timeline that the per-line stall profile of
+// a warp-specialised kernel cannot show.  Record slot = [CTA][role][event][tile counter], value = bit 63 | clock low 32 bits.
+#ifdef VQB_TC_TRACE
+__device__ unsigned long long* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_cap = 0;      // records per CTA: 8 roles x 8 events x 1024 counters
+// the record base of this CTA is read ONCE per thread (VQB_TRACE_INIT): a device-global read per event would cost a memory round trip
+__device__ __forceinline__ void trace_ev(unsigned long long* base, int role, int event, unsigned int counter) {
+    if (base && counter < 1024u)                  // fire-and-forget store into the record's own slot: no atomics, no waiting
+        base[(size_t)(((role << 3) | event) << 10) + counter] = (1ull << 63) | (unsigned long long)(unsigned int)clock64();
+}
+#define VQB_TRACE_INIT() unsigned long long* const trace_base__ = (blockIdx.x < 2 && g_trace_buf) ? g_trace_buf + (size_t)blockIdx.x * g_trace_cap : nullptr
+#define VQB_TRACE(role, event, counter) trace_ev(trace_base__, role, event, counter)
+#else
+#define VQB_TRACE_INIT() ((void)0)
+#define VQB_TRACE(role, event, counter) ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------------------------- the kernel
 // kTwo = false: cta_group::1 MMAs, every CTA holds whole codebook tiles (optionally multicast inside a cluster).
 // kTwo = true : CTA pairs with cta_group::2 MMAs (M = 256 over the pair): each CTA holds its own 128 frames and HALF of every
@@ -496,8 +571,8 @@ __device__ __forceinline__ void tail_stream(const unsigned char* sTx, uint32_t b
 //               128-byte-swizzled TMA boxes [D dims][32 frames] (an MN-major operand: no conversion, no copy); the codebook tiles are
 //               fp32 boxes [codes][32 dims].  Warp 19 only loads A tiles, warp 18 measures |x| and |x - tf32(x)| of the landed tile
 //               (guard band) and then releases it to the MMA issuer.  tf32 runs at half the bf16 tensor rate, the band is ~3x tighter.
-// kRing = true (needs kFuse, no kTail): the epilogue captures whole slabs into per-warp shared-memory rings (scan_slab_ring) instead
-//               of 8-code chunks into per-thread stacks; chosen by tc_plan for small codebooks when shared memory leaves room.
+// kRing = true (needs kFuse, no kTail): the grouped epilogue with per-warp chunk queues (scan_slab_q) instead of per-thread stacks;
+//               chosen by tc_plan for small codebooks (K <= 1024).
 template <bool kTwo, bool kFuse, bool kTail, bool kTf32 = false, bool kRing = false>
 __global__ void __launch_bounds__(kTail ? NUM_THREADS_TAIL : NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
@@ -507,9 +582,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
                  const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots, const int ring_cap) {
+    VQB_TRACE_INIT();
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     static_assert(!kTf32 || (kFuse && !kTail), "tf32 reads the fp32 latents in place; no fused tail");
-    static_assert(!kRing || (kFuse && !kTail), "the ring epilogue reads the guard bands from shared memory; no fused tail");
+    static_assert(!kRing || (kFuse && !kTail), "the grouped epilogue reads the guard bands from shared memory; no fused tail");
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t a_slot_bytes = kTf32 ? (uint32_t)BM * (uint32_t)D * 4u : (uint32_t)A_CHUNK_BYTES;   // tf32: a_slots whole fp32 tiles
     unsigned char* sA = smem;                                            // a_slots x 16 KiB (tf32: a_slots x 128 D x 4 bytes)
@@ -525,10 +601,12 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
     uint32_t* sEv = reinterpret_cast<uint32_t*>(sCnt + 3 * BM);          // [512][ev_sm] shared-memory part of the event stacks
     // fused tail: the shortlists of two frame tiles (the epilogue fills one while the tail warps consume the other)
-    // ring epilogue: [16 warps][ring_cap] capture entries, then the tile's shortlists [128][kCandMax] (written out as 32-byte rows)
+    // grouped epilogue: [16 warps][ring_cap] queue entries, then the tile's shortlists [128][kCandMax] (written out as 32-byte rows)
+    // per-thread stacks: [16 warps][ring_cap] overflow pool entries of the warps (same 48-byte entries)
     unsigned char* sRing = reinterpret_cast<unsigned char*>(sEv + (size_t)EPI_THREADS * ev_sm * EV_WORDS);
-    uint16_t* sList = reinterpret_cast<uint16_t*>(sRing + (kRing ? (size_t)EPI_WARPS * ring_cap * RING_ENTRY : 0));
-    uint16_t* sCand = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(sList) + (kRing ? BM * kCandMax * 2 : 0));   // [2][128][kCandFill] codes
+    uint16_t* sList = reinterpret_cast<uint16_t*>(sRing + (size_t)EPI_WARPS * ring_cap * Q_ENTRY);
+    uint32_t* sPoolCnt = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(sList) + (kRing ? BM * kCandMax * 2 : 0));   // [16] pool fills
+    uint16_t* sCand = reinterpret_cast<uint16_t*>(sPoolCnt + 2 * EPI_WARPS);   // (128 bytes: what follows keeps its alignment) [2][128][kCandFill] codes
     uint8_t* sCandCnt = reinterpret_cast<uint8_t*>(sCand + (kTail ? 2 * BM * kCandFill : 0));   // [2][128] 0 = not for the tail
     float2* sPair = reinterpret_cast<float2*>(sCandCnt + (kTail ? 2 * BM : 0));                  // [4][32] (distance, code) hand-back
     unsigned char* sTx = reinterpret_cast<unsigned char*>(sPair + (kTail ? TAIL_WARPS * 32 + 16 : 0));   // (+128 B of per-warp totals) TX_SLOTS x 4 KiB latent boxes
@@ -584,7 +662,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->tmem_full[i]), 1);
-            mbar_init(smem_u32(&bars->tmem_empty[i]), (kTwo ? 2 : 1) * EPI_THREADS / 32);   // 2-CTA: both CTAs' epilogues report to the leader
+            // 2-CTA: both CTAs' epilogues report to the leader; grouped epilogue: only the 8 warps of a stage's group read it
+            mbar_init(smem_u32(&bars->tmem_empty[i]), (kTwo ? 2 : 1) * (kRing ? EPI_WARPS / 2 : EPI_WARPS));
         }
         fence_barrier_init();
     }
@@ -679,7 +758,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t bar_tfull = smem_u32(&bars->tmem_full[0]), bar_tempty = smem_u32(&bars->tmem_empty[0]);
         for (int rd = 0; rd < rounds; ++rd) {
             for (int nt = 0; nt < num_n_tiles; ++nt) {
+                if (lane == 0) VQB_TRACE(1, 0, rd * num_n_tiles + nt);        // MMA: about to wait for the accumulator stage
                 mbar_wait(bar_tempty + as * 8, t_ph ^ 1);
+                if (lane == 0) VQB_TRACE(1, 1, rd * num_n_tiles + nt);        // MMA: stage free
                 const uint32_t tmem_d = tmem_base + as * BN;
                 const bool last_nt = nt == num_n_tiles - 1;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -715,7 +796,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     uint32_t slot = a_slot0 + kb, a_phk = a_ph;
                     if (slot >= (uint32_t)a_slots) { slot -= a_slots; a_phk ^= 1; }
                     if (nt == 0) mbar_wait(bar_afull + slot * 8, a_phk);
+                    if (lane == 0 && kb == 0) VQB_TRACE(1, 2, rd * num_n_tiles + nt);   // MMA: A chunk 0 ready
                     mbar_wait(bar_bfull + b_st * 8, b_ph);
+                    if (lane == 0 && kb == 0) VQB_TRACE(1, 3, rd * num_n_tiles + nt);   // MMA: codebook stage 0 ready
                     tc_fence_after();
                     if (elect_one()) {
                         // descriptors address shared memory in 16-byte units: +1024 per 16 KiB A chunk, +2048 per 32 KiB B stage,
@@ -744,6 +827,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
                 // the bias K step: acc -= |e_k|^2 / 2, then hand the accumulator to the epilogue
                 mbar_wait(bar_efull + es * 8, e_ph);
+                if (lane == 0) VQB_TRACE(1, 4, rd * num_n_tiles + nt);        // MMA: bias operand ready, tile about to be committed
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t eh_u = sEH_u + es * kEhBytes;
@@ -927,6 +1011,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (lane == 0) {
                     if (kTwo && crank != 0) mbar_arrive_remote(bar_afull + slot * 8, 0);
                     else mbar_arrive(bar_afull + slot * 8);
+                    VQB_TRACE(warp == CONVERT_WARP ? 2 : 3, 0, rd * num_kb + kb);   // converter: A chunk published
                 }
             }
             a_slot0 += num_kb;
@@ -1041,6 +1126,148 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             atomicAdd(&meta->rescored, (unsigned long long)(c[0] + c[2] + c[4] + c[6]));
             atomicAdd(&meta->shortlisted, (unsigned long long)(c[1] + c[3] + c[5] + c[7]));
         }
+    } else if (kRing && warp < EPI_WARPS) {
+        // ================================================================ grouped epilogue (small codebooks)
+        const int ew = warp - EPI_WARP0;
+        const uint32_t grp = (uint32_t)ew >> 3;   // the accumulator stage this warp reads: tiles with n_it % 2 == grp
+        const int quarter = warp & 3;             // TMEM lanes this warp may touch: 32*quarter .. +31
+        const int half = (ew >> 2) & 1;           // columns [128 half, 128 half + 128) of every tile: four 32-column slabs
+        const int slot4 = ew >> 2;                // which of the four threads of a frame this one is
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
+        const bool force_fallback = meta->cb_nonfinite != 0;
+        int* smax = sCnt + 2 * BM + row_in_tile;  // pooled running maximum of the frame (ordered int)
+        const uint32_t q_u = smem_u32(sRing + (size_t)ew * ring_cap * Q_ENTRY);
+        if (slot4 == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; *smax = f2ord(-INFINITY); }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const bool tr = lane == 0 && (ew == 0 || ew == 8);   // trace: first warp of each group
+        const int trole = 4 + (ew != 0);
+        (void)tr; (void)trole;
+        uint32_t n_it = 0;
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
+            const int b = mt / tiles_per_item;
+            const int64_t w = (int64_t)(mt - b * tiles_per_item) * BM + row_in_tile;
+            const int64_t row = (mt < num_m_tiles && w < W) ? (int64_t)b * W + w : N;   // global frame index, or N: no frame
+            float band = 0.f, hband = 0.f, thr = -INFINITY, mymax = -INFINITY;
+            bool first = true;
+            uint32_t qn = 0;                      // fill of this warp's queue (warp-uniform)
+            int mine = 0;                         // entries this lane appended
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
+                if ((n_it & 1u) != grp) continue;
+                const uint32_t ph = (n_it >> 1) & 1u;
+                if (tr) VQB_TRACE(trole, 0, n_it);
+                mbar_wait(smem_u32(&bars->tmem_full[grp]), ph);
+                tc_fence_after();
+                if (tr) VQB_TRACE(trole, 1, n_it);
+                const uint32_t taddr = tmem_base + t_lane + grp * BN + (uint32_t)half * 128u;
+                const int chunk0 = (nt * BN + half * 128) >> 3;
+                uint32_t ra[32], rb[32];
+                if (first) {                      // the converter published this tile's bands before the first MMA could start
+                    band = sBand[(rd & 3) * BM + row_in_tile];
+                    hband = 0.5f * band;          // the band in accumulator units (acc = -score / 2)
+                    // the group's first tile of the round: its maximum first (the accumulator stays in TMEM), then the scan
+                    float pre = -INFINITY;
+#pragma unroll
+                    for (int sb = 0; sb < 4; ++sb) {
+                        tmem_ld32(taddr + sb * 32, ra);
+                        tmem_ld_wait(ra);
+                        pre = fmaxf(pre, slab_max32(ra));
+                    }
+                    mymax = pre;
+                    thr = pre - hband;
+                    atomicMax(smax, f2ord(pre));
+                    first = false;
+                }
+                thr = fmaxf(thr, ord2f(*reinterpret_cast<volatile int*>(smax)) - hband);   // what the frame's other threads have seen
+                // four slabs, the load of the next one in flight behind the scan of the current one
+                tmem_ld32(taddr, ra);
+                tmem_ld_wait(ra);
+                tmem_ld32(taddr + 32, rb);
+                if (tr) VQB_TRACE(6 + (ew != 0), 0, n_it);
+                scan_slab_q(ra, chunk0, hband, thr, mymax, smax, q_u, (uint32_t)ring_cap, qn, mine, lane);
+                tmem_ld_wait(rb);
+                tmem_ld32(taddr + 64, ra);
+                if (tr) VQB_TRACE(6 + (ew != 0), 1, n_it);
+                scan_slab_q(rb, chunk0 + 4, hband, thr, mymax, smax, q_u, (uint32_t)ring_cap, qn, mine, lane);
+                tmem_ld_wait(ra);
+                tmem_ld32(taddr + 96, rb);
+                if (tr) VQB_TRACE(6 + (ew != 0), 2, n_it);
+                scan_slab_q(ra, chunk0 + 8, hband, thr, mymax, smax, q_u, (uint32_t)ring_cap, qn, mine, lane);
+                tmem_ld_wait(rb);
+                // the last slab of this accumulator stage is in registers: hand the stage back before scanning it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (kTwo && crank != 0) mbar_arrive_remote(smem_u32(&bars->tmem_empty[grp]), 0);   // the leader issues the pair's MMAs
+                    else mbar_arrive(smem_u32(&bars->tmem_empty[grp]));
+                }
+                if (tr) VQB_TRACE(trole, 2, n_it);
+                scan_slab_q(rb, chunk0 + 12, hband, thr, mymax, smax, q_u, (uint32_t)ring_cap, qn, mine, lane);
+                if (tr) VQB_TRACE(6 + (ew != 0), 3, n_it);
+            }
+            // ---- end of the round: the four warps that share these 32 frames meet (the other lane quarters run on), every warp deals
+            // ITS queue's entries one per lane and filters them against the final maximum of the frame each entry belongs to
+            if (tr) VQB_TRACE(trole, 3, n_it);
+            sMin[slot4 * BM + row_in_tile] = mymax;
+            if ((!(band < INFINITY) && !first) || mine > Q_LANE_CAP) sCnt[BM + row_in_tile] = 1;   // non-finite latent / flooded: exact search
+            asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
+            if (tr) VQB_TRACE(trole, 6, n_it);
+            {
+                if (qn > (uint32_t)ring_cap) {    // queue overflow: some frame of this quarter lost an event - all 32 go to the exact search
+                    sCnt[BM + row_in_tile] = 1;
+                    qn = (uint32_t)ring_cap;
+                }
+                const unsigned char* qb = sRing + (size_t)ew * ring_cap * Q_ENTRY;
+                for (uint32_t e = (uint32_t)lane; e < qn; e += 32u) {
+                    const unsigned char* en = qb + (size_t)e * Q_ENTRY;
+                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 32);
+                    const int r = quarter * 32 + (int)(hd.y >> 16);
+                    const float gmax = fmaxf(fmaxf(sMin[r], sMin[BM + r]), fmaxf(sMin[2 * BM + r], sMin[3 * BM + r]));
+                    const float cutoff = gmax - 0.5f * sBand[(rd & 3) * BM + r];
+                    if (__uint_as_float(hd.x) >= cutoff) {
+                        const int k0 = (int)(hd.y & 0xFFFFu) * 8;
+                        const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 16);
+                        const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        unsigned pm = 0;          // which of the 8 codes pass: ONE shared-memory atomic per entry, not one per code
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pm |= (__uint_as_float(av[j]) >= cutoff) ? (1u << j) : 0u;
+                        int pos = atomicAdd(&sCnt[r], __popc(pm));
+                        while (pm) {
+                            const int j = __ffs((int)pm) - 1;
+                            pm &= pm - 1u;
+                            if (pos < kCandFill) sList[r * kCandMax + pos] = (uint16_t)(k0 + j);
+                            else sCnt[BM + r] = 1;
+                            ++pos;
+                        }
+                    }
+                }
+            }
+            if (slot4 == 0) *smax = f2ord(-INFINITY);     // nobody reads the pooled maximum between the two barriers
+            if (tr) VQB_TRACE(trole, 4, n_it);
+            asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
+            if (tr) VQB_TRACE(trole, 5, n_it);
+            if (slot4 == 0) {
+                if (row < N) {
+                    const int cnt = sCnt[row_in_tile];
+                    if (force_fallback || cnt == 0 || sCnt[BM + row_in_tile]) {
+                        cand_cnt[row] = kCandFinal;          // the exact search fills in the final code
+                        const int fp = atomicAdd(&meta->fallback_count, 1);
+                        fallback_rows[fp] = (int)row;
+                        best64[fp] = ~0ull;
+                        atomicAdd(&meta->fallback_total, 1ull);
+                    } else {
+                        cand_cnt[row] = (uint8_t)(cnt < kCandFill ? cnt : kCandFill);
+                        const uint4* src = reinterpret_cast<const uint4*>(sList + row_in_tile * kCandMax);
+                        uint4* dst = reinterpret_cast<uint4*>(cand_idx + (size_t)row * kCandMax);
+                        dst[0] = src[0];
+                        dst[1] = src[1];
+                    }
+                }
+                sCnt[row_in_tile] = 0;
+                sCnt[BM + row_in_tile] = 0;
+            }
+        }
     } else if (warp < EPI_WARPS) {
         // ================================================================ epilogue
         const int ew = warp - EPI_WARP0;
@@ -1055,12 +1282,14 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         ev.sbase = sEv + (size_t)et * ev_sm * EV_WORDS;
         ev.sm = ev_sm;
         ev.n = 0;
+        ev.ng = 0;
+        ev.pool_u = smem_u32(sRing + (size_t)ew * ring_cap * Q_ENTRY);
+        ev.pool_cnt_u = smem_u32(sPoolCnt + ew);
+        ev.pool_cap = (kFuse && !kTail) ? (uint32_t)ring_cap : 0u;   // (the pool's resolution reads the bands and writes global shortlists)
+        ev.lane = (uint32_t)lane;
+        if (lane == 0) sPoolCnt[ew] = 0u;
         if (colq == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; sCnt[2 * BM + row_in_tile] = f2ord(-INFINITY); }
         int* smax = sCnt + 2 * BM + row_in_tile;
-        unsigned char* ring = sRing + (size_t)ew * (kRing ? ring_cap : 0) * RING_ENTRY;   // this warp's capture ring
-        const uint32_t ring_u = smem_u32(ring);
-        int ring_n = 0;
-        bool ring_lost = false;
         asm volatile("bar.sync 1, 512;" ::: "memory");
         uint32_t n_it = 0;
         for (int rd = 0; rd < rounds; ++rd) {
@@ -1077,9 +1306,12 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             float hband = 0.5f * band;                    // the band in accumulator units (acc = -score / 2)
             float thr = -INFINITY;
             ev.n = 0;
+            ev.ng = 0;
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1;
+                if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 0, n_it);   // epilogue: about to wait for the accumulator
                 mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
+                if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 1, n_it);   // epilogue: accumulator visible
                 tc_fence_after();
                 if (kFuse && nt == 0) {                   // the converter published this tile's bands before the first MMA could start
                     band = sBand[(rd & 3) * BM + row_in_tile];
@@ -1105,6 +1337,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 for (int sb = 0; sb < COLS_PER_WARP / 32; ++sb) {
                     tmem_ld32(taddr + sb * 32, ra);
                     tmem_ld_wait(ra);
+                    if (lane == 0 && ew == 0) VQB_TRACE(6, 2 * sb, n_it);                        // epilogue: slab in registers
                     if (sb == COLS_PER_WARP / 32 - 1) {
                         // the last slab of this accumulator stage is in registers: hand the stage back BEFORE scanning it - the
                         // hand-off round trip (release -> MMA issue -> commit -> wake-up -> read-out), not the scan, is what a
@@ -1114,114 +1347,107 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         if (lane == 0) {
                             if (kTwo && crank != 0) mbar_arrive_remote(smem_u32(&bars->tmem_empty[as]), 0);   // the leader issues the pair's MMAs
                             else mbar_arrive(smem_u32(&bars->tmem_empty[as]));
+                            if (ew == 0 || ew == 13) VQB_TRACE(4 + (ew != 0), 2, n_it);                   // epilogue: stage released
                         }
                     }
                     if (scores_dbg) {
                         if (row < N) dump_slab(ra, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
-                    } else if (kRing) {
-                        scan_slab_ring(ra, code0 + sb * 32, hband, thr, smax, ring_u, ring_cap, ring_n, ring_lost, lane);
                     } else {
                         scan_slab(ra, (code0 + sb * 32) >> 3, hband, thr, ev, smax);
                     }
+                    if (lane == 0 && ew == 0) VQB_TRACE(6, 2 * sb + 1, n_it);                    // epilogue: slab scanned
                 }
-            }
-            if (kRing && !scores_dbg) {
-                // ---- ring form: the four warps that share these 32 frames meet on their own named barrier (the other lane quarters
-                // run on), then every warp deals ITS ring's entries one per lane and filters them against the final maximum of the
-                // frame each entry belongs to; the shortlists collect in shared memory and leave as 32-byte rows
-                sMin[colq * BM + row_in_tile] = thr + hband;
-                if (ring_lost || !(band < INFINITY)) sCnt[BM + row_in_tile] = 1;
-                asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
-                const int n_ev = ring_n < ring_cap ? ring_n : ring_cap;
-                for (int e = lane; e < n_ev; e += 32) {
-                    const unsigned char* en = ring + (size_t)e * RING_ENTRY;
-                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 128);
-                    const int r = quarter * 32 + (int)(hd.y >> 16);
-                    const float gmax = fmaxf(fmaxf(sMin[r], sMin[BM + r]), fmaxf(sMin[2 * BM + r], sMin[3 * BM + r]));
-                    const float cutoff = gmax - 0.5f * sBand[(rd & 3) * BM + r];
-                    if (__uint_as_float(hd.x) >= cutoff) {
-                        const int k0 = (int)(hd.y & 0xFFFFu);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint4 a = *reinterpret_cast<const uint4*>(en + 16 * q);
-                            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                if (__uint_as_float(av[c]) >= cutoff) {
-                                    const int pos = atomicAdd(&sCnt[r], 1);
-                                    if (pos < kCandFill) sList[r * kCandMax + pos] = (uint16_t)(k0 + 4 * q + c);
-                                    else sCnt[BM + r] = 1;
-                                }
-                            }
-                        }
-                    }
-                }
-                ring_n = 0;
-                ring_lost = false;
-                if (colq == 0) *smax = f2ord(-INFINITY);   // nobody reads the pooled maximum between the two barriers
-                asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
-                if (colq == 0) {
-                    if (row < N) {
-                        const int cnt = sCnt[row_in_tile];
-                        if (force_fallback || cnt == 0 || sCnt[BM + row_in_tile]) {
-                            cand_cnt[row] = kCandFinal;          // the exact search fills in the final code
-                            const int fp = atomicAdd(&meta->fallback_count, 1);
-                            fallback_rows[fp] = (int)row;
-                            best64[fp] = ~0ull;
-                            atomicAdd(&meta->fallback_total, 1ull);
-                        } else {
-                            cand_cnt[row] = (uint8_t)(cnt < kCandFill ? cnt : kCandFill);
-                            const uint4* src = reinterpret_cast<const uint4*>(sList + row_in_tile * kCandMax);
-                            uint4* dst = reinterpret_cast<uint4*>(cand_idx + (size_t)row * kCandMax);
-                            dst[0] = src[0];
-                            dst[1] = src[1];
-                        }
-                    }
-                    sCnt[row_in_tile] = 0;
-                    sCnt[BM + row_in_tile] = 0;
-                }
-                continue;
             }
             // ---- resolve this thread's chunks against the frame's final maximum and publish the shortlist
+            if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 3, n_it);   // epilogue: sweep scanned, resolution starts
             sMin[colq * BM + row_in_tile] = thr + hband;                     // running maximum of this column quarter
             const int tbuf = rd & 1;
             if (kTail) mbar_wait(smem_u32(&tbars->tail_empty[tbuf]), ((rd >> 1) & 1) ^ 1);   // the tail is done with the tile before last
             asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 6, n_it);   // epilogue: past the first barrier
             if (row < N && !scores_dbg) {
                 const float gmax = fmaxf(fmaxf(sMin[row_in_tile], sMin[BM + row_in_tile]),
                                          fmaxf(sMin[2 * BM + row_in_tile], sMin[3 * BM + row_in_tile]));
                 const float cutoff = gmax - hband;
                 uint16_t* dst = kTail ? sCand + (tbuf * BM + row_in_tile) * kCandFill : cand_idx + (size_t)row * kCandMax;
-                const int n_ev = ev.n < EV_CAP ? ev.n : EV_CAP;
-                bool lost = ev.n > EV_CAP || !(band < INFINITY);
-                for (int e0 = 0; e0 < n_ev; e0 += 8) {
-                    uint2 hd[8];     // headers (chunk maximum, chunk id) of 8 events fetched together: one L2 latency, not eight
+                bool lost = ev.ng > EV_CAP || !(band < INFINITY);
+                // one event: which of its 8 codes pass, ONE shared-memory atomic for them (unrolled over the codes, the returning atomics
+                // of the lanes of a warp ran one after the other: 2 700 cycles of a 12 700-cycle round at K = 1024)
+                auto take = [&](const uint32_t* en, uint32_t chunk) {
+                    const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 4);
+                    const int k0 = (int)chunk * 8;
+                    const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    unsigned pm = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pm |= (__uint_as_float(av[j]) >= cutoff) ? (1u << j) : 0u;
+                    int pos = atomicAdd(&sCnt[row_in_tile], __popc(pm));
+                    while (pm) {
+                        const int j = __ffs((int)pm) - 1;
+                        pm &= pm - 1u;
+                        if (pos < kCandFill) dst[pos] = (uint16_t)(k0 + j);
+                        else lost = true;
+                        ++pos;
+                    }
+                };
+                for (int i = 0; i < ev.n; ++i) {             // own shared-memory slots (at most 3)
+                    const uint32_t* en = ev.own(i);
+                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 8);
+                    if (__uint_as_float(hd.x) >= cutoff) take(en, hd.y);
+                }
+                const int n_g = ev.ng < EV_CAP ? ev.ng : EV_CAP;
+                for (int e0 = 0; e0 < n_g; e0 += 8) {        // global stack (rare): headers of 8 events fetched together
+                    uint2 hd[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        hd[u] = (e0 + u < n_ev) ? *reinterpret_cast<const uint2*>(ev.slot(e0 + u) + 8)
-                                                : make_uint2(0xff800000u, 0u);
+                        hd[u] = (e0 + u < n_g) ? *reinterpret_cast<const uint2*>(ev.glob(e0 + u) + 8) : make_uint2(0xff800000u, 0u);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (__uint_as_float(hd[u].x) >= cutoff) {
-                            const uint32_t* en = ev.slot(e0 + u);
+                    for (int u = 0; u < 8; ++u)
+                        if (__uint_as_float(hd[u].x) >= cutoff) take(ev.glob(e0 + u), hd[u].y);
+                }
+                if (lost) sCnt[BM + row_in_tile] = 1;
+            }
+            if (kFuse && !kTail && ring_cap > 0 && !scores_dbg) {
+                // the warp's overflow pool: entries dealt one per lane; an entry belongs to the frame of the lane that appended it
+                uint32_t pn;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pn) : "r"(ev.pool_cnt_u) : "memory");
+                if (pn > (uint32_t)ring_cap) pn = (uint32_t)ring_cap;
+                for (uint32_t e0 = 0; e0 < pn; e0 += 32u) {
+                    const uint32_t e = e0 + (uint32_t)lane;
+                    const bool act = e < pn;
+                    const uint32_t* en = reinterpret_cast<const uint32_t*>(sRing + ((size_t)ew * ring_cap + (act ? e : 0u)) * Q_ENTRY);
+                    const uint4 hd = *reinterpret_cast<const uint4*>(en + 8);            // chunk maximum, chunk id, lane, 0
+                    const int src = act ? (int)hd.z : 0;
+                    const int64_t row_e = __shfl_sync(0xffffffffu, row, src);            // global frame of that lane (N: none)
+                    const int r = quarter * 32 + src;
+                    if (act && row_e < N) {
+                        const float gmax = fmaxf(fmaxf(sMin[r], sMin[BM + r]), fmaxf(sMin[2 * BM + r], sMin[3 * BM + r]));
+                        const float cutoff = gmax - 0.5f * sBand[(rd & 3) * BM + r];
+                        if (__uint_as_float(hd.x) >= cutoff) {
                             const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 4);
-                            const int k0 = (int)hd[u].y * 8;
+                            const int k0 = (int)hd.y * 8;
                             const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                            unsigned pm = 0;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (__uint_as_float(av[j]) >= cutoff) {
-                                    const int pos = atomicAdd(&sCnt[row_in_tile], 1);
-                                    if (pos < kCandFill) dst[pos] = (uint16_t)(k0 + j);
-                                    else lost = true;
-                                }
+                            for (int j = 0; j < 8; ++j) pm |= (__uint_as_float(av[j]) >= cutoff) ? (1u << j) : 0u;
+                            int pos = atomicAdd(&sCnt[r], __popc(pm));
+                            uint16_t* dst = cand_idx + (size_t)row_e * kCandMax;
+                            while (pm) {
+                                const int j = __ffs((int)pm) - 1;
+                                pm &= pm - 1u;
+                                if (pos < kCandFill) dst[pos] = (uint16_t)(k0 + j);
+                                else sCnt[BM + r] = 1;
+                                ++pos;
                             }
                         }
                     }
                 }
-                if (lost) sCnt[BM + row_in_tile] = 1;
+                __syncwarp();
+                if (lane == 0) sPoolCnt[ew] = 0u;
             }
             if (colq == 0) *smax = f2ord(-INFINITY);       // nobody reads the pooled maximum between the two barriers
+            if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 4, n_it);   // epilogue: own stack resolved
             asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 5, n_it);   // epilogue: past the second barrier
             if (colq == 0) {
                 int tcnt = 0;                                    // what the tail warps get: 0 = frame is not theirs
                 if (row < N && !scores_dbg) {
@@ -1358,7 +1584,7 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 // One function decides for the launcher AND for the callers that must know beforehand whether a variant fits
 // (tc_can_fuse, tc_fused_tail_fits).
 struct TcPlan {
-    bool ok, two;
+    bool ok, two, ring;   // ring: grouped epilogue (ring_cap = queue entries per warp); else ring_cap = overflow-pool entries per warp
     int cs, a_slots, b_stages, ev_sm, eh_slots, ring_cap;
     size_t smem;
 };
@@ -1394,7 +1620,7 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     const size_t fixed_no_a = (size_t)p.eh_slots * EH_SLICE_BYTES + AX_BYTES + ZERO_BYTES + 4 * BM * 4 + 3 * BM * 4 +
                               (fuse ? (tf32 ? 0 : STG_SLOTS * STG_BYTES) + 4 * BM * 4 : 0) +
                               (with_tail ? 2 * BM * kCandFill * 2 + 2 * BM + TAIL_WARPS * 32 * 8 + 128 + TX_SLOTS * TX_BYTES + sizeof(TailBarriers) : 0) +
-                              sizeof(Barriers);   // no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
+                              2 * EPI_WARPS * 4 + sizeof(Barriers);   // (+ 128 bytes for the pool fills) no slack: the dynamic segment starts 1024-byte aligned (no static shared memory in this kernel)
     if (!tf32 && fuse && !with_tail && num_kb > 2 && 2 * num_kb <= MAX_A_SLOTS) {
         // the full second tile must leave three codebook stages (it does for CTA pairs at D = 256: 3 x 16 KiB half-tile stages)
         bool full_second_tile = fixed_no_a + (size_t)2 * num_kb * A_CHUNK_BYTES + 3 * stage_bytes <= 227 * 1024;
@@ -1403,28 +1629,33 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     }
     if (tf32 && fixed_no_a + 2 * a_unit + 3 * stage_bytes > 227 * 1024) p.a_slots = 1;
     const size_t fixed = (size_t)p.a_slots * a_unit + fixed_no_a;
-    // shared-memory part of the event stacks: whatever four codebook stages leave, at most 3 entries per epilogue thread
+    // Shared-memory part of the event stacks, from what four codebook stages leave: own slots of every epilogue thread (24 KiB per
+    // level) and an overflow pool per warp (EventStack).  With room for 72 KiB (D = 64): two own slots + 32 pool entries per warp.
     const size_t ev_entry_bytes = (size_t)EPI_THREADS * EV_WORDS * 4;   // one entry for every epilogue thread: 24 KiB
+    const size_t pool_entry_bytes = (size_t)EPI_WARPS * Q_ENTRY;        // one pool entry for every epilogue warp: 768 bytes
     p.ev_sm = 0;
-    if (!with_tail && !dbg && 227 * 1024 > fixed + 4 * stage_bytes) {
-        p.ev_sm = (int)((227 * 1024 - fixed - 4 * stage_bytes) / ev_entry_bytes);
-        if (p.ev_sm > 3) p.ev_sm = 3;
-    }
-    if (const int v = env_get(ENV_TC_EVSM, -1); v >= 0 && v < p.ev_sm) p.ev_sm = v;   // experiments
-    // Ring epilogue (small codebooks, K <= 2048): per-warp capture rings + the tile's shortlists instead of the shared-memory part of
-    // the per-thread stacks, when four codebook stages leave room for at least 24 entries per warp (about 22 events per warp and frame
-    // tile at K = 1024, 16 at K = 512; a full ring only sends the frame to the exact search).  OPT-IN (VQB_TC_EPI=1): measured at cfg 2
-    // it executes 40 % fewer instructions and takes the SAME time - the kernel is bound by the accumulator hand-off round trip, not
-    // by the epilogue's instruction count - and its rings overflow on 0.6 - 3 % of the frames.
     p.ring_cap = 0;
     size_t ring_bytes = 0;
-    if (fuse && !with_tail && !dbg && K_pad > 0 && K_pad <= 2048 && env_get(ENV_TC_EPI, 0) == 1) {
+    if (!with_tail && !dbg && 227 * 1024 > fixed + 4 * stage_bytes) {
+        const size_t room = 227 * 1024 - fixed - 4 * stage_bytes;
+        const bool pool_ok = fuse && env_get(ENV_TC_EVSM, -1) != -2;        // VQB_TC_EVSM=-2 (experiments): no pool
+        if (pool_ok && room >= 2 * ev_entry_bytes + 32 * pool_entry_bytes) { p.ev_sm = 2; p.ring_cap = 32; }
+        else if (pool_ok && room >= 2 * ev_entry_bytes + 16 * pool_entry_bytes) { p.ev_sm = 2; p.ring_cap = 16; }
+        else if (pool_ok && room >= ev_entry_bytes + 32 * pool_entry_bytes) { p.ev_sm = 1; p.ring_cap = 32; }
+        else { p.ev_sm = (int)(room / ev_entry_bytes); if (p.ev_sm > 3) p.ev_sm = 3; }
+        ring_bytes = (size_t)p.ring_cap * pool_entry_bytes;
+    }
+    if (const int v = env_get(ENV_TC_EVSM, -1); v >= 0 && v < p.ev_sm) p.ev_sm = v;   // experiments
+    // Grouped epilogue (small codebooks, K <= 1024; see scan_slab_q): per-warp chunk queues + the tile's shortlists + queue fills instead
+    // of the shared-memory part of the per-thread stacks.  About 22 events per warp and frame-tile round at K = 1024 (fewer at K = 512);
+    // a full queue sends the 32 frames of its lane quarter to the exact search.  VQB_TC_EPI=0 (experiments) keeps the per-thread stacks.
+    if (fuse && !with_tail && !dbg && K_pad > 0 && K_pad <= 1024 && env_get(ENV_TC_EPI, 0) == 1) {
         const size_t list_bytes = (size_t)BM * kCandMax * 2;
         const size_t base = fixed + 4 * stage_bytes + list_bytes;
         if (227 * 1024 > base) {
-            int cap = (int)((227 * 1024 - base) / ((size_t)EPI_WARPS * RING_ENTRY));
-            if (cap > 64) cap = 64;
-            if (cap >= 24) { p.ring_cap = cap; p.ev_sm = 0; ring_bytes = (size_t)EPI_WARPS * cap * RING_ENTRY + list_bytes; }
+            int cap = (int)((227 * 1024 - base) / ((size_t)EPI_WARPS * Q_ENTRY));
+            if (cap > 96) cap = 96;
+            if (cap >= 48) { p.ring = true; p.ring_cap = cap; p.ev_sm = 0; ring_bytes = (size_t)EPI_WARPS * cap * Q_ENTRY + list_bytes; }
         }
     }
     const size_t fixed_ev = fixed + (size_t)p.ev_sm * ev_entry_bytes + ring_bytes;
@@ -1523,7 +1754,7 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     const int num_m_tiles = fuse ? B * tiles_per_item : (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
     const TcPlan plan = tc_plan(fuse, with_tail, scores_dbg != nullptr, num_m_tiles, D, tf32, K_pad);
-    const bool ring = plan.ring_cap > 0;
+    const bool ring = plan.ring;
     if (!plan.ok) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
     const bool two = plan.two;
     const int cs = plan.cs, a_slots = plan.a_slots, b_stages = plan.b_stages, ev_sm = plan.ev_sm;
@@ -1598,6 +1829,15 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
 }  // namespace vqb
 
 extern "C" {
+#ifdef VQB_TC_TRACE
+// debug builds only: device buffer of 2 x cap records (CTA 0 and CTA 1) for the hand-off timeline; cap = 0 switches tracing off
+__attribute__((visibility("default"))) int vqb_debug_set_trace(void* buf, unsigned int cap) {
+    unsigned long long* b = static_cast<unsigned long long*>(buf);
+    if (cudaMemcpyToSymbol(vqb::tc::g_trace_buf, &b, sizeof(b)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(vqb::tc::g_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return 1;
+    return 0;
+}
+#endif
 // enable != 0: record a CUDA-event pair around every stage of vqb_forward from now on (and forget earlier ones)
 int vqb_debug_kernel_timing(int enable) {
     vqb::g_timing = enable != 0;

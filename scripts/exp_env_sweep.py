@@ -1,0 +1,68 @@
+"""Stage times of the training-mode forward under sets of experiment switches (VQB_EXPERIMENTS=1), one JSON line per (case, env).
+usage: python scripts/exp_env_sweep.py case1,case2 "A=1 B=2" "C=3" ...   (an empty string = defaults)"""
+import ctypes as C, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import vq_b200  # noqa: F401
+from vq_b200 import _lib, functional as F
+
+CASES = {"cfg2": (64, 64, 16384, 1024), "cfg5": (64, 64, 11000, 512), "cfg1": (2, 64, 11000, 512), "mid": (64, 128, 16384, 2048),
+         "cfg3s": (128, 256, 16384, 8192), "cfg3q": (256, 256, 16384, 8192)}
+dev = torch.device("cuda:0")
+lib = _lib.lib()
+os.environ["VQB_EXPERIMENTS"] = "1"
+names = sys.argv[1].split(",")
+envs = sys.argv[2:] or [""]
+known = set()
+for name in names:
+    B, D, W, K = CASES[name]
+    z = torch.randn(B, D, W, device=dev, generator=torch.Generator(device=dev).manual_seed(42))
+    cb = torch.randn(K, D, device=dev, generator=torch.Generator(device=dev).manual_seed(4242))
+    stats = torch.empty(_lib.stats_len(K, D), device=dev)
+    ref = None
+    for env in envs:
+        for k in known:
+            os.environ.pop(k, None)
+        for kv in env.split():
+            k, v = kv.split("=")
+            os.environ[k] = v
+            known.add(k)
+        lib.vqb_debug_reload_env()
+        prec = os.environ.get("PREC", "bf16")
+        want_q, want_resid = os.environ.get("WANT_Q", "1") == "1", os.environ.get("WANT_RESID", "1") == "1"
+        try:
+            for _ in range(3):
+                idx, q, st = F.vq_forward(z, cb, precision=prec, want_q=want_q, want_resid=want_resid, stats=stats)
+            torch.cuda.synchronize()
+            lib.vqb_debug_kernel_timing(1)
+            steps = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                idx, q, st = F.vq_forward(z, cb, precision=prec, want_q=want_q, want_resid=want_resid, stats=stats)
+            e1.record()
+            torch.cuda.synchronize()
+        except Exception as ex:  # noqa: BLE001
+            print(json.dumps({"case": name, "env": env, "error": str(ex)[:200]}), flush=True)
+            continue
+        out = {"case": name, "env": env, "step_ms": round(e0.elapsed_time(e1) / steps, 4)}
+        for sid, sname in enumerate(("search", "prep", "fallback", "tail", "pack")):
+            ms, n = C.c_double(0), C.c_int(0)
+            lib.vqb_debug_stage_time_ms(sid, C.byref(ms), C.byref(n))
+            out[sname] = round(ms.value / max(1, n.value), 4)
+        lib.vqb_debug_kernel_timing(0)
+        c = F.debug_counters(dev)
+        out.update(rescored=c["rescored"], fallback_frames=c["fallback"])
+        out["tail_GBs"] = round((8 * D + 8) * B * W / max(out["tail"], 1e-9) / 1e6, 1)
+        cur = (idx.clone(), q.clone() if q is not None else None, st.clone())
+        if not (want_q and want_resid):
+            pass
+        elif ref is None:
+            ref = cur
+        else:
+            same = torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]) and torch.equal(cur[2][:K], ref[2][:K])
+            err = ((cur[2][K:] - ref[2][K:]).abs().max() / ref[2][K:].abs().max().clamp_min(1e-30)).item()
+            out["check"] = f"idx/q/counts identical={same}, stats err {err:.1e}, idx diff {int((cur[0] != ref[0]).sum())}"
+        print(json.dumps(out), flush=True)
+    del z, idx
+    torch.cuda.empty_cache()

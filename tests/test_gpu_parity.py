@@ -202,11 +202,13 @@ def test_fused_tail_variant_matches_oracle(B, D, W, K, cb_scale, experiment_env)
     np.testing.assert_allclose(vq.codebook.weight.grad.cpu().numpy(), dE, rtol=1e-4, atol=1e-6 * np.abs(dE).max())
 
 
-@pytest.mark.parametrize("env", [{"VQB_TAIL_TMA": "0"}, {"VQB_TAIL_VARIANT": "0"}, {"VQB_RESID_REPLICAS": "1"},
+@pytest.mark.parametrize("env", [{"VQB_TAIL_TMA": "0"}, {"VQB_TAIL_FORM": "0"}, {"VQB_TAIL_FORM": "0", "VQB_TAIL_VARIANT": "0"},
+                                 {"VQB_TAIL_FORM": "2"}, {"VQB_TAIL_FORM": "216"}, {"VQB_TAIL_FORM": "300"}, {"VQB_TC_EPI": "1"}, {"VQB_RESID_REPLICAS": "1"},
                                  {"VQB_RESID_REPLICAS": "8"}, {"VQB_DX_TILES": "1"}, {"VQB_TC_ASLOTS": "6"},
                                  {"VQB_L2_ONCE": "1"}, {"VQB_TC_EHSLOTS": "5"}, {"VQB_TC_MODE": "1"}])
 def test_kernel_variants_agree_with_the_default_path(env, experiment_env):
-    """The experiment switches select other forms of the same kernels (register-staged tail, 8-warp TMA tail, one / eight
+    """The experiment switches select other forms of the same kernels (register-staged tail, round-1 TMA tails, tail2_kernel
+    with 32- and 16-frame tiles - the default is tail3_kernel -, one / eight
     residual-sum replicas, tile-staged backward, two spare A chunks, evict-first latent loads, a deeper bias-operand ring,
     cta_group::1 MMAs): indices and `quantized` must be identical, statistics and
     gradients equal up to the summation order of the atomics.  A hot code (a quarter of the frames) stresses the replicas."""
