@@ -731,7 +731,7 @@ def main():
     if stages.get("tail", 0.0) > 0.0:
         tail_bytes = ((8.0 if not (args.no_q or export_only) else 4.0) * D + 8.0) * N
         gbs = tail_bytes / (stages["tail"] * 1e-3) / 1e9
-        roofline_tail = {"bound": "hbm", "kernel": "tail kernel (stage: memsets + tail + residual fold)", "achieved": gbs, "peak": peaks["hbm_gbs"],
+        roofline_tail = {"bound": "hbm", "kernel": "tail3_kernel / tail2_kernel (stage: memsets + tail + residual fold)", "achieved": gbs, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "kernel_ms": stages["tail"],
                          "kernel_share_of_step": stages["tail"] / ms_per_step, "algorithmic_bytes_per_launch": tail_bytes,
                          "traffic": load_traffic(args.workload + "_tail") if N == WORKLOADS[args.workload][0] * W else None,

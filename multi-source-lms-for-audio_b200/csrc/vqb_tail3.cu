@@ -59,8 +59,9 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 struct Bars { unsigned long long full[2], done[2]; };
 
 // J: D = 32 J.  LPF: lanes per frame (8, 4, 2; D / LPF <= 32 dims per lane).  kRun: keep the residual sum of a run of equal codes in
-// registers (at most 16 dims per lane).  kBulk: residual sums leave as one bulk reduction per frame from a per-warp staging row (needs kResid, !kRun).
-template <int J, int LPF, bool kResid, bool kRun, bool kBulk>
+// registers (at most 16 dims per lane).  kAhead: the next tile's shortlists are fetched one tile ahead and |x|^2 rides along with the pair
+// scoring (chosen per shape by measurement, see launch_tail3).  kBulk: residual sums leave as one bulk reduction per frame from a per-warp staging row (needs kResid, !kRun).
+template <int J, int LPF, bool kResid, bool kRun, bool kBulk, bool kAhead>
 __global__ void __launch_bounds__(32 * ((LPF == 2 ? 2 : 4) + 1), (32 * J / LPF >= 24) ? 3 : ((32 * J / LPF >= 12) ? 4 : 5))
 tail3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_q, const float* __restrict__ Ep,
              const float* __restrict__ e2, int64_t W, int tiles_per_item, int num_tiles, const int* __restrict__ idx32,
@@ -167,10 +168,7 @@ tail3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__
                 else v = reinterpret_cast<const uint4*>(cand_idx + (size_t)n * kCandMax)[lane & 1];
             }
         };
-        // Measured per D (profiles/r03_exp_tail3_opts.jsonl): fetching the next tile's shortlists one tile ahead and letting |x|^2 ride along
-        // with the pair scoring take 10 % off at D = 256 (1.49 -> 1.33 ms per 2^21 frames) and ADD 10 - 15 % at D = 128 / 64, where more
-        // blocks per SM already hide the list loads - so only the large-D instances get them
-        constexpr bool pf = J >= 6, foldx2 = J >= 6;
+        constexpr bool pf = kAhead, foldx2 = kAhead;
         int cnt_nx;
         uint4 v_nx;
         if (pf) fetch_lists(tile0, cnt_nx, v_nx);
@@ -416,7 +414,7 @@ template <int J, int LPF>
 static cudaError_t launch_t(const CUtensorMap& mz, const CUtensorMap& mq, const float* ep, const float* e2, int64_t W, int tiles_per_item,
                             int num_tiles, const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out,
                             bool has_q, int* counts, float* resid_rep, int n_rep, size_t rep_stride, double* part, int n_partials, WsMeta* meta,
-                            bool read_once, bool bulk, cudaStream_t s) {
+                            bool read_once, bool bulk, bool ahead, cudaStream_t s) {
     constexpr int D = 32 * J, NWARP = LPF == 2 ? 2 : 4, FW = TF / NWARP, G = 32 / LPF, NTHREADS = 32 * (NWARP + 1);
     constexpr bool kRun = D / LPF <= 16;
     bulk = bulk && resid_rep && !kRun;
@@ -447,9 +445,14 @@ static cudaError_t launch_t(const CUtensorMap& mz, const CUtensorMap& mq, const 
                                                       counts, resid_rep, n_rep, rep_stride, part, meta, read_once ? 1 : 0);
         return cudaGetLastError();
     };
-    if (!resid_rep) return go(tail3_kernel<J, LPF, false, false, false>);
-    if constexpr (!kRun) { if (bulk) return go(tail3_kernel<J, LPF, true, false, true>); }
-    return go(tail3_kernel<J, LPF, true, kRun, false>);
+    if (ahead) {
+        if (!resid_rep) return go(tail3_kernel<J, LPF, false, false, false, true>);
+        if constexpr (!kRun) { if (bulk) return go(tail3_kernel<J, LPF, true, false, true, true>); }
+        return go(tail3_kernel<J, LPF, true, kRun, false, true>);
+    }
+    if (!resid_rep) return go(tail3_kernel<J, LPF, false, false, false, false>);
+    if constexpr (!kRun) { if (bulk) return go(tail3_kernel<J, LPF, true, false, true, false>); }
+    return go(tail3_kernel<J, LPF, true, kRun, false, false>);
 }
 
 // sums the (permuted) replicas into the caller's residual sums, un-permuting
@@ -499,9 +502,13 @@ cudaError_t launch_tail3(const float* z, const float* ep, const float* e2, int B
     // VQB_TAIL_FORM=300 (experiments): red.v4 everywhere
     const bool bulk = env_get(ENV_TAIL_FORM, 3) != 300;
     const int lpf = tail3_lpf(D);
+    // shortlists one tile ahead + |x|^2 folded into the pair scoring: measured per shape (profiles/r03_exp_tail3_ahead*.jsonl): a gain
+    // at D = 256 (1.34 -> 1.31 - 1.33 ms per 2^21 frames in most runs), none at D = 64, a loss at D = 128 with 8 lanes per frame
+    bool ahead = D >= 192;
+    if (const int v = env_get(ENV_TAIL_AHEAD, -1); v >= 0) ahead = v != 0;   // experiments
     cudaError_t e = cudaErrorInvalidValue;
 #define VQB_T3(J, LPF) e = launch_t<J, LPF>(mz, mq, ep, e2, W, tiles_per_item, num_tiles, idx32, cand_cnt, cand_idx, idx_out, q_out != nullptr, counts, \
-                                            rep, n_rep, rep_stride, part, n_partials, meta, once, bulk, s)
+                                            rep, n_rep, rep_stride, part, n_partials, meta, once, bulk, ahead, s)
     switch ((D / 32) * 16 + lpf) {
         case 1 * 16 + 2: VQB_T3(1, 2); break;
         case 1 * 16 + 4: VQB_T3(1, 4); break;

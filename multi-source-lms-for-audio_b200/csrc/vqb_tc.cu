@@ -1389,11 +1389,43 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         ++pos;
                     }
                 };
-                for (int i = 0; i < ev.n; ++i) {             // own shared-memory slots (at most 3)
-                    const uint32_t* en = ev.own(i);
-                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 8);
-                    if (__uint_as_float(hd.x) >= cutoff) take(en, hd.y);
+                if (lane == 0 && ew == 0) VQB_TRACE(7, 0, n_it);
+                {   // own shared-memory slots (at most 3): every entry is read up front (one shared-memory latency, not one per entry
+                    // and per dependent step) and the thread asks for all its shortlist positions with ONE atomic
+                    unsigned pm[3];
+                    uint32_t ch[3];
+                    int total = 0;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        pm[i] = 0u;
+                        ch[i] = 0u;
+                        if (i < ev.n) {
+                            const uint32_t* en = ev.own(i);
+                            const uint2 hd = *reinterpret_cast<const uint2*>(en + 8);
+                            const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 4);
+                            const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) pm[i] |= (__uint_as_float(av[j]) >= cutoff) ? (1u << j) : 0u;
+                            ch[i] = hd.y;
+                            total += __popc(pm[i]);
+                        }
+                    }
+                    if (total) {
+                        int pos = atomicAdd(&sCnt[row_in_tile], total);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            unsigned m = pm[i];
+                            while (m) {
+                                const int j = __ffs((int)m) - 1;
+                                m &= m - 1u;
+                                if (pos < kCandFill) dst[pos] = (uint16_t)(ch[i] * 8u + (uint32_t)j);
+                                else lost = true;
+                                ++pos;
+                            }
+                        }
+                    }
                 }
+                if (lane == 0 && ew == 0) VQB_TRACE(7, 1, n_it);
                 const int n_g = ev.ng < EV_CAP ? ev.ng : EV_CAP;
                 for (int e0 = 0; e0 < n_g; e0 += 8) {        // global stack (rare): headers of 8 events fetched together
                     uint2 hd[8];
@@ -1406,6 +1438,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
                 if (lost) sCnt[BM + row_in_tile] = 1;
             }
+            if (lane == 0 && ew == 0) VQB_TRACE(7, 2, n_it);
             if (kFuse && !kTail && ring_cap > 0 && !scores_dbg) {
                 // the warp's overflow pool: entries dealt one per lane; an entry belongs to the frame of the lane that appended it
                 uint32_t pn;

@@ -12,7 +12,7 @@ procs = []
 for src in B.SOURCES:
     obj = os.path.join(out_dir, src[:-3] + ".o")
     flags = [f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
-    procs.append((src, subprocess.Popen([B.nvcc(), *B.ARCH, *flags, "-DVQB_TC_TRACE", "-c", os.path.join(B.CSRC, src), "-o", obj])))
+    procs.append((src, subprocess.Popen([B.nvcc(), *B.ARCH, *flags, "-DVQB_TC_TRACE", *sys.argv[1:], "-c", os.path.join(B.CSRC, src), "-o", obj])))
     objs.append(obj)
 for src, p in procs:
     if p.wait() != 0:

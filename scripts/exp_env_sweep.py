@@ -13,6 +13,7 @@ lib = _lib.lib()
 os.environ["VQB_EXPERIMENTS"] = "1"
 names = sys.argv[1].split(",")
 envs = sys.argv[2:] or [""]
+PASSES = int(os.environ.get("PASSES", "1"))   # > 1: every environment is measured PASSES times in round-robin order, the line with the smallest step time is printed
 known = set()
 for name in names:
     B, D, W, K = CASES[name]
@@ -20,7 +21,8 @@ for name in names:
     cb = torch.randn(K, D, device=dev, generator=torch.Generator(device=dev).manual_seed(4242))
     stats = torch.empty(_lib.stats_len(K, D), device=dev)
     ref = None
-    for env in envs:
+    best = {}
+    for env in [e for _ in range(PASSES) for e in envs]:
         for k in known:
             os.environ.pop(k, None)
         for kv in env.split():
@@ -63,6 +65,15 @@ for name in names:
             same = torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]) and torch.equal(cur[2][:K], ref[2][:K])
             err = ((cur[2][K:] - ref[2][K:]).abs().max() / ref[2][K:].abs().max().clamp_min(1e-30)).item()
             out["check"] = f"idx/q/counts identical={same}, stats err {err:.1e}, idx diff {int((cur[0] != ref[0]).sum())}"
-        print(json.dumps(out), flush=True)
+        if PASSES == 1:
+            print(json.dumps(out), flush=True)
+        elif env not in best:
+            best[env] = out
+        else:                                   # smallest time of every stage over the passes (stages vary independently with the clocks)
+            for k in ("step_ms", "search", "prep", "fallback", "tail", "pack"):
+                best[env][k] = min(best[env][k], out[k])
+    for env in envs if PASSES > 1 else []:
+        if env in best:
+            print(json.dumps(best[env]), flush=True)
     del z, idx
     torch.cuda.empty_cache()

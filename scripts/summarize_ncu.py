@@ -30,8 +30,8 @@ def main():
             v, u = vals.get(k, ("0", "byte"))
             f = float(v.replace(",", ""))
             return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
-        if key and "tc_search" in name:
-            traffic[key] = {"dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
+        if key and ("tc_search" in name or "tail" in name):
+            traffic[key + ("_tail" if "tail" in name else "")] = {"dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
                             "dram_read": to_bytes("dram__bytes_read.sum"), "dram_write": to_bytes("dram__bytes_write.sum"),
                             "source": "ncu --set full --clock-control none, one launch, " + rep.split("/")[-1]}
     open(out + ".txt", "w").write("\n".join(lines) + "\n")

@@ -45,7 +45,7 @@ json.dump(res, open(out, "w"))
 # summary for CTA 0: steady-state tiles 40..79
 names = {"1.0": "mma wait_tempty", "1.1": "mma stage_free", "1.2": "mma A ready", "1.3": "mma B ready", "1.4": "mma bias ready",
          "4.0": "epi0 wait_tfull", "4.1": "epi0 acc visible", "4.2": "epi0 released", "4.3": "epi0 resolve start", "4.4": "epi0 resolved",
-         "4.5": "epi0 past bar2", "4.6": "epi0 past bar1", "6.0": "epi0 slab0 in regs", "6.1": "epi0 slab0 scanned", "6.2": "epi0 slab1 in regs", "6.3": "epi0 slab1 scanned", "5.0": "epi13 wait_tfull", "5.1": "epi13 acc visible", "5.2": "epi13 released"}
+         "4.5": "epi0 past bar2", "4.6": "epi0 past bar1", "7.0": "epi0 cutoff known", "7.1": "epi0 own slots done", "7.2": "epi0 global done", "6.0": "epi0 slab0 in regs", "6.1": "epi0 slab0 scanned", "6.2": "epi0 slab1 in regs", "6.3": "epi0 slab1 scanned", "5.0": "epi13 wait_tfull", "5.1": "epi13 acc visible", "5.2": "epi13 released"}
 for cta in range(2):
     e = res[cta]
     if "1.4" not in e:
@@ -54,7 +54,7 @@ for cta in range(2):
     t0 = e["1.4"].get(40)
     for t in range(40, 52):
         row = [f"tile {t:3d}"]
-        for key in ("1.0", "1.1", "1.2", "1.3", "1.4", "4.0", "4.1", "6.0", "6.1", "6.2", "4.2", "6.3", "5.1", "5.2", "4.3", "4.6", "4.4", "4.5"):
+        for key in ("1.0", "1.1", "1.2", "1.3", "1.4", "4.0", "4.1", "6.0", "6.1", "6.2", "4.2", "6.3", "5.1", "5.2", "4.3", "4.6", "7.0", "7.1", "7.2", "4.4", "4.5"):
             v = e.get(key, {}).get(t)
             dv = ((v - t0) & 0xFFFFFFFF) if v is not None and t0 is not None else -1
             if dv > 0x7FFFFFFF:

@@ -234,6 +234,29 @@ def test_kernel_variants_agree_with_the_default_path(env, experiment_env):
     np.testing.assert_allclose(got[5], ref[5], rtol=1e-4, atol=1e-6 * np.abs(ref[5]).max())
 
 
+@pytest.mark.parametrize("D,lpf", [(64, 2), (64, 4), (64, 8), (32, 2), (128, 4), (128, 8), (96, 4)])
+def test_tail3_lanes_per_frame_agree_with_the_oracle(D, lpf, experiment_env):
+    """tail3_kernel reads the swizzled latent box in place with 8, 4 or 2 lanes per frame (the permutation of the codebook copy and
+    of the residual replicas follows): every choice must give the oracle's indices, `quantized`, losses and gradients.  W is not a
+    multiple of the 32-frame tile, so the last tile of every item is ragged."""
+    experiment_env(VQB_TAIL_LPF=str(lpf))
+    B, W, K, beta = 3, 1100, 300, 0.25
+    cb = seeded(21, (K, D))
+    z = seeded(22, (B, D, W))
+    Gq = seeded(23, z.shape, 1e-3)
+    ref = O.vq_forward(z, cb, beta)
+    vq, zt, (emb, com, q, ppl, enc, idx) = run_module(z, cb, beta, "bf16", Gq=Gq)
+    got = idx.reshape(-1).cpu().numpy()
+    n_bad = assert_index_parity(got, z, cb, ref.indices, ref.margin, ref.eps)
+    if n_bad == 0:
+        assert np.array_equal(q.detach().cpu().numpy(), ref.quantized)
+    np.testing.assert_allclose(emb.item(), ref.embedding_loss, rtol=1e-5)
+    np.testing.assert_allclose(ppl.item(), ref.perplexity, rtol=1e-5)
+    dX, dE = O.vq_backward(z, cb, got, beta, 1.0, 1.0, Gq)
+    np.testing.assert_allclose(zt.grad.cpu().numpy(), dX, rtol=1e-5, atol=1e-7 * np.abs(dX).max())
+    np.testing.assert_allclose(vq.codebook.weight.grad.cpu().numpy(), dE, rtol=1e-4, atol=1e-6 * np.abs(dE).max())
+
+
 def test_stage_timing_reports_every_stage_of_the_forward():
     """vqb_debug_stage_time_ms (bench.py's roofline legs): one timed launch per stage and forward, durations positive."""
     import ctypes as C
