@@ -40,6 +40,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// One non-blocking look at a barrier phase (acquire on success): issued EARLY, so that its latency hides behind other work and the
+// blocking wait can be skipped when the phase has long completed (a try_wait on a completed phase still costs ~270 cycles here)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Polling wait (no hardware suspend): for the two barriers of the accumulator hand-shake, where the wake-up latency of a
 // suspended warp sits on the critical path when one codebook tile is only a few hundred tensor-core cycles (small D).
 __device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {

@@ -1292,6 +1292,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         int* smax = sCnt + 2 * BM + row_in_tile;
         asm volatile("bar.sync 1, 512;" ::: "memory");
         uint32_t n_it = 0;
+        bool pre_ok = false;
         for (int rd = 0; rd < rounds; ++rd) {
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             int64_t row;                                  // global frame index n = b*W + w, or N when this lane has no frame
@@ -1310,7 +1311,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
                 const uint32_t as = n_it & 1, ph = (n_it >> 1) & 1;
                 if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 0, n_it);   // epilogue: about to wait for the accumulator
-                mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
+                if (!pre_ok) mbar_wait(smem_u32(&bars->tmem_full[as]), ph);   // (pre_ok: seen complete before the last slab of the previous tile was scanned)
                 if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 1, n_it);   // epilogue: accumulator visible
                 tc_fence_after();
                 if (kFuse && nt == 0) {                   // the converter published this tile's bands before the first MMA could start
@@ -1349,6 +1350,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             else mbar_arrive(smem_u32(&bars->tmem_empty[as]));
                             if (ew == 0 || ew == 13) VQB_TRACE(4 + (ew != 0), 2, n_it);                   // epilogue: stage released
                         }
+                        // a first look at the NEXT accumulator before this slab is scanned: with a small codebook the epilogue is the
+                        // slower side, the next accumulator is nearly always complete, and the look's latency hides behind the scan
+                        pre_ok = mbar_test(smem_u32(&bars->tmem_full[(n_it + 1u) & 1u]), ((n_it + 1u) >> 1) & 1u);
                     }
                     if (scores_dbg) {
                         if (row < N) dump_slab(ra, code0 + sb * 32, K, scores_dbg + (size_t)row * K);
