@@ -474,11 +474,13 @@ bool tail3_supports(int D) { return D % 32 == 0 && (D / 32 <= 4 || D == 192 || D
 // Lanes per frame (decides the permutation of the codebook copy and of the residual replicas).  VQB_TAIL_LPF (experiments) overrides
 // where the shape allows it.
 int tail3_lpf(int D) {
-    int lpf = D >= 192 ? 8 : (D >= 96 ? 8 : 4);
+    int lpf = D >= 96 ? 8 : 4;   // measured: D = 64 / 32 want fewer lanes per frame (per-frame bookkeeping), D = 128 is equal with 4 and 8
     const int v = env_get(ENV_TAIL_LPF, 0);
     if ((v == 2 || v == 4 || v == 8) && D % (4 * v) == 0 && D / v <= 32 && (v != 2 || D <= 64) && (v != 4 || D <= 128)) lpf = v;
     return lpf;
 }
+// Measured against tail2_kernel (profiles/r03_exp_tail_forms.jsonl, r03_exp_tail3_ahead*.jsonl): D = 256 -10 %, D = 128 -10 %; at D = 64 the two
+// are within the +-5 % run-to-run spread of each other (r03_exp_tail_address_alias.jsonl), so every supported D takes this kernel.
 bool tail3_preferred(int D) { return tail3_supports(D); }
 
 // `ep`: the permuted fp32 codebook (codebook_prep_kernel, tail3_lpf(D)); `resid_rep`: n_rep zeroed copies of [K, D] in the workspace
