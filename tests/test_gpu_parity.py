@@ -257,6 +257,36 @@ def test_tail3_lanes_per_frame_agree_with_the_oracle(D, lpf, experiment_env):
     np.testing.assert_allclose(vq.codebook.weight.grad.cpu().numpy(), dE, rtol=1e-4, atol=1e-6 * np.abs(dE).max())
 
 
+@pytest.mark.parametrize("env", [{}, {"VQB_TC_EPI": "1"}, {"VQB_TC_EVSM": "-2"}, {"VQB_TC_EVSM": "0"}])
+@pytest.mark.parametrize("K", [512, 1024, 4096])
+def test_adversarial_code_order_floods_the_event_stacks(K, env, experiment_env):
+    """Codes ordered so that a frame's score keeps improving along the codebook sweep: nearly every 8-code chunk is a new running
+    maximum, the per-thread event stacks run through all their levels (own shared-memory slots, the warp's overflow pool, global
+    scratch) and many frames fall back to the exact search - the result must still be the oracle's.  Also with the grouped epilogue
+    (per-warp queues, a flooding lane must only lose itself), without the pool and without shared-memory slots."""
+    if env:
+        experiment_env(**env)
+    B, D, W, beta = 2, 64, 2048, 0.25
+    rng = np.random.default_rng(31)
+    u = rng.standard_normal(D).astype(np.float32)
+    u /= np.linalg.norm(u)
+    # random codes SORTED by their projection on the direction u all flooding latents share: a frame's score improves along the sweep
+    # (a new running maximum in nearly every chunk) while the final candidates stay few (the top projections are well separated)
+    cb = seeded(30, (K, D))
+    cb = np.ascontiguousarray(cb[np.argsort(cb @ u)])
+    a = rng.uniform(3.0, 6.0, (B, 1, W)).astype(np.float32)
+    z = (a * u[None, :, None] + 0.05 * rng.standard_normal((B, D, W))).astype(np.float32)
+    z[1, :, ::2] = seeded(32, (D, W // 2))            # half of the second item: ordinary latents between flooding neighbours
+    ref = O.vq_forward(z, cb, beta)
+    vq, zt, (emb, com, q, ppl, enc, idx) = run_module(z, cb, beta, "bf16")
+    got = idx.reshape(-1).cpu().numpy()
+    n_bad = assert_index_parity(got, z, cb, ref.indices, ref.margin, ref.eps)
+    np.testing.assert_allclose(emb.item(), ref.embedding_loss, rtol=LOSS_RTOL)
+    if n_bad == 0:
+        assert np.array_equal(q.detach().cpu().numpy(), ref.quantized)
+        np.testing.assert_allclose(ppl.item(), ref.perplexity, rtol=LOSS_RTOL)
+
+
 def test_stage_timing_reports_every_stage_of_the_forward():
     """vqb_debug_stage_time_ms (bench.py's roofline legs): one timed launch per stage and forward, durations positive."""
     import ctypes as C
