@@ -154,11 +154,20 @@ tail3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__
         float2* pr = pairres + warp * (FW * kPairMax);
         // shortlist length (lane u < FW holds frame fbase + u) and shortlist (two lanes per frame) of a tile: fetched ONE TILE AHEAD into
         // registers - at the top of a tile these loads were the longest single stall of the pass (12.8 % of the samples)
-        auto fetch_lists = [&](int tile, int& cnt, uint4& v) {
+        // (batch item, tile inside the item) of this warp's current tile, advanced by the grid stride without a division per tile
+        // (three divisions per tile were 8 % of the instructions at D = 64)
+        const int qs = tstep / tiles_per_item, rs = tstep - qs * tiles_per_item;
+        int pb = tile0 / tiles_per_item, pt = tile0 - pb * tiles_per_item;
+        auto advance = [&](int& b_, int& t_) {
+            b_ += qs;
+            t_ += rs;
+            if (t_ >= tiles_per_item) { t_ -= tiles_per_item; ++b_; }
+        };
+        auto fetch_lists = [&](int tile, int b, int t_in, int& cnt, uint4& v) {
             cnt = 0;
             v = make_uint4(0u, 0u, 0u, 0u);
             if (tile >= num_tiles) return;
-            const int b = tile / tiles_per_item, w0 = (tile - b * tiles_per_item) * TF;
+            const int w0 = t_in * TF;
             const int64_t n0 = (int64_t)b * W + w0;
             const int wlim = (int)((W - w0) < TF ? (W - w0) : TF);
             if (lane < FW && fbase + lane < wlim) cnt = idx32 ? kCandFinal : (int)cand_cnt[n0 + fbase + lane];
@@ -171,17 +180,18 @@ tail3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__
         constexpr bool pf = kAhead, foldx2 = kAhead;
         int cnt_nx;
         uint4 v_nx;
-        if (pf) fetch_lists(tile0, cnt_nx, v_nx);
+        if (pf) fetch_lists(tile0, pb, pt, cnt_nx, v_nx);
         uint32_t it = 0;
         for (int tile = tile0; tile < num_tiles; tile += tstep, ++it) {
             const int buf = (int)(it & 1u);
-            const int b = tile / tiles_per_item, w0 = (tile - b * tiles_per_item) * TF;
+            const int b = pb, w0 = pt * TF;
             const int64_t n0 = (int64_t)b * W + w0;    // global frame id of the tile's first frame
             const int wlim = (int)((W - w0) < TF ? (W - w0) : TF);
-            if (!pf) fetch_lists(tile, cnt_nx, v_nx);
+            advance(pb, pt);                           // (pb, pt) now is the position of tile + tstep
+            if (!pf) fetch_lists(tile, b, w0 / TF, cnt_nx, v_nx);
             const int cnt_l = cnt_nx;
             if (lane < 2 * FW) reinterpret_cast<uint4*>(sC + (fbase + (lane >> 1)) * kCandMax)[lane & 1] = v_nx;
-            if (pf) fetch_lists(tile + tstep, cnt_nx, v_nx);
+            if (pf) fetch_lists(tile + tstep, pb, pt, cnt_nx, v_nx);
             const int np_l = (cnt_l != kCandFinal && cnt_l > 1) ? cnt_l : 0;
             int incl_l = np_l;
 #pragma unroll
