@@ -571,9 +571,9 @@ __device__ __forceinline__ void trace_ev(unsigned long long* base, int role, int
 //               128-byte-swizzled TMA boxes [D dims][32 frames] (an MN-major operand: no conversion, no copy); the codebook tiles are
 //               fp32 boxes [codes][32 dims].  Warp 19 only loads A tiles, warp 18 measures |x| and |x - tf32(x)| of the landed tile
 //               (guard band) and then releases it to the MMA issuer.  tf32 runs at half the bf16 tensor rate, the band is ~3x tighter.
-// kRing = true (needs kFuse, no kTail): the grouped epilogue with per-warp chunk queues (scan_slab_q) instead of per-thread stacks;
+// kGrouped = true (needs kFuse, no kTail): the grouped epilogue with per-warp chunk queues (scan_slab_q) instead of per-thread stacks;
 //               chosen by tc_plan for small codebooks (K <= 1024).
-template <bool kTwo, bool kFuse, bool kTail, bool kTf32 = false, bool kRing = false>
+template <bool kTwo, bool kFuse, bool kTail, bool kTf32 = false, bool kGrouped = false>
 __global__ void __launch_bounds__(kTail ? NUM_THREADS_TAIL : NUM_THREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_e,
                  const __grid_constant__ CUtensorMap tmap_eh, const __grid_constant__ CUtensorMap tmap_xt, const __nv_bfloat16* __restrict__ eh, int64_t W, int tiles_per_item, int D,
@@ -581,11 +581,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
-                 const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots, const int ring_cap) {
+                 const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots, const int wq_cap) {
     VQB_TRACE_INIT();
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     static_assert(!kTf32 || (kFuse && !kTail), "tf32 reads the fp32 latents in place; no fused tail");
-    static_assert(!kRing || (kFuse && !kTail), "the grouped epilogue reads the guard bands from shared memory; no fused tail");
+    static_assert(!kGrouped || (kFuse && !kTail), "the grouped epilogue reads the guard bands from shared memory; no fused tail");
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t a_slot_bytes = kTf32 ? (uint32_t)BM * (uint32_t)D * 4u : (uint32_t)A_CHUNK_BYTES;   // tf32: a_slots whole fp32 tiles
     unsigned char* sA = smem;                                            // a_slots x 16 KiB (tf32: a_slots x 128 D x 4 bytes)
@@ -601,11 +601,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
     uint32_t* sEv = reinterpret_cast<uint32_t*>(sCnt + 3 * BM);          // [512][ev_sm] shared-memory part of the event stacks
     // fused tail: the shortlists of two frame tiles (the epilogue fills one while the tail warps consume the other)
-    // grouped epilogue: [16 warps][ring_cap] queue entries, then the tile's shortlists [128][kCandMax] (written out as 32-byte rows)
-    // per-thread stacks: [16 warps][ring_cap] overflow pool entries of the warps (same 48-byte entries)
-    unsigned char* sRing = reinterpret_cast<unsigned char*>(sEv + (size_t)EPI_THREADS * ev_sm * EV_WORDS);
-    uint16_t* sList = reinterpret_cast<uint16_t*>(sRing + (size_t)EPI_WARPS * ring_cap * Q_ENTRY);
-    uint32_t* sPoolCnt = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(sList) + (kRing ? BM * kCandMax * 2 : 0));   // [16] pool fills
+    // grouped epilogue: [16 warps][wq_cap] queue entries, then the tile's shortlists [128][kCandMax] (written out as 32-byte rows)
+    // per-thread stacks: [16 warps][wq_cap] overflow pool entries of the warps (same 48-byte entries)
+    unsigned char* sWarpQ = reinterpret_cast<unsigned char*>(sEv + (size_t)EPI_THREADS * ev_sm * EV_WORDS);
+    uint16_t* sList = reinterpret_cast<uint16_t*>(sWarpQ + (size_t)EPI_WARPS * wq_cap * Q_ENTRY);
+    uint32_t* sPoolCnt = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(sList) + (kGrouped ? BM * kCandMax * 2 : 0));   // [16] pool fills
     uint16_t* sCand = reinterpret_cast<uint16_t*>(sPoolCnt + 2 * EPI_WARPS);   // (128 bytes: what follows keeps its alignment) [2][128][kCandFill] codes
     uint8_t* sCandCnt = reinterpret_cast<uint8_t*>(sCand + (kTail ? 2 * BM * kCandFill : 0));   // [2][128] 0 = not for the tail
     float2* sPair = reinterpret_cast<float2*>(sCandCnt + (kTail ? 2 * BM : 0));                  // [4][32] (distance, code) hand-back
@@ -663,7 +663,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->tmem_full[i]), 1);
             // 2-CTA: both CTAs' epilogues report to the leader; grouped epilogue: only the 8 warps of a stage's group read it
-            mbar_init(smem_u32(&bars->tmem_empty[i]), (kTwo ? 2 : 1) * (kRing ? EPI_WARPS / 2 : EPI_WARPS));
+            mbar_init(smem_u32(&bars->tmem_empty[i]), (kTwo ? 2 : 1) * (kGrouped ? EPI_WARPS / 2 : EPI_WARPS));
         }
         fence_barrier_init();
     }
@@ -1126,7 +1126,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             atomicAdd(&meta->rescored, (unsigned long long)(c[0] + c[2] + c[4] + c[6]));
             atomicAdd(&meta->shortlisted, (unsigned long long)(c[1] + c[3] + c[5] + c[7]));
         }
-    } else if (kRing && warp < EPI_WARPS) {
+    } else if (kGrouped && warp < EPI_WARPS) {
         // ================================================================ grouped epilogue (small codebooks)
         const int ew = warp - EPI_WARP0;
         const uint32_t grp = (uint32_t)ew >> 3;   // the accumulator stage this warp reads: tiles with n_it % 2 == grp
@@ -1137,7 +1137,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
         const bool force_fallback = meta->cb_nonfinite != 0;
         int* smax = sCnt + 2 * BM + row_in_tile;  // pooled running maximum of the frame (ordered int)
-        const uint32_t q_u = smem_u32(sRing + (size_t)ew * ring_cap * Q_ENTRY);
+        const uint32_t q_u = smem_u32(sWarpQ + (size_t)ew * wq_cap * Q_ENTRY);
         if (slot4 == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; *smax = f2ord(-INFINITY); }
         asm volatile("bar.sync 1, 512;" ::: "memory");
         const bool tr = lane == 0 && (ew == 0 || ew == 8);   // trace: first warp of each group
@@ -1185,15 +1185,15 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 tmem_ld_wait(ra);
                 tmem_ld32(taddr + 32, rb);
                 if (tr) VQB_TRACE(6 + (ew != 0), 0, n_it);
-                scan_slab_q(ra, chunk0, hband, thr, mymax, smax, q_u, (uint32_t)ring_cap, qn, mine, lane);
+                scan_slab_q(ra, chunk0, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, qn, mine, lane);
                 tmem_ld_wait(rb);
                 tmem_ld32(taddr + 64, ra);
                 if (tr) VQB_TRACE(6 + (ew != 0), 1, n_it);
-                scan_slab_q(rb, chunk0 + 4, hband, thr, mymax, smax, q_u, (uint32_t)ring_cap, qn, mine, lane);
+                scan_slab_q(rb, chunk0 + 4, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, qn, mine, lane);
                 tmem_ld_wait(ra);
                 tmem_ld32(taddr + 96, rb);
                 if (tr) VQB_TRACE(6 + (ew != 0), 2, n_it);
-                scan_slab_q(ra, chunk0 + 8, hband, thr, mymax, smax, q_u, (uint32_t)ring_cap, qn, mine, lane);
+                scan_slab_q(ra, chunk0 + 8, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, qn, mine, lane);
                 tmem_ld_wait(rb);
                 // the last slab of this accumulator stage is in registers: hand the stage back before scanning it
                 tc_fence_before();
@@ -1203,7 +1203,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     else mbar_arrive(smem_u32(&bars->tmem_empty[grp]));
                 }
                 if (tr) VQB_TRACE(trole, 2, n_it);
-                scan_slab_q(rb, chunk0 + 12, hband, thr, mymax, smax, q_u, (uint32_t)ring_cap, qn, mine, lane);
+                scan_slab_q(rb, chunk0 + 12, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, qn, mine, lane);
                 if (tr) VQB_TRACE(6 + (ew != 0), 3, n_it);
             }
             // ---- end of the round: the four warps that share these 32 frames meet (the other lane quarters run on), every warp deals
@@ -1214,11 +1214,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
             if (tr) VQB_TRACE(trole, 6, n_it);
             {
-                if (qn > (uint32_t)ring_cap) {    // queue overflow: some frame of this quarter lost an event - all 32 go to the exact search
+                if (qn > (uint32_t)wq_cap) {    // queue overflow: some frame of this quarter lost an event - all 32 go to the exact search
                     sCnt[BM + row_in_tile] = 1;
-                    qn = (uint32_t)ring_cap;
+                    qn = (uint32_t)wq_cap;
                 }
-                const unsigned char* qb = sRing + (size_t)ew * ring_cap * Q_ENTRY;
+                const unsigned char* qb = sWarpQ + (size_t)ew * wq_cap * Q_ENTRY;
                 for (uint32_t e = (uint32_t)lane; e < qn; e += 32u) {
                     const unsigned char* en = qb + (size_t)e * Q_ENTRY;
                     const uint2 hd = *reinterpret_cast<const uint2*>(en + 32);
@@ -1283,9 +1283,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         ev.sm = ev_sm;
         ev.n = 0;
         ev.ng = 0;
-        ev.pool_u = smem_u32(sRing + (size_t)ew * ring_cap * Q_ENTRY);
+        ev.pool_u = smem_u32(sWarpQ + (size_t)ew * wq_cap * Q_ENTRY);
         ev.pool_cnt_u = smem_u32(sPoolCnt + ew);
-        ev.pool_cap = (kFuse && !kTail) ? (uint32_t)ring_cap : 0u;   // (the pool's resolution reads the bands and writes global shortlists)
+        ev.pool_cap = (kFuse && !kTail) ? (uint32_t)wq_cap : 0u;   // (the pool's resolution reads the bands and writes global shortlists)
         ev.lane = (uint32_t)lane;
         if (lane == 0) sPoolCnt[ew] = 0u;
         if (colq == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; sCnt[2 * BM + row_in_tile] = f2ord(-INFINITY); }
@@ -1443,15 +1443,15 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (lost) sCnt[BM + row_in_tile] = 1;
             }
             if (lane == 0 && ew == 0) VQB_TRACE(7, 2, n_it);
-            if (kFuse && !kTail && ring_cap > 0 && !scores_dbg) {
+            if (kFuse && !kTail && wq_cap > 0 && !scores_dbg) {
                 // the warp's overflow pool: entries dealt one per lane; an entry belongs to the frame of the lane that appended it
                 uint32_t pn;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pn) : "r"(ev.pool_cnt_u) : "memory");
-                if (pn > (uint32_t)ring_cap) pn = (uint32_t)ring_cap;
+                if (pn > (uint32_t)wq_cap) pn = (uint32_t)wq_cap;
                 for (uint32_t e0 = 0; e0 < pn; e0 += 32u) {
                     const uint32_t e = e0 + (uint32_t)lane;
                     const bool act = e < pn;
-                    const uint32_t* en = reinterpret_cast<const uint32_t*>(sRing + ((size_t)ew * ring_cap + (act ? e : 0u)) * Q_ENTRY);
+                    const uint32_t* en = reinterpret_cast<const uint32_t*>(sWarpQ + ((size_t)ew * wq_cap + (act ? e : 0u)) * Q_ENTRY);
                     const uint4 hd = *reinterpret_cast<const uint4*>(en + 8);            // chunk maximum, chunk id, lane, 0
                     const int src = act ? (int)hd.z : 0;
                     const int64_t row_e = __shfl_sync(0xffffffffu, row, src);            // global frame of that lane (N: none)
@@ -1621,8 +1621,8 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 // One function decides for the launcher AND for the callers that must know beforehand whether a variant fits
 // (tc_can_fuse, tc_fused_tail_fits).
 struct TcPlan {
-    bool ok, two, ring;   // ring: grouped epilogue (ring_cap = queue entries per warp); else ring_cap = overflow-pool entries per warp
-    int cs, a_slots, b_stages, ev_sm, eh_slots, ring_cap;
+    bool ok, two, grouped;   // grouped: grouped epilogue (wq_cap = queue entries per warp); else wq_cap = overflow-pool entries per warp
+    int cs, a_slots, b_stages, ev_sm, eh_slots, wq_cap;
     size_t smem;
 };
 
@@ -1671,16 +1671,16 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
     const size_t ev_entry_bytes = (size_t)EPI_THREADS * EV_WORDS * 4;   // one entry for every epilogue thread: 24 KiB
     const size_t pool_entry_bytes = (size_t)EPI_WARPS * Q_ENTRY;        // one pool entry for every epilogue warp: 768 bytes
     p.ev_sm = 0;
-    p.ring_cap = 0;
-    size_t ring_bytes = 0;
+    p.wq_cap = 0;
+    size_t wq_bytes = 0;
     if (!with_tail && !dbg && 227 * 1024 > fixed + 4 * stage_bytes) {
         const size_t room = 227 * 1024 - fixed - 4 * stage_bytes;
         const bool pool_ok = fuse && env_get(ENV_TC_EVSM, -1) != -2;        // VQB_TC_EVSM=-2 (experiments): no pool
-        if (pool_ok && room >= 2 * ev_entry_bytes + 32 * pool_entry_bytes) { p.ev_sm = 2; p.ring_cap = 32; }
-        else if (pool_ok && room >= 2 * ev_entry_bytes + 16 * pool_entry_bytes) { p.ev_sm = 2; p.ring_cap = 16; }
-        else if (pool_ok && room >= ev_entry_bytes + 32 * pool_entry_bytes) { p.ev_sm = 1; p.ring_cap = 32; }
+        if (pool_ok && room >= 2 * ev_entry_bytes + 32 * pool_entry_bytes) { p.ev_sm = 2; p.wq_cap = 32; }
+        else if (pool_ok && room >= 2 * ev_entry_bytes + 16 * pool_entry_bytes) { p.ev_sm = 2; p.wq_cap = 16; }
+        else if (pool_ok && room >= ev_entry_bytes + 32 * pool_entry_bytes) { p.ev_sm = 1; p.wq_cap = 32; }
         else { p.ev_sm = (int)(room / ev_entry_bytes); if (p.ev_sm > 3) p.ev_sm = 3; }
-        ring_bytes = (size_t)p.ring_cap * pool_entry_bytes;
+        wq_bytes = (size_t)p.wq_cap * pool_entry_bytes;
     }
     if (const int v = env_get(ENV_TC_EVSM, -1); v >= 0 && v < p.ev_sm) p.ev_sm = v;   // experiments
     // Grouped epilogue (small codebooks, K <= 1024; see scan_slab_q): per-warp chunk queues + the tile's shortlists + queue fills instead
@@ -1692,10 +1692,10 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
         if (227 * 1024 > base) {
             int cap = (int)((227 * 1024 - base) / ((size_t)EPI_WARPS * Q_ENTRY));
             if (cap > 96) cap = 96;
-            if (cap >= 48) { p.ring = true; p.ring_cap = cap; p.ev_sm = 0; ring_bytes = (size_t)EPI_WARPS * cap * Q_ENTRY + list_bytes; }
+            if (cap >= 48) { p.grouped = true; p.wq_cap = cap; p.ev_sm = 0; wq_bytes = (size_t)EPI_WARPS * cap * Q_ENTRY + list_bytes; }
         }
     }
-    const size_t fixed_ev = fixed + (size_t)p.ev_sm * ev_entry_bytes + ring_bytes;
+    const size_t fixed_ev = fixed + (size_t)p.ev_sm * ev_entry_bytes + wq_bytes;
     p.b_stages = fixed_ev < 227 * 1024 ? (int)((227 * 1024 - fixed_ev) / stage_bytes) : 0;
     if (p.b_stages > (p.two ? 8 : 4)) p.b_stages = p.two ? 8 : 4;
     if (const int v = env_get(ENV_TC_STAGES, 0); v >= 2 && v < p.b_stages) p.b_stages = v;   // experiments
@@ -1791,7 +1791,7 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     const int num_m_tiles = fuse ? B * tiles_per_item : (int)(N_pad / BM);
     const int num_n_tiles = K_pad / BN;
     const TcPlan plan = tc_plan(fuse, with_tail, scores_dbg != nullptr, num_m_tiles, D, tf32, K_pad);
-    const bool ring = plan.ring;
+    const bool grouped = plan.grouped;
     if (!plan.ok) { set_error("tc_search: D=%d does not fit the shared-memory pipeline", D); return VQB_E_SHAPE; }
     const bool two = plan.two;
     const int cs = plan.cs, a_slots = plan.a_slots, b_stages = plan.b_stages, ev_sm = plan.ev_sm;
@@ -1841,11 +1841,11 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
 #define VQB_TC_LAUNCH(TWO, FUSE, TAIL, ...)                                                                                                  \
     le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL, ##__VA_ARGS__>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
                             num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \
-                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, ev_sm, l2_once, plan.eh_slots, plan.ring_cap)
-    if (ring && tf32 && two) VQB_TC_LAUNCH(true, true, false, true, true);
-    else if (ring && tf32) VQB_TC_LAUNCH(false, true, false, true, true);
-    else if (ring && two) VQB_TC_LAUNCH(true, true, false, false, true);
-    else if (ring) VQB_TC_LAUNCH(false, true, false, false, true);
+                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, ev_sm, l2_once, plan.eh_slots, plan.wq_cap)
+    if (grouped && tf32 && two) VQB_TC_LAUNCH(true, true, false, true, true);
+    else if (grouped && tf32) VQB_TC_LAUNCH(false, true, false, true, true);
+    else if (grouped && two) VQB_TC_LAUNCH(true, true, false, false, true);
+    else if (grouped) VQB_TC_LAUNCH(false, true, false, false, true);
     else if (tf32 && two) VQB_TC_LAUNCH(true, true, false, true);
     else if (tf32) VQB_TC_LAUNCH(false, true, false, true);
     else if (two && with_tail) VQB_TC_LAUNCH(true, true, true);
