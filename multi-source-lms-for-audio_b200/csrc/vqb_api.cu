@@ -181,12 +181,16 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
     float* ep = (D % 32 == 0) ? reinterpret_cast<float*>(ws + L.ep) : nullptr;
 
     void* tprep = stage_timing_begin(s, VQB_STAGE_PREP);
+    // ONE memset over the workspace regions that start a call at zero - meta | (e2, rewritten by codebook_prep) | counts | SSE partials |
+    // residual-sum replicas lie back to back (ws_layout) - instead of four: small batches are launch-bound
+    const int n_rep = resid ? resid_replicas(K, D) : 0;
+    const size_t zero_end = resid_rep ? L.resid_rep + (size_t)n_rep * K * D * 4 : L.sse_partials + (size_t)L.n_partials * sizeof(double);
     if (!accumulate) {
-        VQB_CUDA(cudaMemsetAsync(meta, 0, sizeof(WsMeta), s), "memset meta");
-        VQB_CUDA(cudaMemsetAsync(counts, 0, (size_t)K * 4, s), "memset counts");
+        VQB_CUDA(cudaMemsetAsync(ws + L.meta, 0, zero_end - L.meta, s), "memset workspace head");
         if (resid) VQB_CUDA(cudaMemsetAsync(resid, 0, (size_t)K * D * 4, s), "memset resid");
-    } else {
+    } else {                                      // the host-buffer path accumulates counts / statistics over its chunks
         VQB_CUDA(cudaMemsetAsync(&meta->fallback_count, 0, sizeof(int), s), "memset fallback_count");
+        VQB_CUDA(cudaMemsetAsync(ws + L.sse_partials, 0, zero_end - L.sse_partials, s), "memset partials + replicas");
     }
 
     if (prec == VQB_PREC_FP32) {
@@ -219,7 +223,6 @@ int forward_impl(const float* z, const float* codebook, int B, int D, int64_t W,
         double* part_d = reinterpret_cast<double*>(part);
         TailArgs targs{z, codebook, e2, idx_out, (flags & VQB_WANT_Q) ? q_out : nullptr, counts, resid, part_d};
         if (!fuse) VQB_CUDA(launch_latent_prep_bf16(z, B, D, W, L.n_pad, xb, x2, meta, s), "latent_prep");
-        if (fused_tail) VQB_CUDA(cudaMemsetAsync(part, 0, (size_t)L.n_partials * sizeof(double), s), "memset sse partials");
         stage_timing_end(tprep, s);
         rc = launch_tc_search(fuse ? z : nullptr, B, W, xb, eb, eh, x2, N, L.n_pad, K, L.k_pad, D, cand_cnt, cand_idx, fb_rows, meta, best64,
                               scores_dbg, ws + L.ev, fused_tail ? &targs : nullptr, tf32 ? codebook : nullptr, s);

@@ -1016,9 +1016,9 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
                         const int* idx32, const uint8_t* cand_cnt, const uint16_t* cand_idx, int64_t* idx_out, float* q_out,
                         int* counts, float* resid, float* sse_partials, int n_partials, WsMeta* meta, float* resid_rep, cudaStream_t s,
                         const float* ep) {
+    // the caller (forward_impl) zeroed the SSE partials and resid_replicas(K, D) residual-sum replicas with the head of the workspace
     const int64_t N = (int64_t)B * W;
-    cudaError_t e = cudaMemsetAsync(sse_partials, 0, (size_t)n_partials * sizeof(double), s);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
     double* part = reinterpret_cast<double*>(sse_partials);
     const size_t rep_stride = (size_t)K * D;
     int n_rep = (resid && resid_rep) ? resid_replicas(K, D) : 1;
@@ -1026,12 +1026,10 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
     if (((form == 3 && tail3_preferred(D)) || form == 300) && ep && tail_tma_enabled() && tail3_supports(D) && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
         (!q_out || (reinterpret_cast<uintptr_t>(q_out) & 15) == 0)) {
         // all n_rep residual-sum replicas live in the workspace (permuted layout); their un-permuted sum is added to `resid`
-        if (resid && (!resid_rep || (e = cudaMemsetAsync(resid_rep, 0, (size_t)n_rep * rep_stride * 4, s)) != cudaSuccess))
-            return resid_rep ? e : cudaErrorInvalidValue;
+        if (resid && !resid_rep) return cudaErrorInvalidValue;
         return launch_tail3(z, ep, e2, B, D, W, K, idx32, cand_cnt, cand_idx, idx_out, q_out, counts, resid, part, n_partials, meta, resid_rep,
                             n_rep, s);
     }
-    if (n_rep > 1 && (e = cudaMemsetAsync(resid_rep, 0, (size_t)(n_rep - 1) * rep_stride * 4, s)) != cudaSuccess) return e;
     auto fold = [&]() -> cudaError_t {            // sum the residual replicas into the caller's buffer
         if (n_rep <= 1) return cudaSuccess;
         const size_t blocks = (rep_stride + 255) / 256;
