@@ -336,24 +336,25 @@ __device__ __forceinline__ void scan_slab(const uint32_t (&r)[32], int chunk0, f
     }
 }
 
-// ---- small codebooks (K <= 1024): two epilogue groups + per-WARP chunk queues in shared memory ------------------------------------
+// ---- small codebooks (K <= 1024): per-WARP slab queues in shared memory ------------------------------------------------------------
 // What the hand-off timeline (scripts/trace_tc.py, profiles/r03_trace_cfg2_*.txt) showed for the per-thread stacks at K = 1024, D = 64:
-// a frame-tile round of 12 700 cycles = 4 tiles x ~1 600 (all 16 warps wait for the same accumulator, read it at the same time - the
-// TMEM read of a slab takes ~200 cycles under that contention - and then run ~100 dependent instructions per slab, four warps per
-// scheduler in lock-step) + 5 450 cycles of end-of-round resolution (two 512-thread barriers around dependent L2 round trips to the
-// stack entries that did not fit shared memory); the tensor core needs 640 cycles per tile.  This form
-//  * splits the 16 epilogue warps into two groups of 8, one per accumulator stage: group g reads every tile with n_it % 2 = g, four
-//    32-column slabs per warp, the load of slab s + 1 in flight behind the scan of slab s - the groups run out of phase, so TMEM reads
-//    and scans of different warps overlap, and a warp waits for an accumulator half as often;
-//  * appends events as 8-code chunks (raw accumulators, chunk maximum, chunk id | lane) to a queue of the WARP (slot by shared-memory
-//    atomic), so the end-of-round resolution is one pass in which the queue's entries are dealt one per lane - no per-thread stacks,
-//    nothing in global memory, barriers of the 128 threads that share 32 frames instead of all 512;
-//  * takes the group's first tile of a round twice (maximum first), and pools the running maximum of a frame's four threads through
-//    shared memory once per tile.
-constexpr int Q_ENTRY = 48;        // bytes: 8 raw accumulators, (chunk maximum, chunk id | lane << 16), 8 pad: 16-byte aligned rows
-constexpr int Q_LANE_CAP = 12;     // entries one lane may append per round: a frame that floods (adversarial code order) only loses itself
-__device__ __forceinline__ void scan_slab_q(const uint32_t (&r)[32], int chunk0, float hband, float& thr, float& mymax, int* smax, uint32_t q_u,
-                                            uint32_t q_cap, uint32_t& qn, int& mine, int lane) {
+// a frame-tile round of 12 000 cycles = 4 tiles x ~1 600 (the scan phases are issue-bound: ~100 instructions per 32-column slab and
+// warp, four warps per scheduler in lock-step, because with a small codebook a 32-frame x 32-code slab nearly always holds an event
+// and the four predicated chunk appends run for every slab) + ~3 500 cycles of end-of-round resolution; the tensor core needs 640
+// cycles per tile.  This form keeps the lock-step of all 16 warps (the thread-level parallelism the scan needs; a split into two
+// groups of 8 warps made the scan latency-bound at the same throughput) and makes both parts cheaper:
+//  * a lane whose slab maximum reaches its threshold stores the slab RAW (32 accumulators + maximum + first code | lane) as ONE entry
+//    of its warp's queue - slot by ballot prefix, the fill is a warp-uniform register, no atomics, no per-chunk bookkeeping;
+//  * the pooled running maximum of a frame's four threads is read once per tile, not once per slab;
+//  * at the end of the round the queue's entries are dealt one per lane, whatever frame they belong to: 32 compares into a bit mask,
+//    ONE shared-memory atomic for the entry's shortlist positions; barriers of the 128 threads that share 32 frames;
+//  * a full queue spills into the warp's global scratch (never a fall-back of 32 frames at once); a lane that floods only loses itself.
+constexpr int Q_ENTRY = 48;        // overflow-pool entries of the per-thread stacks: 8 raw accumulators, (chunk maximum, chunk id, lane, 0)
+constexpr int SQ_ENTRY = 144;      // slab-queue entries: 32 raw accumulators, (slab maximum, first code | lane << 16), 8 pad (16-byte reads stay conflict-free)
+constexpr int SQ_LANE_CAP = 16;    // entries one lane may append per round: a frame that floods (adversarial code order) only loses itself
+constexpr int SQ_SPILL = 256;      // entries per warp in global scratch behind the shared-memory queue
+__device__ __forceinline__ void scan_slab_sq(const uint32_t (&r)[32], int code0, float hband, float& thr, float& mymax, int* smax, uint32_t q_u,
+                                             uint32_t q_cap, unsigned char* spill, uint32_t& qn, int& mine, int lane) {
     float t[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {      // depth-3 trees (the chain form of slab_max32 is 16 dependent instructions)
@@ -362,37 +363,34 @@ __device__ __forceinline__ void scan_slab_q(const uint32_t (&r)[32], int chunk0,
         t[g] = fmaxf(fmaxf(fmaxf(m0, m1), __uint_as_float(r[g * 8 + 6])), __uint_as_float(r[g * 8 + 7]));
     }
     const float m = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
-    const bool hit = m >= thr;
-    if (__any_sync(0xffffffffu, hit)) {
-        const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            // queue slot by ballot prefix: no atomics, and the fill `qn` stays a warp-uniform register
-            const bool want = hit && t[g] >= thr;
-            const bool hg = want && mine < Q_LANE_CAP;
-            if (want && !hg) mine = Q_LANE_CAP + 1;      // flooded: this frame goes to the exact search, it takes no more slots
-            const unsigned mk = __ballot_sync(0xffffffffu, hg);
-            if (mk) {
-                if (hg) {
-                    const uint32_t pos = qn + (uint32_t)__popc(mk & lt);
-                    if (pos < q_cap) {
-                        const uint32_t a = q_u + pos * Q_ENTRY;
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r[g * 8 + 0]), "r"(r[g * 8 + 1]), "r"(r[g * 8 + 2]),
-                                     "r"(r[g * 8 + 3])
-                                     : "memory");
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(r[g * 8 + 4]), "r"(r[g * 8 + 5]), "r"(r[g * 8 + 6]),
-                                     "r"(r[g * 8 + 7])
-                                     : "memory");
-                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 32), "r"(__float_as_uint(t[g])),
-                                     "r"((uint32_t)(chunk0 + g) | ((uint32_t)lane << 16))
-                                     : "memory");
-                    }
-                    mine += 1;
-                }
-                qn += (uint32_t)__popc(mk);              // may pass q_cap: the round then sends the warp's 32 frames to the exact search
-            }
-        }
+    const bool want = m >= thr;
+    if (__any_sync(0xffffffffu, want)) {
+        const bool hit = want && mine < SQ_LANE_CAP;
+        if (want && !hit) mine = SQ_LANE_CAP + 1;        // flooded: this frame goes to the exact search, it takes no more slots
+        const unsigned mk = __ballot_sync(0xffffffffu, hit);
         if (hit) {
+            const uint32_t pos = qn + (uint32_t)__popc(mk & ((1u << lane) - 1u));
+            const uint32_t hd1 = (uint32_t)code0 | ((uint32_t)lane << 16);
+            if (pos < q_cap) {
+                const uint32_t a = q_u + pos * SQ_ENTRY;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16 * q), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]),
+                                 "r"(r[4 * q + 3])
+                                 : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 128), "r"(__float_as_uint(m)), "r"(hd1) : "memory");
+            } else if (pos < q_cap + (uint32_t)SQ_SPILL) {
+                uint4* gdst = reinterpret_cast<uint4*>(spill + (size_t)(pos - q_cap) * SQ_ENTRY);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) gdst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                *reinterpret_cast<uint2*>(gdst + 8) = make_uint2(__float_as_uint(m), hd1);
+            } else {
+                mine = SQ_LANE_CAP + 1;                  // no room anywhere
+            }
+            mine += 1;
+        }
+        qn += (uint32_t)__popc(mk);
+        if (want) {
             thr = fmaxf(thr, m - hband);
             if (m > mymax) {
                 mymax = m;
@@ -571,7 +569,7 @@ __device__ __forceinline__ void trace_ev(unsigned long long* base, int role, int
 //               128-byte-swizzled TMA boxes [D dims][32 frames] (an MN-major operand: no conversion, no copy); the codebook tiles are
 //               fp32 boxes [codes][32 dims].  Warp 19 only loads A tiles, warp 18 measures |x| and |x - tf32(x)| of the landed tile
 //               (guard band) and then releases it to the MMA issuer.  tf32 runs at half the bf16 tensor rate, the band is ~3x tighter.
-// kGrouped = true (needs kFuse, no kTail): the grouped epilogue with per-warp chunk queues (scan_slab_q) instead of per-thread stacks;
+// kGrouped = true (needs kFuse, no kTail): the slab-queue epilogue (scan_slab_sq: per-warp queues of raw slabs) instead of per-thread stacks;
 //               chosen by tc_plan for small codebooks (K <= 1024).
 template <bool kTwo, bool kFuse, bool kTail, bool kTf32 = false, bool kGrouped = false>
 __global__ void __launch_bounds__(kTail ? NUM_THREADS_TAIL : NUM_THREADS, 1)
@@ -585,7 +583,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     VQB_TRACE_INIT();
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     static_assert(!kTf32 || (kFuse && !kTail), "tf32 reads the fp32 latents in place; no fused tail");
-    static_assert(!kGrouped || (kFuse && !kTail), "the grouped epilogue reads the guard bands from shared memory; no fused tail");
+    static_assert(!kGrouped || (kFuse && !kTail), "the slab-queue epilogue reads the guard bands from shared memory; no fused tail");
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t a_slot_bytes = kTf32 ? (uint32_t)BM * (uint32_t)D * 4u : (uint32_t)A_CHUNK_BYTES;   // tf32: a_slots whole fp32 tiles
     unsigned char* sA = smem;                                            // a_slots x 16 KiB (tf32: a_slots x 128 D x 4 bytes)
@@ -601,10 +599,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int* sCnt = reinterpret_cast<int*>(sMin + 4 * BM);                   // [128] shortlist fill per frame, [128] overflow flags,
     uint32_t* sEv = reinterpret_cast<uint32_t*>(sCnt + 3 * BM);          // [512][ev_sm] shared-memory part of the event stacks
     // fused tail: the shortlists of two frame tiles (the epilogue fills one while the tail warps consume the other)
-    // grouped epilogue: [16 warps][wq_cap] queue entries, then the tile's shortlists [128][kCandMax] (written out as 32-byte rows)
+    // slab-queue epilogue: [16 warps][wq_cap] queue entries of 144 bytes, then the tile's shortlists [128][kCandMax] (written out as 32-byte rows)
     // per-thread stacks: [16 warps][wq_cap] overflow pool entries of the warps (same 48-byte entries)
     unsigned char* sWarpQ = reinterpret_cast<unsigned char*>(sEv + (size_t)EPI_THREADS * ev_sm * EV_WORDS);
-    uint16_t* sList = reinterpret_cast<uint16_t*>(sWarpQ + (size_t)EPI_WARPS * wq_cap * Q_ENTRY);
+    uint16_t* sList = reinterpret_cast<uint16_t*>(sWarpQ + (size_t)EPI_WARPS * wq_cap * (kGrouped ? SQ_ENTRY : Q_ENTRY));
     uint32_t* sPoolCnt = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(sList) + (kGrouped ? BM * kCandMax * 2 : 0));   // [16] pool fills
     uint16_t* sCand = reinterpret_cast<uint16_t*>(sPoolCnt + 2 * EPI_WARPS);   // (128 bytes: what follows keeps its alignment) [2][128][kCandFill] codes
     uint8_t* sCandCnt = reinterpret_cast<uint8_t*>(sCand + (kTail ? 2 * BM * kCandFill : 0));   // [2][128] 0 = not for the tail
@@ -662,8 +660,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->tmem_full[i]), 1);
-            // 2-CTA: both CTAs' epilogues report to the leader; grouped epilogue: only the 8 warps of a stage's group read it
-            mbar_init(smem_u32(&bars->tmem_empty[i]), (kTwo ? 2 : 1) * (kGrouped ? EPI_WARPS / 2 : EPI_WARPS));
+            mbar_init(smem_u32(&bars->tmem_empty[i]), (kTwo ? 2 : 1) * EPI_WARPS);   // 2-CTA: both CTAs' epilogues report to the leader
         }
         fence_barrier_init();
     }
@@ -1127,111 +1124,105 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             atomicAdd(&meta->shortlisted, (unsigned long long)(c[1] + c[3] + c[5] + c[7]));
         }
     } else if (kGrouped && warp < EPI_WARPS) {
-        // ================================================================ grouped epilogue (small codebooks)
+        // ================================================================ slab-queue epilogue (small codebooks)
         const int ew = warp - EPI_WARP0;
-        const uint32_t grp = (uint32_t)ew >> 3;   // the accumulator stage this warp reads: tiles with n_it % 2 == grp
         const int quarter = warp & 3;             // TMEM lanes this warp may touch: 32*quarter .. +31
-        const int half = (ew >> 2) & 1;           // columns [128 half, 128 half + 128) of every tile: four 32-column slabs
-        const int slot4 = ew >> 2;                // which of the four threads of a frame this one is
+        const int colq = ew >> 2;                 // which 64-column quarter of every tile: two 32-column slabs
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
         const bool force_fallback = meta->cb_nonfinite != 0;
         int* smax = sCnt + 2 * BM + row_in_tile;  // pooled running maximum of the frame (ordered int)
-        const uint32_t q_u = smem_u32(sWarpQ + (size_t)ew * wq_cap * Q_ENTRY);
-        if (slot4 == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; *smax = f2ord(-INFINITY); }
+        const uint32_t q_u = smem_u32(sWarpQ + (size_t)ew * wq_cap * SQ_ENTRY);
+        unsigned char* spill = reinterpret_cast<unsigned char*>(ev_scratch + ((size_t)blockIdx.x * EPI_THREADS + (size_t)ew * 32) * (EV_CAP * EV_WORDS));
+        if (colq == 0) { sCnt[row_in_tile] = 0; sCnt[BM + row_in_tile] = 0; *smax = f2ord(-INFINITY); }
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        const bool tr = lane == 0 && (ew == 0 || ew == 8);   // trace: first warp of each group
+        const bool tr = lane == 0 && (ew == 0 || ew == 13);
         const int trole = 4 + (ew != 0);
         (void)tr; (void)trole;
         uint32_t n_it = 0;
+        bool pre_ok = false;
         for (int rd = 0; rd < rounds; ++rd) {
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             const int b = mt / tiles_per_item;
             const int64_t w = (int64_t)(mt - b * tiles_per_item) * BM + row_in_tile;
             const int64_t row = (mt < num_m_tiles && w < W) ? (int64_t)b * W + w : N;   // global frame index, or N: no frame
             float band = 0.f, hband = 0.f, thr = -INFINITY, mymax = -INFINITY;
-            bool first = true;
             uint32_t qn = 0;                      // fill of this warp's queue (warp-uniform)
             int mine = 0;                         // entries this lane appended
             for (int nt = 0; nt < num_n_tiles; ++nt, ++n_it) {
-                if ((n_it & 1u) != grp) continue;
-                const uint32_t ph = (n_it >> 1) & 1u;
+                const uint32_t as = n_it & 1u, ph = (n_it >> 1) & 1u;
                 if (tr) VQB_TRACE(trole, 0, n_it);
-                mbar_wait(smem_u32(&bars->tmem_full[grp]), ph);
+                if (!pre_ok) mbar_wait(smem_u32(&bars->tmem_full[as]), ph);
                 tc_fence_after();
                 if (tr) VQB_TRACE(trole, 1, n_it);
-                const uint32_t taddr = tmem_base + t_lane + grp * BN + (uint32_t)half * 128u;
-                const int chunk0 = (nt * BN + half * 128) >> 3;
+                const uint32_t taddr = tmem_base + t_lane + as * BN + (uint32_t)colq * COLS_PER_WARP;
+                const int code0 = nt * BN + colq * COLS_PER_WARP;
                 uint32_t ra[32], rb[32];
-                if (first) {                      // the converter published this tile's bands before the first MMA could start
+                if (nt == 0) {                    // the converter published this tile's bands before the first MMA could start
                     band = sBand[(rd & 3) * BM + row_in_tile];
                     hband = 0.5f * band;          // the band in accumulator units (acc = -score / 2)
-                    // the group's first tile of the round: its maximum first (the accumulator stays in TMEM), then the scan
-                    float pre = -INFINITY;
-#pragma unroll
-                    for (int sb = 0; sb < 4; ++sb) {
-                        tmem_ld32(taddr + sb * 32, ra);
-                        tmem_ld_wait(ra);
-                        pre = fmaxf(pre, slab_max32(ra));
-                    }
+                    // first codebook tile of the round: its maximum first (the accumulator stays in TMEM), then the scan
+                    tmem_ld32(taddr, ra);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 32, rb);
+                    float pre = slab_max32(ra);
+                    tmem_ld_wait(rb);
+                    pre = fmaxf(pre, slab_max32(rb));
                     mymax = pre;
                     thr = pre - hband;
                     atomicMax(smax, f2ord(pre));
-                    first = false;
                 }
                 thr = fmaxf(thr, ord2f(*reinterpret_cast<volatile int*>(smax)) - hband);   // what the frame's other threads have seen
-                // four slabs, the load of the next one in flight behind the scan of the current one
                 tmem_ld32(taddr, ra);
                 tmem_ld_wait(ra);
-                tmem_ld32(taddr + 32, rb);
-                if (tr) VQB_TRACE(6 + (ew != 0), 0, n_it);
-                scan_slab_q(ra, chunk0, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, qn, mine, lane);
-                tmem_ld_wait(rb);
-                tmem_ld32(taddr + 64, ra);
-                if (tr) VQB_TRACE(6 + (ew != 0), 1, n_it);
-                scan_slab_q(rb, chunk0 + 4, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, qn, mine, lane);
-                tmem_ld_wait(ra);
-                tmem_ld32(taddr + 96, rb);
-                if (tr) VQB_TRACE(6 + (ew != 0), 2, n_it);
-                scan_slab_q(ra, chunk0 + 8, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, qn, mine, lane);
+                tmem_ld32(taddr + 32, rb);        // in flight behind the scan of the first slab
+                if (tr && ew == 0) VQB_TRACE(6, 0, n_it);
+                scan_slab_sq(ra, code0, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, spill, qn, mine, lane);
+                if (tr && ew == 0) VQB_TRACE(6, 1, n_it);
                 tmem_ld_wait(rb);
                 // the last slab of this accumulator stage is in registers: hand the stage back before scanning it
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (kTwo && crank != 0) mbar_arrive_remote(smem_u32(&bars->tmem_empty[grp]), 0);   // the leader issues the pair's MMAs
-                    else mbar_arrive(smem_u32(&bars->tmem_empty[grp]));
+                    if (kTwo && crank != 0) mbar_arrive_remote(smem_u32(&bars->tmem_empty[as]), 0);   // the leader issues the pair's MMAs
+                    else mbar_arrive(smem_u32(&bars->tmem_empty[as]));
                 }
                 if (tr) VQB_TRACE(trole, 2, n_it);
-                scan_slab_q(rb, chunk0 + 12, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, qn, mine, lane);
-                if (tr) VQB_TRACE(6 + (ew != 0), 3, n_it);
+                pre_ok = mbar_test(smem_u32(&bars->tmem_full[(n_it + 1u) & 1u]), ((n_it + 1u) >> 1) & 1u);
+                scan_slab_sq(rb, code0 + 32, hband, thr, mymax, smax, q_u, (uint32_t)wq_cap, spill, qn, mine, lane);
+                if (tr && ew == 0) VQB_TRACE(6, 3, n_it);
             }
             // ---- end of the round: the four warps that share these 32 frames meet (the other lane quarters run on), every warp deals
             // ITS queue's entries one per lane and filters them against the final maximum of the frame each entry belongs to
             if (tr) VQB_TRACE(trole, 3, n_it);
-            sMin[slot4 * BM + row_in_tile] = mymax;
-            if ((!(band < INFINITY) && !first) || mine > Q_LANE_CAP) sCnt[BM + row_in_tile] = 1;   // non-finite latent / flooded: exact search
+            sMin[colq * BM + row_in_tile] = mymax;
+            if (!(band < INFINITY) || mine > SQ_LANE_CAP) sCnt[BM + row_in_tile] = 1;   // non-finite latent / flooded: exact search
             asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
             if (tr) VQB_TRACE(trole, 6, n_it);
             {
-                if (qn > (uint32_t)wq_cap) {    // queue overflow: some frame of this quarter lost an event - all 32 go to the exact search
+                if (qn > (uint32_t)wq_cap + (uint32_t)SQ_SPILL) {   // (only when no lane cap applies: unreachable with 32 lanes x SQ_LANE_CAP <= capacity)
                     sCnt[BM + row_in_tile] = 1;
-                    qn = (uint32_t)wq_cap;
+                    qn = (uint32_t)wq_cap + (uint32_t)SQ_SPILL;
                 }
-                const unsigned char* qb = sWarpQ + (size_t)ew * wq_cap * Q_ENTRY;
+                const unsigned char* qb = sWarpQ + (size_t)ew * wq_cap * SQ_ENTRY;
                 for (uint32_t e = (uint32_t)lane; e < qn; e += 32u) {
-                    const unsigned char* en = qb + (size_t)e * Q_ENTRY;
-                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 32);
+                    const bool in_sm = e < (uint32_t)wq_cap;
+                    const unsigned char* en = in_sm ? qb + (size_t)e * SQ_ENTRY : spill + (size_t)(e - (uint32_t)wq_cap) * SQ_ENTRY;
+                    const uint2 hd = *reinterpret_cast<const uint2*>(en + 128);
                     const int r = quarter * 32 + (int)(hd.y >> 16);
                     const float gmax = fmaxf(fmaxf(sMin[r], sMin[BM + r]), fmaxf(sMin[2 * BM + r], sMin[3 * BM + r]));
                     const float cutoff = gmax - 0.5f * sBand[(rd & 3) * BM + r];
                     if (__uint_as_float(hd.x) >= cutoff) {
-                        const int k0 = (int)(hd.y & 0xFFFFu) * 8;
-                        const uint4 a0 = *reinterpret_cast<const uint4*>(en), a1 = *reinterpret_cast<const uint4*>(en + 16);
-                        const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                        unsigned pm = 0;          // which of the 8 codes pass: ONE shared-memory atomic per entry, not one per code
+                        const int k0 = (int)(hd.y & 0xFFFFu);
+                        unsigned pm = 0;          // which of the 32 codes pass: ONE shared-memory atomic per entry
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) pm |= (__uint_as_float(av[j]) >= cutoff) ? (1u << j) : 0u;
+                        for (int q = 0; q < 8; ++q) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(en + 16 * q);
+                            pm |= (__uint_as_float(a.x) >= cutoff ? 1u : 0u) << (4 * q);
+                            pm |= (__uint_as_float(a.y) >= cutoff ? 2u : 0u) << (4 * q);
+                            pm |= (__uint_as_float(a.z) >= cutoff ? 4u : 0u) << (4 * q);
+                            pm |= (__uint_as_float(a.w) >= cutoff ? 8u : 0u) << (4 * q);
+                        }
                         int pos = atomicAdd(&sCnt[r], __popc(pm));
                         while (pm) {
                             const int j = __ffs((int)pm) - 1;
@@ -1243,11 +1234,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                 }
             }
-            if (slot4 == 0) *smax = f2ord(-INFINITY);     // nobody reads the pooled maximum between the two barriers
+            if (colq == 0) *smax = f2ord(-INFINITY);      // nobody reads the pooled maximum between the two barriers
             if (tr) VQB_TRACE(trole, 4, n_it);
             asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
             if (tr) VQB_TRACE(trole, 5, n_it);
-            if (slot4 == 0) {
+            if (colq == 0) {
                 if (row < N) {
                     const int cnt = sCnt[row_in_tile];
                     if (force_fallback || cnt == 0 || sCnt[BM + row_in_tile]) {
@@ -1620,6 +1611,7 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 // Shared-memory plan of one launch: cluster mode, A ring, codebook stages, shared-memory event-stack entries.
 // One function decides for the launcher AND for the callers that must know beforehand whether a variant fits
 // (tc_can_fuse, tc_fused_tail_fits).
+constexpr int kSlabQueueDefault = 0;   // 1: the slab-queue epilogue is the default for K <= 1024 (set by measurement)
 struct TcPlan {
     bool ok, two, grouped;   // grouped: grouped epilogue (wq_cap = queue entries per warp); else wq_cap = overflow-pool entries per warp
     int cs, a_slots, b_stages, ev_sm, eh_slots, wq_cap;
@@ -1683,16 +1675,16 @@ static TcPlan tc_plan(bool fuse, bool with_tail, bool dbg, int num_m_tiles, int 
         wq_bytes = (size_t)p.wq_cap * pool_entry_bytes;
     }
     if (const int v = env_get(ENV_TC_EVSM, -1); v >= 0 && v < p.ev_sm) p.ev_sm = v;   // experiments
-    // Grouped epilogue (small codebooks, K <= 1024; see scan_slab_q): per-warp chunk queues + the tile's shortlists + queue fills instead
-    // of the shared-memory part of the per-thread stacks.  About 22 events per warp and frame-tile round at K = 1024 (fewer at K = 512);
-    // a full queue sends the 32 frames of its lane quarter to the exact search.  VQB_TC_EPI=0 (experiments) keeps the per-thread stacks.
-    if (fuse && !with_tail && !dbg && K_pad > 0 && K_pad <= 1024 && env_get(ENV_TC_EPI, 0) == 1) {
+    // Slab-queue epilogue (small codebooks, K <= 1024; see scan_slab_sq): per-warp queues of raw slabs + the tile's shortlists instead of
+    // the per-thread stacks.  About 22 entries per warp and frame-tile round at K = 1024 (fewer at K = 512); what does not fit the
+    // shared-memory queue spills into the warp's global scratch.  VQB_TC_EPI=0 / 1 (experiments) forces the per-thread stacks / this form.
+    if (fuse && !with_tail && !dbg && K_pad > 0 && K_pad <= 1024 && env_get(ENV_TC_EPI, kSlabQueueDefault) == 1) {
         const size_t list_bytes = (size_t)BM * kCandMax * 2;
         const size_t base = fixed + 4 * stage_bytes + list_bytes;
         if (227 * 1024 > base) {
-            int cap = (int)((227 * 1024 - base) / ((size_t)EPI_WARPS * Q_ENTRY));
-            if (cap > 96) cap = 96;
-            if (cap >= 48) { p.grouped = true; p.wq_cap = cap; p.ev_sm = 0; wq_bytes = (size_t)EPI_WARPS * cap * Q_ENTRY + list_bytes; }
+            int cap = (int)((227 * 1024 - base) / ((size_t)EPI_WARPS * SQ_ENTRY));
+            if (cap > 48) cap = 48;
+            if (cap >= 24) { p.grouped = true; p.wq_cap = cap; p.ev_sm = 0; wq_bytes = (size_t)EPI_WARPS * cap * SQ_ENTRY + list_bytes; }
         }
     }
     const size_t fixed_ev = fixed + (size_t)p.ev_sm * ev_entry_bytes + wq_bytes;

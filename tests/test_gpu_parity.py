@@ -262,8 +262,8 @@ def test_tail3_lanes_per_frame_agree_with_the_oracle(D, lpf, experiment_env):
 def test_adversarial_code_order_floods_the_event_stacks(K, env, experiment_env):
     """Codes ordered so that a frame's score keeps improving along the codebook sweep: nearly every 8-code chunk is a new running
     maximum, the per-thread event stacks run through all their levels (own shared-memory slots, the warp's overflow pool, global
-    scratch) and many frames fall back to the exact search - the result must still be the oracle's.  Also with the grouped epilogue
-    (per-warp queues, a flooding lane must only lose itself), without the pool and without shared-memory slots."""
+    scratch) and many frames fall back to the exact search - the result must still be the oracle's.  Also with the slab-queue epilogue
+    (per-warp queues with a global spill, a flooding lane must only lose itself), without the pool and without shared-memory slots."""
     if env:
         experiment_env(**env)
     B, D, W, beta = 2, 64, 2048, 0.25
