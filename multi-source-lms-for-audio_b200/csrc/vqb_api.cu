@@ -29,7 +29,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 static const char* const kEnvNames[ENV_COUNT] = {
     "VQB_TC_MODE", "VQB_TC_CLUSTER", "VQB_TC_FUSE", "VQB_TC_STAGES", "VQB_TC_ASLOTS", "VQB_TC_EVSM", "VQB_TC_EHSLOTS", "VQB_TC_TAIL",
     "VQB_TMA_PROMO", "VQB_TILE_LDG", "VQB_RESID_REPLICAS", "VQB_L2_ONCE", "VQB_TAIL_VARIANT", "VQB_TAIL_TMA", "VQB_TAIL_EXACT",
-    "VQB_DX_TILES", "VQB_TC_EPI", "VQB_TAIL_FORM", "VQB_TAIL_LPF", "VQB_TAIL_AHEAD"};
+    "VQB_DX_TILES", "VQB_TC_EPI", "VQB_TAIL_FORM", "VQB_TAIL_LPF", "VQB_TAIL_AHEAD", "VQB_TC_SLEEP"};
 static int g_env_val[ENV_COUNT];
 static bool g_env_set[ENV_COUNT];
 static std::atomic<bool> g_env_loaded{false};

@@ -52,7 +52,7 @@ void  stage_timing_end(void* slot, cudaStream_t s);
 enum EnvKey {
     ENV_TC_MODE, ENV_TC_CLUSTER, ENV_TC_FUSE, ENV_TC_STAGES, ENV_TC_ASLOTS, ENV_TC_EVSM, ENV_TC_EHSLOTS, ENV_TC_TAIL, ENV_TMA_PROMO,
     ENV_TILE_LDG, ENV_RESID_REPLICAS, ENV_L2_ONCE, ENV_TAIL_VARIANT, ENV_TAIL_TMA, ENV_TAIL_EXACT, ENV_DX_TILES, ENV_TC_EPI, ENV_TAIL_FORM,
-    ENV_TAIL_LPF, ENV_TAIL_AHEAD,
+    ENV_TAIL_LPF, ENV_TAIL_AHEAD, ENV_TC_SLEEP,
     ENV_COUNT
 };
 int  env_get(EnvKey key, int unset_value);         // value of the switch, or unset_value when it is not set / not enabled

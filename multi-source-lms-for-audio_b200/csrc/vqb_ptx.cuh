@@ -40,6 +40,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// The same wait for roles that are far off the critical path (the TMA producer waiting for a free stage, the MMA issuer waiting for
+// the epilogue, converters waiting for a free operand slot): between two looks the warp sleeps `ns` nanoseconds.  On this part a
+// failed try_wait comes back after a few tens of cycles whatever its suspend hint says, so a waiting helper warp spins - at K = 1024,
+// D = 64 those loops were 23 % of ALL executed instructions of the search kernel (ncu), issued on the same schedulers as the
+// issue-bound epilogue warps.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (ok) return;
+        if (ns) __nanosleep(ns);
+        if ((it & 63u) == 63u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) __trap();   // seconds: only a broken pipeline gets here
+        }
+    }
+}
 // One non-blocking look at a barrier phase (acquire on success): issued EARLY, so that its latency hides behind other work and the
 // blocking wait can be skipped when the phase has long completed (a try_wait on a completed phase still costs ~270 cycles here)
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {

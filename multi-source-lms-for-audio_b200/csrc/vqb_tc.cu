@@ -579,7 +579,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  int num_kb, int a_slots, int b_stages, int cs, int K, uint8_t* __restrict__ cand_cnt,
                  uint16_t* __restrict__ cand_idx, int* __restrict__ fallback_rows, WsMeta* meta,
                  unsigned long long* __restrict__ best64, float* __restrict__ scores_dbg, uint32_t* __restrict__ ev_scratch,
-                 const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots, const int wq_cap) {
+                 const TailArgs tail, const int ev_sm, const int l2_once, const int eh_slots, const int wq_cap, const uint32_t spin_ns) {
     VQB_TRACE_INIT();
     static_assert(!kTail || kFuse, "the fused tail needs frame tiles that never straddle a batch item");
     static_assert(!kTf32 || (kFuse && !kTail), "tf32 reads the fp32 latents in place; no fused tail");
@@ -694,7 +694,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;   // may be >= num_m_tiles: dummy tile
             const int a_row = (mt < num_m_tiles ? mt : 0) * BM;               // dummy tiles re-read tile 0, nothing is published
             for (int nt = 0; nt < num_n_tiles; ++nt) {
-                mbar_wait(bar_eempty + es * 8, e_ph ^ 1);
+                mbar_wait_sleep(bar_eempty + es * 8, e_ph ^ 1, spin_ns);
                 if (elect_one()) {
                     if (kTwo) {   // own half of the bias operand; both halves complete on the leader's barrier
                         if (leader) mbar_expect_tx(bar_efull + es * 8, EH_SLICE_BYTES);
@@ -709,8 +709,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 for (int kb = 0; kb < num_kb; ++kb) {
                     uint32_t slot = a_slot0 + kb, a_phk = a_ph;          // ring position of chunk kb of this tile
                     if (slot >= (uint32_t)a_slots) { slot -= a_slots; a_phk ^= 1; }
-                    if (nt == 0 && !kFuse) mbar_wait(bar_aempty + slot * 8, a_phk ^ 1);
-                    mbar_wait(bar_bempty + b_st * 8, b_ph ^ 1);
+                    if (nt == 0 && !kFuse) mbar_wait_sleep(bar_aempty + slot * 8, a_phk ^ 1, spin_ns);
+                    mbar_wait_sleep(bar_bempty + b_st * 8, b_ph ^ 1, spin_ns);
                     if (elect_one()) {
                         if (nt == 0 && !kFuse) {
                             if (kTwo) {
@@ -756,7 +756,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int rd = 0; rd < rounds; ++rd) {
             for (int nt = 0; nt < num_n_tiles; ++nt) {
                 if (lane == 0) VQB_TRACE(1, 0, rd * num_n_tiles + nt);        // MMA: about to wait for the accumulator stage
-                mbar_wait(bar_tempty + as * 8, t_ph ^ 1);
+                mbar_wait_sleep(bar_tempty + as * 8, t_ph ^ 1, spin_ns >> 1);   // (the epilogue is waiting for what this wait gates: half the nap)
                 if (lane == 0) VQB_TRACE(1, 1, rd * num_n_tiles + nt);        // MMA: stage free
                 const uint32_t tmem_d = tmem_base + as * BN;
                 const bool last_nt = nt == num_n_tiles - 1;
@@ -857,7 +857,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             int mt = (rd * n_clusters + cluster_id) * cs + (int)crank;
             if (mt >= num_m_tiles) mt = 0;                                   // dummy tile: re-read tile 0, nothing is published
             const int b_ = mt / tiles_per_item, w0_ = (mt - b_ * tiles_per_item) * BM;
-            mbar_wait(bar_aempty + tslot * 8, t_phase ^ 1);                  // the MMAs that read this slot last are done
+            mbar_wait_sleep(bar_aempty + tslot * 8, t_phase ^ 1, spin_ns);   // the MMAs that read this slot last are done
             if (elect_one()) {
                 mbar_expect_tx(bar_land + tslot * 8, a_slot_bytes);
 #pragma unroll
@@ -880,7 +880,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const float emax = sqrtf(__uint_as_float(meta_ro->emax2_bits)) * 1.0001f;
         for (int rd = 0; rd < rounds; ++rd) {
             const uint32_t tslot = (uint32_t)rd % (uint32_t)a_slots, t_phase = ((uint32_t)rd / (uint32_t)a_slots) & 1u;
-            mbar_wait(bar_land + tslot * 8, t_phase);
+            mbar_wait_sleep(bar_land + tslot * 8, t_phase, spin_ns >> 1);
             const unsigned char* tile = sA + (size_t)tslot * a_slot_bytes;
             float s2[4] = {0.f, 0.f, 0.f, 0.f}, sd2[4] = {0.f, 0.f, 0.f, 0.f};
             for (int d = 0; d < D; ++d) {
@@ -926,7 +926,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         auto ensure_issued = [&](long long upto) {
             while (issued <= upto && issued < total_sub) {
                 const uint32_t sl_ = (uint32_t)(issued % STG_SLOTS), ph_ = (uint32_t)((issued / STG_SLOTS) & 1);
-                mbar_wait(bar_sempty + sl_ * 8, ph_ ^ 1);
+                mbar_wait_sleep(bar_sempty + sl_ * 8, ph_ ^ 1, spin_ns);
                 const int rd_ = (int)(issued / num_sub), sub_ = (int)(issued - (long long)rd_ * num_sub);
                 int mt_ = (rd_ * n_clusters + cluster_id) * cs + (int)crank;
                 if (mt_ >= num_m_tiles) mt_ = 0;                                 // dummy tile: re-read tile 0, nothing is published
@@ -949,13 +949,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 uint32_t slot = a_slot0 + kb, a_phk = a_ph;
                 if (slot >= (uint32_t)a_slots) { slot -= a_slots; a_phk ^= 1; }
                 if (is_loader) ensure_issued(g + STG_SLOTS - 1);
-                mbar_wait(bar_aempty + slot * 8, a_phk ^ 1);                     // the MMAs that read this ring slot last are done
+                mbar_wait_sleep(bar_aempty + slot * 8, a_phk ^ 1, spin_ns);      // the MMAs that read this ring slot last are done
                 unsigned char* chunk = sA + (size_t)slot * A_CHUNK_BYTES;
                 for (int q = 0; q < BK / SUB_DIMS; ++q, ++sub) {
                     if (sub < num_sub) {
                         if (is_loader) ensure_issued(g + STG_SLOTS - 1);
                         const uint32_t sg = (uint32_t)(g % STG_SLOTS), sg_ph = (uint32_t)((g / STG_SLOTS) & 1);
-                        mbar_wait(bar_sfull + sg * 8, sg_ph);
+                        mbar_wait_sleep(bar_sfull + sg * 8, sg_ph, spin_ns >> 1);
                         const float* stg = reinterpret_cast<const float*>(sStg + (size_t)sg * STG_BYTES) + r0;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {                             // two 16-byte units (8 dims) per sub-chunk
@@ -1611,6 +1611,7 @@ int make_latent_map(CUtensorMap* map, const float* z, uint64_t B, uint64_t D, ui
 // Shared-memory plan of one launch: cluster mode, A ring, codebook stages, shared-memory event-stack entries.
 // One function decides for the launcher AND for the callers that must know beforehand whether a variant fits
 // (tc_can_fuse, tc_fused_tail_fits).
+constexpr int kHelperNapNs = 0;        // default nap of waiting helper warps in ns (set by measurement)
 constexpr int kSlabQueueDefault = 0;   // 1: the slab-queue epilogue is the default for K <= 1024 (set by measurement)
 struct TcPlan {
     bool ok, two, grouped;   // grouped: grouped epilogue (wq_cap = queue entries per warp); else wq_cap = overflow-pool entries per warp
@@ -1830,10 +1831,12 @@ int launch_tc_search(const float* z_fused, int B, int64_t W, const __nv_bfloat16
     cudaError_t le;
     const TailArgs targs = with_tail ? *tail_args : TailArgs{};
     const int l2_once = (fuse && latents_read_once((size_t)N * D * 4)) ? 1 : 0;   // stream the latents past the L2-resident working set
+    // nap of the helper warps between two looks at a barrier they wait on (mbar_wait_sleep); VQB_TC_SLEEP (experiments): ns, 0 = spin
+    const uint32_t spin_ns = (uint32_t)env_get(ENV_TC_SLEEP, kHelperNapNs);
 #define VQB_TC_LAUNCH(TWO, FUSE, TAIL, ...)                                                                                                  \
     le = cudaLaunchKernelEx(&cfg, tc_search_kernel<TWO, FUSE, TAIL, ##__VA_ARGS__>, mx, me_c, meh, mxt, eh, W, tiles_per_item, D, (const WsMeta*)meta, band, N,   \
                             num_m_tiles, num_n_tiles, num_kb, a_slots, b_stages, cs, K, cand_cnt, cand_idx, fallback_rows, meta, best64,        \
-                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, ev_sm, l2_once, plan.eh_slots, plan.wq_cap)
+                            scores_dbg, reinterpret_cast<uint32_t*>(ev_scratch), targs, ev_sm, l2_once, plan.eh_slots, plan.wq_cap, spin_ns)
     if (grouped && tf32 && two) VQB_TC_LAUNCH(true, true, false, true, true);
     else if (grouped && tf32) VQB_TC_LAUNCH(false, true, false, true, true);
     else if (grouped && two) VQB_TC_LAUNCH(true, true, false, false, true);
