@@ -1022,8 +1022,13 @@ cudaError_t launch_tail(const float* z, const float* codebook, const float* e2, 
     double* part = reinterpret_cast<double*>(sse_partials);
     const size_t rep_stride = (size_t)K * D;
     int n_rep = (resid && resid_rep) ? resid_replicas(K, D) : 1;
-    const int form = env_get(ENV_TAIL_FORM, 3);     // 3 (default): tail3_kernel where it applies; 2 / 216 / 232: tail2_kernel; 0: round-1 kernels
-    if (((form == 3 && tail3_preferred(D)) || form == 300) && ep && tail_tma_enabled() && tail3_supports(D) && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
+    // 3 (default): tail3_kernel where it applies and pays; 30 / 300: tail3_kernel wherever it applies (300: red.v4 residual sums at every D);
+    // 2 / 216 / 232: tail2_kernel; 0: round-1 kernels
+    const int form = env_get(ENV_TAIL_FORM, 3);
+    // tail3_kernel's blocks run a load -> compute -> store pipeline over many tiles; with fewer than a tile or two per block (small
+    // batches: BASELINE config 1, N = 22 000) the pipeline never fills and tail2_kernel is faster (0.028 against 0.043 ms)
+    const bool enough_tiles = (int64_t)B * ((W + 31) / 32) >= 1184;
+    if (((form == 3 && tail3_preferred(D) && enough_tiles) || form == 30 || form == 300) && ep && tail_tma_enabled() && tail3_supports(D) && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
         (!q_out || (reinterpret_cast<uintptr_t>(q_out) & 15) == 0)) {
         // all n_rep residual-sum replicas live in the workspace (permuted layout); their un-permuted sum is added to `resid`
         if (resid && !resid_rep) return cudaErrorInvalidValue;

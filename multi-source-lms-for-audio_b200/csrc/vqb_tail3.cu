@@ -62,7 +62,7 @@ struct Bars { unsigned long long full[2], done[2]; };
 // registers (at most 16 dims per lane).  kAhead: the next tile's shortlists are fetched one tile ahead and |x|^2 rides along with the pair
 // scoring (chosen per shape by measurement, see launch_tail3).  kBulk: residual sums leave as one bulk reduction per frame from a per-warp staging row (needs kResid, !kRun).
 template <int J, int LPF, bool kResid, bool kRun, bool kBulk, bool kAhead>
-__global__ void __launch_bounds__(32 * ((LPF == 2 ? 2 : 4) + 1), (32 * J / LPF >= 24) ? 3 : ((32 * J / LPF >= 12) ? 4 : 5))
+__global__ void __launch_bounds__(32 * ((LPF == 2 ? 2 : 4) + 1), (32 * J / LPF >= 24) ? 3 : ((32 * J / LPF >= 12) ? (LPF <= 4 ? 5 : 4) : 6))
 tail3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_q, const float* __restrict__ Ep,
              const float* __restrict__ e2, int64_t W, int tiles_per_item, int num_tiles, const int* __restrict__ idx32,
              const uint8_t* __restrict__ cand_cnt, const uint16_t* __restrict__ cand_idx, int64_t* __restrict__ idx_out, int has_q,
@@ -296,18 +296,31 @@ tail3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__
                     if (foldx2) score_fold(r, act, fi, kc, ev, e2c);
                     else score_plain(r, act, fi, kc, ev, e2c);
                 };
-                // rounds are software-pipelined two deep (ping-pong registers)
-                float4 eva[T], evb[T];
-                float e2a = 0.f, e2b = 0.f;
-                int fia = 0, kca = 0, fib = 0, kcb = 0;
-                bool acta = pair_of(0, fia, kca), actb = false;
-                fetch_row(kca, eva, e2a);
-                for (int r = 0; r < rounds; r += 2) {
-                    if (r + 1 < rounds) { actb = pair_of(r + 1, fib, kcb); fetch_row(kcb, evb, e2b); }
-                    score(r, acta, fia, kca, eva, e2a);
-                    if (r + 1 < rounds) {
-                        if (r + 2 < rounds) { acta = pair_of(r + 2, fia, kca); fetch_row(kca, eva, e2a); }
-                        score(r + 1, actb, fib, kcb, evb, e2b);
+                if (G >= 8) {
+                    // 8 or 16 pairs per round: a warp's frames rarely need more than one round, and the second row buffer of the
+                    // pipelined form below costs the registers of a fifth block per SM
+                    for (int r = 0; r < rounds; ++r) {
+                        float4 ev[T];
+                        float e2c;
+                        int fi, kc;
+                        const bool act = pair_of(r, fi, kc);
+                        fetch_row(kc, ev, e2c);
+                        score(r, act, fi, kc, ev, e2c);
+                    }
+                } else {
+                    // rounds are software-pipelined two deep (ping-pong registers)
+                    float4 eva[T], evb[T];
+                    float e2a = 0.f, e2b = 0.f;
+                    int fia = 0, kca = 0, fib = 0, kcb = 0;
+                    bool acta = pair_of(0, fia, kca), actb = false;
+                    fetch_row(kca, eva, e2a);
+                    for (int r = 0; r < rounds; r += 2) {
+                        if (r + 1 < rounds) { actb = pair_of(r + 1, fib, kcb); fetch_row(kcb, evb, e2b); }
+                        score(r, acta, fia, kca, eva, e2a);
+                        if (r + 1 < rounds) {
+                            if (r + 2 < rounds) { acta = pair_of(r + 2, fia, kca); fetch_row(kca, eva, e2a); }
+                            score(r + 1, actb, fib, kcb, evb, e2b);
+                        }
                     }
                 }
             }

@@ -154,9 +154,15 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("tail_form", [None, "30"])
 @pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("B,D,W,K,cb_scale,z_scale", CASES)
-def test_oracle_parity(B, D, W, K, cb_scale, z_scale, precision):
+def test_oracle_parity(B, D, W, K, cb_scale, z_scale, precision, tail_form, experiment_env):
+    """tail_form "30": tail3_kernel wherever the shape allows it (by default small batches take tail2_kernel: too few tiles per block)."""
+    if tail_form:
+        if precision == "fp32" and D > 256:
+            pytest.skip("same kernels as the default run")
+        experiment_env(VQB_TAIL_FORM=tail_form)
     z = seeded(100 + D + K, (B, D, W), z_scale)
     if cb_scale is None:
         cb = np.random.default_rng(5).uniform(-1 / K, 1 / K, (K, D)).astype(np.float32)
@@ -203,7 +209,7 @@ def test_fused_tail_variant_matches_oracle(B, D, W, K, cb_scale, experiment_env)
 
 
 @pytest.mark.parametrize("env", [{"VQB_TAIL_TMA": "0"}, {"VQB_TAIL_FORM": "0"}, {"VQB_TAIL_FORM": "0", "VQB_TAIL_VARIANT": "0"},
-                                 {"VQB_TAIL_FORM": "2"}, {"VQB_TAIL_FORM": "216"}, {"VQB_TAIL_FORM": "300"}, {"VQB_TC_EPI": "1"}, {"VQB_RESID_REPLICAS": "1"},
+                                 {"VQB_TAIL_FORM": "2"}, {"VQB_TAIL_FORM": "216"}, {"VQB_TAIL_FORM": "30"}, {"VQB_TAIL_FORM": "300"}, {"VQB_TC_EPI": "1"}, {"VQB_RESID_REPLICAS": "1"},
                                  {"VQB_RESID_REPLICAS": "8"}, {"VQB_DX_TILES": "1"}, {"VQB_TC_ASLOTS": "6"},
                                  {"VQB_L2_ONCE": "1"}, {"VQB_TC_EHSLOTS": "5"}, {"VQB_TC_MODE": "1"}])
 def test_kernel_variants_agree_with_the_default_path(env, experiment_env):
@@ -239,7 +245,7 @@ def test_tail3_lanes_per_frame_agree_with_the_oracle(D, lpf, experiment_env):
     """tail3_kernel reads the swizzled latent box in place with 8, 4 or 2 lanes per frame (the permutation of the codebook copy and
     of the residual replicas follows): every choice must give the oracle's indices, `quantized`, losses and gradients.  W is not a
     multiple of the 32-frame tile, so the last tile of every item is ragged."""
-    experiment_env(VQB_TAIL_LPF=str(lpf))
+    experiment_env(VQB_TAIL_LPF=str(lpf), VQB_TAIL_FORM="30")
     B, W, K, beta = 3, 1100, 300, 0.25
     cb = seeded(21, (K, D))
     z = seeded(22, (B, D, W))
