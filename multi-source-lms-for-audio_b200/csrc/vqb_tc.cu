@@ -1358,7 +1358,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             sMin[colq * BM + row_in_tile] = thr + hband;                     // running maximum of this column quarter
             const int tbuf = rd & 1;
             if (kTail) mbar_wait(smem_u32(&tbars->tail_empty[tbuf]), ((rd >> 1) & 1) ^ 1);   // the tail is done with the tile before last
-            asm volatile("bar.sync 1, 512;" ::: "memory");
+            // the 128 threads that share these 32 frames (four column quarters of one TMEM lane quarter) meet; the other lane quarters
+            // run on - a 512-thread barrier here made every round wait for the slowest of 16 warps (timeline: 700 + 900 cycles of 8 300 at K = 512)
+            asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
             if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 6, n_it);   // epilogue: past the first barrier
             if (row < N && !scores_dbg) {
                 const float gmax = fmaxf(fmaxf(sMin[row_in_tile], sMin[BM + row_in_tile]),
@@ -1474,7 +1476,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             if (colq == 0) *smax = f2ord(-INFINITY);       // nobody reads the pooled maximum between the two barriers
             if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 4, n_it);   // epilogue: own stack resolved
-            asm volatile("bar.sync 2, 512;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(4 + quarter) : "memory");
             if (lane == 0 && (ew == 0 || ew == 13)) VQB_TRACE(4 + (ew != 0), 5, n_it);   // epilogue: past the second barrier
             if (colq == 0) {
                 int tcnt = 0;                                    // what the tail warps get: 0 = frame is not theirs
