@@ -147,6 +147,10 @@ VQB_API long long vqb_debug_launch_count(int reset);
 /* The experiment switches of DESIGN.md section 8 (VQB_* environment variables) are read once and honoured only when
  * VQB_EXPERIMENTS=1 is set; this re-reads them (tests flip them inside one process). */
 VQB_API int vqb_debug_reload_env(void);
+/* Layout contract of tail3_kernel (host-only, no device needed): the lanes-per-frame it uses at this D, and the position inside a
+ * permuted codebook / residual row that holds dim d for a given lanes-per-frame (negative: bad arguments). */
+VQB_API int vqb_debug_tail3_lanes(int D);
+VQB_API int vqb_debug_tail3_perm_pos(int d, int lanes_per_frame);
 /* CUDA-event timing of the stages of vqb_forward on its launching stream: enable, run, then read the summed duration and
  * launch count of a stage (bench.py's roofline leg).  At most 2048 stage launches are recorded per enable.
  * vqb_debug_kernel_time_ms reads VQB_STAGE_SEARCH, the dominant kernel (tc_search_kernel). */

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "vqb_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "vqb_debug_launch_count": (C.c_longlong, [C.c_int]),
     "vqb_debug_reload_env": (C.c_int, []),
+    "vqb_debug_tail3_lanes": (C.c_int, [C.c_int]),
+    "vqb_debug_tail3_perm_pos": (C.c_int, [C.c_int, C.c_int]),
     "vqb_debug_kernel_timing": (C.c_int, [C.c_int]),
     "vqb_debug_kernel_time_ms": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "vqb_debug_stage_time_ms": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),

@@ -360,6 +360,12 @@ int vqb_debug_reload_env(void) {
     return 0;
 }
 
+int vqb_debug_tail3_lanes(int D) { return (D >= 32 && D % 32 == 0) ? tail3_lpf(D) : VQB_E_SHAPE; }
+int vqb_debug_tail3_perm_pos(int d, int lanes_per_frame) {
+    if (d < 0 || (lanes_per_frame != 2 && lanes_per_frame != 4 && lanes_per_frame != 8)) return VQB_E_SHAPE;
+    return tail3_perm_pos(d, lanes_per_frame);
+}
+
 int vqb_debug_counters(const void* workspace, int64_t* counters_out_host) {
     if (!workspace || !counters_out_host) { set_error("vqb_debug_counters: NULL pointer argument"); return VQB_E_NULL; }
     WsMeta m;

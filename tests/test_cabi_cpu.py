@@ -107,3 +107,28 @@ def test_exact_workspace_drops_the_bf16_latent_copy():
     assert ragged <= F.workspace_bytes(4 * 333, 512, 64, _lib.PREC_BF16)
     tiny = F.workspace_bytes_bw(1, 64, 256, 512, _lib.PREC_BF16)             # two frame tiles: event scratch for two CTAs only
     assert tiny < (4 << 20), tiny
+
+
+def test_tail3_permutation_is_the_layout_its_kernel_reads():
+    """tail3_kernel gathers from a permuted copy of the codebook (and accumulates the residual sums in the same order): inside a row,
+    lane sl of a frame's lpf lanes owns the dims whose d % 8 lies in [S sl, S sl + S), S = 8 / lpf, and its m-th dim sits at
+    (m / 4) * 4 lpf + 4 sl + m % 4.  Host-only check of the C++ function codebook_prep_kernel and fold_resid_perm_kernel share:
+    a bijection of [0, D), every aligned group of four positions belongs to ONE lane, and for a fixed float4 index the lanes of a
+    frame are 16 bytes apart (one contiguous line of 16 lpf bytes)."""
+    lib = _lib.lib()
+    for D in (32, 64, 96, 128, 192, 256):
+        assert lib.vqb_debug_tail3_lanes(D) in (4, 8)
+        for lpf in (2, 4, 8):
+            if D // lpf > 32 or (D // lpf) % 4:
+                continue
+            S = 8 // lpf
+            pos = [lib.vqb_debug_tail3_perm_pos(d, lpf) for d in range(D)]
+            assert sorted(pos) == list(range(D))
+            owner = {p: (d % 8) // S for d, p in enumerate(pos)}
+            for p0 in range(0, D, 4):
+                assert len({owner[p0 + j] for j in range(4)}) == 1
+                assert owner[p0] == (p0 // 4) % lpf                      # lanes interleave float4 by float4
+            for d, p in enumerate(pos):                                  # the closed form of the header comment
+                sl, m = (d % 8) // S, (d // 8) * S + (d % 8) % S
+                assert p == (m // 4) * 4 * lpf + 4 * sl + m % 4
+    assert lib.vqb_debug_tail3_perm_pos(-1, 8) < 0 and lib.vqb_debug_tail3_perm_pos(3, 3) < 0 and lib.vqb_debug_tail3_lanes(48) < 0
