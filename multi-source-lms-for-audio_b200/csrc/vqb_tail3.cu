@@ -152,8 +152,6 @@ tail3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__
             }
         };
         float2* pr = pairres + warp * (FW * kPairMax);
-        // shortlist length (lane u < FW holds frame fbase + u) and shortlist (two lanes per frame) of a tile: fetched ONE TILE AHEAD into
-        // registers - at the top of a tile these loads were the longest single stall of the pass (12.8 % of the samples)
         // (batch item, tile inside the item) of this warp's current tile, advanced by the grid stride without a division per tile
         // (three divisions per tile were 8 % of the instructions at D = 64)
         const int qs = tstep / tiles_per_item, rs = tstep - qs * tiles_per_item;
@@ -163,6 +161,8 @@ tail3_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__
             t_ += rs;
             if (t_ >= tiles_per_item) { t_ -= tiles_per_item; ++b_; }
         };
+        // shortlist length (lane u < FW holds frame fbase + u) and shortlist (two lanes per frame) of a tile, into registers; with kAhead
+        // they are fetched ONE TILE AHEAD (at the top of a tile these loads were the longest single stall of the pass at D = 256)
         auto fetch_lists = [&](int tile, int b, int t_in, int& cnt, uint4& v) {
             cnt = 0;
             v = make_uint4(0u, 0u, 0u, 0u);
